@@ -1,0 +1,198 @@
+/* loamlivox_b200.h — C-ABI of the B200-native scan-to-map registration hot path of hku-mars/loam_livox.
+ *
+ * Plain C, POD structs, caller-owned memory, opaque handles, int status (0 = OK, <0 = error, never throws).
+ * No global state; distinct ll_ctx objects may be used from distinct threads concurrently (one CUDA stream each),
+ * which is how the reference calls the path (one Point_cloud_registration per std::async worker,
+ * /root/reference/source/laser_mapping.hpp:1348,1737-1742).
+ *
+ * The reference has no plugin/FFI layer; the boundary is the three C++ call seams SURVEY.md §8(b) lists.
+ * Each entry point below names the reference call it replaces.  Quaternions are (w,x,y,z) unless noted.
+ */
+#ifndef LOAMLIVOX_B200_H
+#define LOAMLIVOX_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- point formats -------------------------------------------------------------------------------- */
+typedef struct { float x, y, z, intensity; } ll_point;                   /* 16 B, the device format     */
+typedef struct { float x, y, z, _pad0, intensity, _pad1, _pad2, _pad3; } ll_pcl_xyzi; /* == pcl::PointXYZI (32 B),
+                                               the reference's PointType: /root/reference/include/tools/common.h:9 */
+enum { LL_FMT_XYZI16 = 0, LL_FMT_PCL32 = 1 };
+enum { LL_HOST = 0, LL_DEVICE = 1 };           /* where an input pointer lives                           */
+
+/* ---- status codes --------------------------------------------------------------------------------- */
+enum {
+  LL_OK = 0,
+  LL_ERR_INVALID = -1,    /* bad argument                                                              */
+  LL_ERR_CUDA = -2,       /* CUDA runtime error (ll_last_error has the text)                           */
+  LL_ERR_CAPACITY = -3,   /* input larger than the context was created for                             */
+  LL_ERR_NO_BLOCKS = -4,  /* no residual block survived the gates (reference would dereference an empty
+                             std::set at point_cloud_registration.hpp:160)                              */
+  LL_ERR_CAP_BINDS = -5   /* maximum_allow_residual_block would bind: the reference then drops blocks with a
+                             std::random_device RNG (:232-238,:438-458); not reproducible, not implemented */
+};
+
+/* ---- pt_type / pt_label bit masks (livox_feature_extractor.hpp:82-103) --------------------------- */
+enum { LL_PT_NORMAL = 0, LL_PT_000 = 1, LL_PT_TOO_NEAR = 2, LL_PT_REFLECTIVITY_LOW = 4, LL_PT_REFLECTIVITY_HIGH = 8,
+       LL_PT_CIRCLE_EDGE = 16, LL_PT_NAN = 32, LL_PT_SMALL_VIEW_ANGLE = 64 };
+enum { LL_LABEL_INVALID = -1, LL_LABEL_UNLABELED = 0, LL_LABEL_CORNER = 1, LL_LABEL_SURFACE = 2, LL_LABEL_NEAR_NAN = 4,
+       LL_LABEL_NEAR_ZERO = 8 };
+
+typedef struct ll_ctx ll_ctx;
+typedef struct ll_map ll_map;
+
+/* Context configuration.  The extractor fields are the ones Laser_feature writes into Livox_laser
+ * (laser_feature_extractor.hpp:152-154,854,859); capacities size the device arenas once. */
+typedef struct {
+  float corner_curvature;     /* feature_extraction/corner_curvature   (YAML 0.1)   */
+  float surface_curvature;    /* feature_extraction/surface_curvature  (YAML 0.005) */
+  float minimum_view_angle;   /* feature_extraction/minimum_view_angle (YAML 5)     */
+  float livox_min_dis;        /* feature_extraction/livox_min_dis      (0.1)        */
+  float livox_min_sigma;      /* feature_extraction/livox_min_sigma    (7e-4)       */
+  float max_fov_deg;          /* Livox_laser::max_fov (17)                          */
+  float time_interval_pts;    /* Livox_laser::m_time_internal_pts (1e-5)            */
+  int   max_scan_points;      /* capacity: raw points per scan                      */
+  int   max_features;         /* capacity: corner + surface features per registration */
+} ll_config;
+void ll_config_default(ll_config* cfg);
+
+int  ll_ctx_create(const ll_config* cfg, int device, ll_ctx** out);
+void ll_ctx_destroy(ll_ctx* ctx);
+const char* ll_last_error(const ll_ctx* ctx);
+/* CUDA stream of the context as a cudaStream_t cast to void* (all work of a context is enqueued on it). */
+void* ll_ctx_stream(ll_ctx* ctx);
+int  ll_ctx_sync(ll_ctx* ctx);
+
+/* ---- S1: feature extraction ------------------------------------------------------------------------ */
+/* Replaces Livox_laser::extract_laser_features (livox_feature_extractor.hpp:722-766; projection_scan_3d_2d
+ * :458-607, compute_features :361-455, split_laser_scan :657-719).  `raw` is one sensor frame in scan order.
+ * *n_scans receives laserCloudScans.size() (the caller drops the frame when it is <= 5,
+ * laser_feature_extractor.hpp:287).  Per-scan state stays on the device for ll_get_features. */
+int ll_extract(ll_ctx* ctx, const void* raw, size_t n, int fmt, int where, double stamp, int* n_scans);
+/* Piece bounds of laser_feature_extractor.hpp:313-323 (fraction of the frame covered by each piece). */
+int ll_piece_bounds(ll_ctx* ctx, int pieces, float* start, float* end);
+/* Replaces Livox_laser::get_features (livox_feature_extractor.hpp:219-272).  Host outputs, each sized n. */
+int ll_get_features(ll_ctx* ctx, float minimum_blur, float maximum_blur, ll_point* corners, size_t* n_corners,
+                    ll_point* surface, size_t* n_surface, ll_point* full, size_t* n_full);
+/* Debug/parity view of the per-point state (Pt_infos, livox_feature_extractor.hpp:118-133); any pointer may be NULL. */
+int ll_extract_point_info(ll_ctx* ctx, int32_t* pt_type, int32_t* pt_label, float* curvature, float* view_angle,
+                          float* depth_sq2, float* time_stamp, float* polar_dis_sq2, int32_t* polar_direction);
+int ll_extract_split_idx(ll_ctx* ctx, int32_t* out, int cap, int* n_out);
+
+/* ---- a5: voxel-grid down-sampling ------------------------------------------------------------------ */
+/* Replaces pcl::VoxelGrid<PointXYZI>::filter at laser_feature_extractor.hpp:372-380 and
+ * laser_mapping.hpp:491,509,533-537,1367-1373,1434-1437.  `out` must hold n points. */
+int ll_voxel_downsample(ll_ctx* ctx, const void* in, size_t n, int fmt, int where, float leaf, ll_point* out, size_t* n_out);
+
+/* ---- S2: map snapshot + index ---------------------------------------------------------------------- */
+/* Replaces pcl::KdTreeFLANN::setInputCloud x2 in Laser_mapping::update_buff_for_matching
+ * (laser_mapping.hpp:544-545) and in the 4-argument registration overload (point_cloud_registration.hpp:596-597).
+ * The two world-frame clouds are copied to HBM and indexed; the handle is immutable and may be shared. */
+int  ll_map_build(ll_ctx* ctx, const void* corner, size_t n_corner, const void* surf, size_t n_surf, int fmt, int where, ll_map** out);
+void ll_map_release(ll_map* map);
+size_t ll_map_size(const ll_map* map, int which /*0 corner, 1 surface*/);
+/* Multi-GPU: keep only the points whose cell (cell_size metres) is owned by `rank` of `world`, plus a halo of
+ * sqrt(max_dis_line) / sqrt(max_dis_plane) metres.  ll_register then only emits residual
+ * blocks for the queries whose cell this rank owns and all-reduces the normal equations (ll_comm_*). */
+int  ll_map_build_sharded(ll_ctx* ctx, const void* corner, size_t n_corner, const void* surf, size_t n_surf, int fmt, int where,
+                          int rank, int world, float cell_size, float halo_corner, float halo_surf, ll_map** out);
+
+/* Parity hook for pcl::KdTreeFLANN::nearestKSearch(k = 5) (point_cloud_registration.hpp:249,351): world-frame
+ * queries in, 5 indices (into the cloud given to ll_map_build, -1 when fewer exist) and float squared distances out. */
+int ll_knn(ll_ctx* ctx, const ll_map* map, int which, const ll_point* queries, size_t nq, int32_t* idx5, float* sqdist5);
+
+/* ---- S3: registration ------------------------------------------------------------------------------ */
+/* Inputs of Point_cloud_registration: exactly what Laser_mapping::init_pointcloud_registration copies
+ * (laser_mapping.hpp:1266-1297) plus the members Scene_alignment pokes (scene_alignment.hpp:233-243,292-306). */
+typedef struct {
+  int    if_motion_deblur;                /* m_if_motion_deblur                                        */
+  int    current_frame_index;             /* m_current_frame_index                                     */
+  int    mapping_init_accumulate_frames;  /* m_mapping_init_accumulate_frames                          */
+  int    icp_max_iterations;              /* m_para_icp_max_iterations                                 */
+  int    cere_max_iterations;             /* m_para_cere_max_iterations                                */
+  int    cere_prerun_times;               /* m_para_cere_prerun_times (2)                              */
+  int    icp_plane, icp_line;             /* ICP_PLANE, ICP_LINE                                       */
+  int    maximum_allow_residual_block;    /* m_maximum_allow_residual_block                            */
+  int    _reserved;
+  double para_max_angular_rate;           /* m_para_max_angular_rate (deg, reject gate)                */
+  double para_max_speed;                  /* m_para_max_speed (bound on |t_incre[j]|)                  */
+  double max_final_cost;                  /* m_max_final_cost                                          */
+  double minimum_pt_time_stamp, maximum_pt_time_stamp;
+  double minimum_icp_R_diff, minimum_icp_T_diff;
+  double inliner_dis, inlier_ratio;       /* m_inliner_dis (0.02), m_inlier_ratio (0.80)               */
+  double maximum_dis_plane_for_match;     /* 50.0, compared with a SQUARED distance (:353)             */
+  double maximum_dis_line_for_match;      /* 2.0,  compared with a SQUARED distance (:254)             */
+  double huber_a;                         /* ceres::HuberLoss(0.1) (:220)                              */
+  double q_w_last[4], t_w_last[3];        /* m_q_w_last, m_t_w_last                                    */
+  double q_w_curr[4], t_w_curr[3];        /* m_q_w_curr, m_t_w_curr                                    */
+  double para_buffer_incremental[7];      /* m_para_buffer_incremental: q (x,y,z,w) then t             */
+} ll_reg_state;
+void ll_reg_state_default(ll_reg_state* s);   /* performance_precision.yaml + launch/rosbag.launch values */
+
+typedef struct {
+  int    status;                 /* return value of find_out_incremental_transfrom: 1 accepted or skipped, 0 rejected */
+  int    registered;             /* 1 when the ICP branch ran (:199)                                    */
+  int    num_residual_blocks;    /* summary.num_residual_blocks of the last solve                       */
+  int    icp_iterations, corner_used, surf_used;
+  int    total_lm_iterations, total_evaluations;
+  double q_w_curr[4], t_w_curr[3];   /* m_q_w_curr, m_t_w_curr                                          */
+  double q_w_incre[4], t_w_incre[3]; /* m_q_w_incre (w,x,y,z), m_t_w_incre                              */
+  double inlier_threshold;       /* m_inlier_threshold after the final/initial cost rescale (:559)      */
+  double final_cost, initial_cost;
+  double angular_diff, t_diff;   /* m_angular_diff (deg), m_t_diff                                      */
+  float  gpu_ms_total, gpu_ms_knn;  /* CUDA-event timings of this call (0 when timing is disabled)      */
+} ll_reg_result;
+
+/* Replaces Point_cloud_registration::find_out_incremental_transfrom (point_cloud_registration.hpp:163-583):
+ * ICP outer loop; per iteration pointAssociateToMap + 5-NN of every feature (:230-432), gates, residual blocks,
+ * Solve #1 (2 iterations), inlier selection (:476-499), Solve #2, pose composition, termination (:514-531), reject
+ * gate (:561-573).  Returns LL_OK and fills `out` (out->status carries the reference's 0/1); <0 on error. */
+int ll_register(ll_ctx* ctx, const ll_map* map, const void* scan_corner, size_t n_corner, const void* scan_surf, size_t n_surf,
+                int fmt, int where, const ll_reg_state* in, ll_reg_result* out);
+
+/* Step-by-step parity hooks (tests): one ICP iteration's residual blocks at the pose in `in`
+ * (type 0 invalid / 1 line / 2 plane, a[3], v[3] per slot; slots = corner features then surface features) ... */
+int ll_build_blocks(ll_ctx* ctx, const ll_map* map, const void* scan_corner, size_t n_corner, const void* scan_surf, size_t n_surf,
+                    int fmt, int where, const ll_reg_state* in, int32_t* type, double* a3, double* v3, int* corner_avail, int* surf_avail);
+/* ... and the loss-corrected normal equations at x (q x,y,z,w ; t): out28 = 21 upper-triangular JtJ (row-major), 6 Jtr, cost. */
+int ll_normal_equations(ll_ctx* ctx, const double x[7], double out28[28]);
+/* ... and one ceres::Solve-equivalent on the blocks currently resident (max_iterations as in Solver::Options). */
+int ll_solve(ll_ctx* ctx, int max_iterations, double x_io[7], double* initial_cost, double* final_cost, int* iterations);
+
+/* ---- a7: pointAssociateToMap over a cloud ----------------------------------------------------------- */
+/* Replaces Point_cloud_registration::pointcloudAssociateToMap (point_cloud_registration.hpp:673-685, non-deblur
+ * branch of :622-661): p_w = q*p + t in fp64, stored as fp32, intensity passed through. */
+int ll_transform(ll_ctx* ctx, const double q_wxyz[4], const double t[3], const void* in, size_t n, int fmt, int where, ll_point* out);
+
+/* ---- whole per-scan step (what Laser_feature::laserCloudHandler + Laser_mapping::process_new_scan do) ------ */
+typedef struct {
+  int   pieces;               /* common/piecewise_number; only piece 0 is registered (odom_mode 0, :385)    */
+  int   use_piece;            /* which piece's features to register (0)                                      */
+  float extractor_leaf_corner;/* laser_feature_extractor.hpp:193 (line_res)                                  */
+  float extractor_leaf_surf;  /* laser_feature_extractor.hpp:192 (plane_res / 2)                             */
+  float mapping_leaf_corner;  /* laser_mapping.hpp:1367-1373 (line_res)                                      */
+  float mapping_leaf_surf;    /* (plane_res)                                                                 */
+  int   whole_frame;          /* 1: ignore pieces, use min_blur = 0, max_blur = 1                            */
+} ll_pipeline_cfg;
+/* raw scan -> features -> VoxelGrid x2 -> registration against `map`, without leaving the device. */
+int ll_scan_to_pose(ll_ctx* ctx, const ll_map* map, const void* raw, size_t n, int fmt, int where, double stamp,
+                    const ll_pipeline_cfg* pc, const ll_reg_state* in, ll_reg_result* out, int* n_corner_used, int* n_surf_used);
+
+/* ---- multi-GPU ------------------------------------------------------------------------------------- */
+/* One process per GPU.  The 28-double normal equations (+4 counters) are all-reduced inside the solver kernel
+ * through peer-mapped staging buffers (CUDA IPC over NVLink); the host only exchanges the IPC handles once. */
+#define LL_IPC_HANDLE_BYTES 64
+int ll_comm_local_handle(ll_ctx* ctx, unsigned char handle[LL_IPC_HANDLE_BYTES]);
+int ll_comm_connect(ll_ctx* ctx, int rank, int world, const unsigned char* all_handles /* world x LL_IPC_HANDLE_BYTES */);
+
+/* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
+uint64_t ll_launch_count(const ll_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOAMLIVOX_B200_H */

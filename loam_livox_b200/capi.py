@@ -1,0 +1,137 @@
+"""ctypes binding of libloamlivox_b200.so (include/loamlivox_b200.h).
+
+The CUDA library is the product: importing this module without the shared object, or creating a context without a
+B200-class GPU, fails loudly — there is no CPU or PyTorch fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libloamlivox_b200.so")
+
+LL_FMT_XYZI16, LL_FMT_PCL32 = 0, 1
+LL_HOST, LL_DEVICE = 0, 1
+LL_OK, LL_ERR_INVALID, LL_ERR_CUDA, LL_ERR_CAPACITY, LL_ERR_NO_BLOCKS, LL_ERR_CAP_BINDS = 0, -1, -2, -3, -4, -5
+LL_IPC_HANDLE_BYTES = 64
+
+EXPORTS = [
+    "ll_config_default", "ll_ctx_create", "ll_ctx_destroy", "ll_last_error", "ll_ctx_stream", "ll_ctx_sync", "ll_extract", "ll_piece_bounds",
+    "ll_get_features", "ll_extract_point_info", "ll_extract_split_idx", "ll_voxel_downsample", "ll_map_build", "ll_map_release", "ll_map_size",
+    "ll_map_build_sharded", "ll_knn", "ll_reg_state_default", "ll_register", "ll_build_blocks", "ll_normal_equations", "ll_solve", "ll_transform",
+    "ll_scan_to_pose", "ll_comm_local_handle", "ll_comm_connect", "ll_launch_count",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("corner_curvature", C.c_float), ("surface_curvature", C.c_float), ("minimum_view_angle", C.c_float), ("livox_min_dis", C.c_float),
+                ("livox_min_sigma", C.c_float), ("max_fov_deg", C.c_float), ("time_interval_pts", C.c_float), ("max_scan_points", C.c_int), ("max_features", C.c_int)]
+
+
+class RegState(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("if_motion_deblur", "current_frame_index", "mapping_init_accumulate_frames", "icp_max_iterations", "cere_max_iterations",
+                                       "cere_prerun_times", "icp_plane", "icp_line", "maximum_allow_residual_block", "_reserved")] + \
+               [(n, C.c_double) for n in ("para_max_angular_rate", "para_max_speed", "max_final_cost", "minimum_pt_time_stamp", "maximum_pt_time_stamp",
+                                          "minimum_icp_R_diff", "minimum_icp_T_diff", "inliner_dis", "inlier_ratio", "maximum_dis_plane_for_match",
+                                          "maximum_dis_line_for_match", "huber_a")] + \
+               [("q_w_last", C.c_double * 4), ("t_w_last", C.c_double * 3), ("q_w_curr", C.c_double * 4), ("t_w_curr", C.c_double * 3),
+                ("para_buffer_incremental", C.c_double * 7)]
+
+
+class RegResult(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("status", "registered", "num_residual_blocks", "icp_iterations", "corner_used", "surf_used", "total_lm_iterations",
+                                       "total_evaluations")] + \
+               [("q_w_curr", C.c_double * 4), ("t_w_curr", C.c_double * 3), ("q_w_incre", C.c_double * 4), ("t_w_incre", C.c_double * 3)] + \
+               [(n, C.c_double) for n in ("inlier_threshold", "final_cost", "initial_cost", "angular_diff", "t_diff")] + \
+               [("gpu_ms_total", C.c_float), ("gpu_ms_knn", C.c_float)]
+
+
+class PipelineCfg(C.Structure):
+    _fields_ = [("pieces", C.c_int), ("use_piece", C.c_int), ("extractor_leaf_corner", C.c_float), ("extractor_leaf_surf", C.c_float),
+                ("mapping_leaf_corner", C.c_float), ("mapping_leaf_surf", C.c_float), ("whole_frame", C.c_int)]
+
+
+class LoamLivoxError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise LoamLivoxError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                             "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, ci, cf, cd = C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_double
+    L.ll_config_default.argtypes = [C.POINTER(Config)]
+    L.ll_ctx_create.argtypes = [C.POINTER(Config), ci, C.POINTER(vp)]
+    L.ll_ctx_destroy.argtypes = [vp]
+    L.ll_last_error.argtypes = [vp]
+    L.ll_last_error.restype = C.c_char_p
+    L.ll_ctx_stream.argtypes = [vp]
+    L.ll_ctx_stream.restype = vp
+    L.ll_ctx_sync.argtypes = [vp]
+    L.ll_extract.argtypes = [vp, vp, sz, ci, ci, cd, C.POINTER(ci)]
+    L.ll_piece_bounds.argtypes = [vp, ci, vp, vp]
+    L.ll_get_features.argtypes = [vp, cf, cf, vp, C.POINTER(sz), vp, C.POINTER(sz), vp, C.POINTER(sz)]
+    L.ll_extract_point_info.argtypes = [vp] + [vp] * 8
+    L.ll_extract_split_idx.argtypes = [vp, vp, ci, C.POINTER(ci)]
+    L.ll_voxel_downsample.argtypes = [vp, vp, sz, ci, ci, cf, vp, C.POINTER(sz)]
+    L.ll_map_build.argtypes = [vp, vp, sz, vp, sz, ci, ci, C.POINTER(vp)]
+    L.ll_map_build_sharded.argtypes = [vp, vp, sz, vp, sz, ci, ci, ci, ci, cf, cf, cf, C.POINTER(vp)]
+    L.ll_map_release.argtypes = [vp]
+    L.ll_map_size.argtypes = [vp, ci]
+    L.ll_map_size.restype = sz
+    L.ll_knn.argtypes = [vp, vp, ci, vp, sz, vp, vp]
+    L.ll_reg_state_default.argtypes = [C.POINTER(RegState)]
+    L.ll_register.argtypes = [vp, vp, vp, sz, vp, sz, ci, ci, C.POINTER(RegState), C.POINTER(RegResult)]
+    L.ll_build_blocks.argtypes = [vp, vp, vp, sz, vp, sz, ci, ci, C.POINTER(RegState), vp, vp, vp, C.POINTER(ci), C.POINTER(ci)]
+    L.ll_normal_equations.argtypes = [vp, vp, vp]
+    L.ll_solve.argtypes = [vp, ci, vp, C.POINTER(cd), C.POINTER(cd), C.POINTER(ci)]
+    L.ll_transform.argtypes = [vp, vp, vp, vp, sz, ci, ci, vp]
+    L.ll_scan_to_pose.argtypes = [vp, vp, vp, sz, ci, ci, cd, C.POINTER(PipelineCfg), C.POINTER(RegState), C.POINTER(RegResult), C.POINTER(ci), C.POINTER(ci)]
+    L.ll_comm_local_handle.argtypes = [vp, vp]
+    L.ll_comm_connect.argtypes = [vp, ci, ci, vp]
+    L.ll_launch_count.argtypes = [vp]
+    L.ll_launch_count.restype = C.c_uint64
+    _LIB = L
+    return L
+
+
+def default_config(**kw) -> Config:
+    c = Config()
+    lib().ll_config_default(C.byref(c))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def default_reg_state(**kw) -> RegState:
+    s = RegState()
+    lib().ll_reg_state_default(C.byref(s))
+    for k, v in kw.items():
+        if isinstance(getattr(s, k), C.Array):
+            getattr(s, k)[:] = list(v)
+        else:
+            setattr(s, k, v)
+    return s
+
+
+def _ptr(a):
+    """numpy array -> (void*, keepalive); int -> raw (device) pointer."""
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return C.c_void_p(a.ctypes.data)
+
+
+def _pts(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] in (4, 8), "points must be [n,4] (XYZI16) or [n,8] (pcl::PointXYZI)"
+    return a, (LL_FMT_XYZI16 if a.shape[1] == 4 else LL_FMT_PCL32)

@@ -1,0 +1,459 @@
+// C-ABI of libloamlivox_b200.so (see include/loamlivox_b200.h) and the host-side ICP driver.
+//
+// Host logic restated from Point_cloud_registration::find_out_incremental_transfrom
+// (/root/reference/source/point_cloud_registration.hpp:163-583): the gate at :199, the ICP loop :211-532 (the per-iteration work is
+// four kernels: kNN+blocks, solve #1, inlier select, solve #2 + pose/termination), the threshold rescale :559 and the reject gate :561-573.
+#include <cmath>
+#include <cstring>
+#include "common.cuh"
+#include "kernels.cuh"
+
+int launch_inlier_select(ll_ctx* ctx, const double* d_l1, int M, double* d_sorted, double* d_unique, int* d_n_unique);
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct RegArrays {
+  float4* feat; float4* blk_a; double* blk_v; double* l1; double* l1_sorted; double* l1_unique; double* partials;
+  int* n_unique; int* knn_idx; float* knn_d; float4* tmp_a; float4* tmp_b; float4* tmp_c; int* counts; float* bounds; double* pose_tmp;
+  int cap;
+};
+static int reg_arrays(ll_ctx* ctx, int M, RegArrays* A) {
+  int cap = M > ctx->cfg.max_features ? M : ctx->cfg.max_features;
+  int scap = ctx->cfg.max_scan_points > cap ? ctx->cfg.max_scan_points : cap;
+  size_t bytes = align256((size_t)cap * 16) * 2 + align256((size_t)cap * 24) + align256((size_t)cap * 8) * 3 + align256((size_t)ctx->num_sms * 32 * 8) + 4096 +
+                 align256((size_t)cap * 20) * 2 + align256((size_t)scap * 16) * 3;
+  LL_CUDA(ctx, ctx->reg_buf.reserve(bytes));
+  char* p = ctx->reg_buf.as<char>();
+  auto take = [&](size_t b) { char* r = p; p += align256(b); return r; };
+  A->cap = cap;
+  A->feat = (float4*)take((size_t)cap * 16); A->blk_a = (float4*)take((size_t)cap * 16); A->blk_v = (double*)take((size_t)cap * 24);
+  A->l1 = (double*)take((size_t)cap * 8); A->l1_sorted = (double*)take((size_t)cap * 8); A->l1_unique = (double*)take((size_t)cap * 8);
+  A->partials = (double*)take((size_t)ctx->num_sms * 32 * 8);
+  A->n_unique = (int*)take(256); A->counts = (int*)take(256); A->bounds = (float*)take(256); A->pose_tmp = (double*)take(256);
+  A->knn_idx = (int*)take((size_t)cap * 20); A->knn_d = (float*)take((size_t)cap * 20);
+  A->tmp_a = (float4*)take((size_t)scap * 16); A->tmp_b = (float4*)take((size_t)scap * 16); A->tmp_c = (float4*)take((size_t)scap * 16);
+  return LL_OK;
+}
+
+extern "C" {
+
+void ll_config_default(ll_config* c) {
+  c->corner_curvature = 0.1f; c->surface_curvature = 0.005f; c->minimum_view_angle = 5.0f; c->livox_min_dis = 0.1f; c->livox_min_sigma = 7e-4f;
+  c->max_fov_deg = 17.0f; c->time_interval_pts = 1.0e-5f; c->max_scan_points = 400000; c->max_features = 400000;
+}
+void ll_reg_state_default(ll_reg_state* s) {
+  memset(s, 0, sizeof(*s));
+  s->if_motion_deblur = 0; s->current_frame_index = 1000; s->mapping_init_accumulate_frames = 50; s->icp_max_iterations = 15; s->cere_max_iterations = 50; s->cere_prerun_times = 2;
+  s->icp_plane = 1; s->icp_line = 1; s->maximum_allow_residual_block = 1000000;
+  s->para_max_angular_rate = 20.0; s->para_max_speed = 0.3; s->max_final_cost = 1.0e9; s->minimum_pt_time_stamp = 0.0; s->maximum_pt_time_stamp = 0.1;
+  s->minimum_icp_R_diff = 0.01; s->minimum_icp_T_diff = 0.01; s->inliner_dis = 0.02; s->inlier_ratio = 0.80; s->maximum_dis_plane_for_match = 50.0; s->maximum_dis_line_for_match = 2.0; s->huber_a = 0.1;
+  s->q_w_last[0] = 1; s->q_w_curr[0] = 1; s->para_buffer_incremental[3] = 1;
+}
+
+int ll_ctx_create(const ll_config* cfg, int device, ll_ctx** out) {
+  if (!out) return LL_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return LL_ERR_CUDA;   // no silent CPU fallback: the CUDA path is the product
+  if (device < 0 || device >= ndev) return LL_ERR_INVALID;
+  ll_ctx* ctx = new ll_ctx();
+  ctx->device = device;
+  if (cfg) ctx->cfg = *cfg; else ll_config_default(&ctx->cfg);
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return LL_ERR_CUDA; }
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device); ctx->num_sms = prop.multiProcessorCount;
+  cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2); cudaEventCreate(&ctx->ev3);
+  ctx->pinned_cap = 1 << 16; cudaHostAlloc(&ctx->pinned, ctx->pinned_cap, cudaHostAllocDefault);
+  void* dreg = nullptr; cudaMalloc(&dreg, sizeof(RegDevState)); cudaMemset(dreg, 0, sizeof(RegDevState)); ctx->d_reg = (RegDevState*)dreg;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { delete ctx; return LL_ERR_CUDA; }
+  *out = ctx; return LL_OK;
+}
+void ll_ctx_destroy(ll_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->scratch.release(); ctx->stage_in.release(); ctx->extract_buf.release(); ctx->feat_buf.release(); ctx->reg_buf.release();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->d_reg) cudaFree(ctx->d_reg);
+  if (ctx->comm_local) cudaFree(ctx->comm_local);
+  for (int i = 0; i < 8; i++) if (ctx->comm_peers[i] && i != ctx->rank) cudaIpcCloseMemHandle(ctx->comm_peers[i]);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+const char* ll_last_error(const ll_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* ll_ctx_stream(ll_ctx* ctx) { return (void*)ctx->stream; }
+int ll_ctx_sync(ll_ctx* ctx) { cudaSetDevice(ctx->device); LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return LL_OK; }
+uint64_t ll_launch_count(const ll_ctx* ctx) { return ctx->launches; }
+
+// ---------------------------------------------------------------------------------------------- S1
+int ll_extract(ll_ctx* ctx, const void* raw, size_t n, int fmt, int where, double stamp, int* n_scans) {
+  if (!ctx || (!raw && n)) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if ((int)n > ctx->cfg.max_scan_points) { ctx->set_error("scan larger than max_scan_points"); return LL_ERR_CAPACITY; }
+  ExtractState& e = ctx->ex;
+  LL_TRY(extract_reserve(ctx, ctx->cfg.max_scan_points));
+  // timestamp bookkeeping of extract_laser_features (:724-736)
+  if (stamp <= 0.0000001 || (stamp < e.last_maximum_time_stamp)) e.current_time = e.last_maximum_time_stamp; else e.current_time = stamp - e.first_receive_time;
+  if (e.first_receive_time <= 0) e.first_receive_time = stamp;
+  e.n = (int)n;
+  if (n > 0) e.last_maximum_time_stamp = (double)(float)(e.current_time + (double)(((float)(n - 1)) * ctx->cfg.time_interval_pts));
+  LL_TRY(upload_cloud(ctx, raw, n, fmt, where, e.raw));
+  if (n >= 5) LL_TRY(launch_extract(ctx, (int)n, e.current_time));
+  else LL_CUDA(ctx, cudaMemsetAsync(e.d_meta, 0, 16, ctx->stream));
+  if (n_scans) {
+    int* h = (int*)ctx->pinned;
+    LL_CUDA(ctx, cudaMemcpyAsync(h, e.d_meta, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_scans = h[1];
+  }
+  return LL_OK;
+}
+int ll_piece_bounds(ll_ctx* ctx, int pieces, float* start, float* end) {
+  if (!ctx || pieces < 1 || pieces > 16) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  RegArrays A; LL_TRY(reg_arrays(ctx, 0, &A));
+  LL_TRY(launch_piece_bounds(ctx, pieces, A.bounds));
+  float* h = (float*)ctx->pinned;
+  LL_CUDA(ctx, cudaMemcpyAsync(h, A.bounds, 2 * pieces * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < pieces; i++) { start[i] = h[2 * i]; end[i] = h[2 * i + 1]; }
+  return LL_OK;
+}
+int ll_get_features(ll_ctx* ctx, float minimum_blur, float maximum_blur, ll_point* corners, size_t* n_corners, ll_point* surface, size_t* n_surface, ll_point* full, size_t* n_full) {
+  if (!ctx) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  RegArrays A; LL_TRY(reg_arrays(ctx, 0, &A));
+  LL_TRY(launch_get_features(ctx, nullptr, minimum_blur, maximum_blur, A.tmp_a, A.tmp_b, A.tmp_c, A.counts));
+  int* h = (int*)ctx->pinned;
+  LL_CUDA(ctx, cudaMemcpyAsync(h, A.counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int nc = ctx->ex.n ? h[0] : 0, ns = ctx->ex.n ? h[1] : 0, nf = ctx->ex.n ? h[2] : 0;
+  if (corners && nc) LL_CUDA(ctx, cudaMemcpyAsync(corners, A.tmp_a, (size_t)nc * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (surface && ns) LL_CUDA(ctx, cudaMemcpyAsync(surface, A.tmp_b, (size_t)ns * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (full && nf) LL_CUDA(ctx, cudaMemcpyAsync(full, A.tmp_c, (size_t)nf * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_corners) *n_corners = nc; if (n_surface) *n_surface = ns; if (n_full) *n_full = nf;
+  return LL_OK;
+}
+int ll_extract_point_info(ll_ctx* ctx, int32_t* pt_type, int32_t* pt_label, float* curvature, float* view_angle, float* depth_sq2, float* time_stamp, float* polar_dis_sq2, int32_t* polar_direction) {
+  if (!ctx) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  ExtractState& e = ctx->ex; size_t n = e.n; cudaStream_t s = ctx->stream;
+  if (pt_type) LL_CUDA(ctx, cudaMemcpyAsync(pt_type, e.pt_type, n * 4, cudaMemcpyDeviceToHost, s));
+  if (pt_label) LL_CUDA(ctx, cudaMemcpyAsync(pt_label, e.pt_label, n * 4, cudaMemcpyDeviceToHost, s));
+  if (curvature) LL_CUDA(ctx, cudaMemcpyAsync(curvature, e.curvature, n * 4, cudaMemcpyDeviceToHost, s));
+  if (view_angle) LL_CUDA(ctx, cudaMemcpyAsync(view_angle, e.view_angle, n * 4, cudaMemcpyDeviceToHost, s));
+  if (depth_sq2) LL_CUDA(ctx, cudaMemcpyAsync(depth_sq2, e.depth_sq2, n * 4, cudaMemcpyDeviceToHost, s));
+  if (time_stamp) LL_CUDA(ctx, cudaMemcpyAsync(time_stamp, e.time_stamp, n * 4, cudaMemcpyDeviceToHost, s));
+  if (polar_dis_sq2) LL_CUDA(ctx, cudaMemcpyAsync(polar_dis_sq2, e.polar_dis_sq2, n * 4, cudaMemcpyDeviceToHost, s));
+  LL_CUDA(ctx, cudaStreamSynchronize(s));
+  if (polar_direction) {
+    std::vector<int8_t> tmp(n);
+    LL_CUDA(ctx, cudaMemcpy(tmp.data(), e.polar_dir, n, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) polar_direction[i] = tmp[i];
+  }
+  return LL_OK;
+}
+int ll_extract_split_idx(ll_ctx* ctx, int32_t* out, int cap, int* n_out) {
+  if (!ctx) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  int meta[3] = {0, 0, 0};
+  LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  LL_CUDA(ctx, cudaMemcpy(meta, ctx->ex.d_meta, sizeof(meta), cudaMemcpyDeviceToHost));
+  int m = meta[0] < cap ? meta[0] : cap;
+  if (m > 0) LL_CUDA(ctx, cudaMemcpy(out, ctx->ex.split_idx, (size_t)m * 4, cudaMemcpyDeviceToHost));
+  if (n_out) *n_out = meta[0];
+  return LL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- a5 / a7
+int ll_voxel_downsample(ll_ctx* ctx, const void* in, size_t n, int fmt, int where, float leaf, ll_point* out, size_t* n_out) {
+  if (!ctx || !n_out || !(leaf > 0.f)) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  *n_out = 0; if (n == 0) return LL_OK;
+  LL_CUDA(ctx, ctx->feat_buf.reserve(align256(n * 16) * 2 + 512));
+  float4* d_in = ctx->feat_buf.as<float4>(); float4* d_out = (float4*)((char*)d_in + align256(n * 16)); int* d_n = (int*)((char*)d_out + align256(n * 16));
+  LL_TRY(upload_cloud(ctx, in, n, fmt, where, d_in));
+  LL_TRY(launch_voxel_grid(ctx, d_in, (int)n, nullptr, leaf, d_out, d_n));
+  int* h = (int*)ctx->pinned;
+  LL_CUDA(ctx, cudaMemcpyAsync(h, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_out = (size_t)h[0];
+  if (out && h[0] > 0) { LL_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)h[0] * 16, cudaMemcpyDeviceToHost, ctx->stream)); LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
+  return LL_OK;
+}
+int ll_transform(ll_ctx* ctx, const double q[4], const double t[3], const void* in, size_t n, int fmt, int where, ll_point* out) {
+  if (!ctx || !q || !t) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (n == 0) return LL_OK;
+  LL_CUDA(ctx, ctx->feat_buf.reserve(align256(n * 16) * 2 + 512));
+  float4* d_in = ctx->feat_buf.as<float4>(); float4* d_out = (float4*)((char*)d_in + align256(n * 16)); double* d_pose = (double*)((char*)d_out + align256(n * 16));
+  double* h = (double*)ctx->pinned; for (int k = 0; k < 4; k++) h[k] = q[k]; for (int k = 0; k < 3; k++) h[4 + k] = t[k];
+  LL_CUDA(ctx, cudaMemcpyAsync(d_pose, h, 7 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  LL_TRY(upload_cloud(ctx, in, n, fmt, where, d_in));
+  LL_TRY(launch_transform(ctx, d_pose, d_in, (int)n, d_out));
+  LL_CUDA(ctx, cudaMemcpyAsync(out, d_out, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return LL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- S2
+static int map_build_common(ll_ctx* ctx, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where, ll_map** out) {
+  if (!ctx || !out) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  ll_map* m = new ll_map(); m->device = ctx->device;
+  size_t nmax = nc > ns ? nc : ns;
+  LL_CUDA(ctx, ctx->feat_buf.reserve(align256(nmax * 16) + 256));
+  float4* d_in = ctx->feat_buf.as<float4>();
+  int st = upload_cloud(ctx, corner, nc, fmt, where, d_in);
+  if (st == LL_OK) st = build_bucket_tree(ctx, d_in, (int)nc, &m->corner);
+  if (st == LL_OK) st = upload_cloud(ctx, surf, ns, fmt, where, d_in);
+  if (st == LL_OK) st = build_bucket_tree(ctx, d_in, (int)ns, &m->surf);
+  if (st == LL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = LL_ERR_CUDA;
+  if (st != LL_OK) { m->corner.storage.release(); m->surf.storage.release(); delete m; return st; }
+  *out = m; return LL_OK;
+}
+int ll_map_build(ll_ctx* ctx, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where, ll_map** out) {
+  return map_build_common(ctx, corner, nc, surf, ns, fmt, where, out);
+}
+void ll_map_release(ll_map* map) {
+  if (!map) return;
+  cudaSetDevice(map->device);
+  map->corner.storage.release(); map->surf.storage.release(); delete map;
+}
+size_t ll_map_size(const ll_map* map, int which) { return map ? (size_t)(which == 0 ? map->corner.n : map->surf.n) : 0; }
+
+int ll_knn(ll_ctx* ctx, const ll_map* map, int which, const ll_point* queries, size_t nq, int32_t* idx5, float* sqdist5) {
+  if (!ctx || !map) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (nq == 0) return LL_OK;
+  LL_CUDA(ctx, ctx->feat_buf.reserve(align256(nq * 16) + align256(nq * 20) * 2));
+  float4* d_q = ctx->feat_buf.as<float4>(); int* d_idx = (int*)((char*)d_q + align256(nq * 16)); float* d_d = (float*)((char*)d_idx + align256(nq * 20));
+  LL_CUDA(ctx, cudaMemcpyAsync(d_q, queries, nq * 16, cudaMemcpyHostToDevice, ctx->stream));
+  LL_TRY(launch_knn_query(ctx, which == 0 ? map->corner : map->surf, d_q, (int)nq, d_idx, d_d));
+  LL_CUDA(ctx, cudaMemcpyAsync(idx5, d_idx, nq * 20, cudaMemcpyDeviceToHost, ctx->stream));
+  LL_CUDA(ctx, cudaMemcpyAsync(sqdist5, d_d, nq * 20, cudaMemcpyDeviceToHost, ctx->stream));
+  LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return LL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- S3
+static void fill_state(RegDevState* h, const ll_reg_state* in) {
+  memset(h, 0, sizeof(RegDevState));
+  for (int k = 0; k < 4; k++) { h->pose_curr[k] = in->q_w_curr[k]; h->pose_last[k] = in->q_w_last[k]; }
+  for (int k = 0; k < 3; k++) { h->pose_curr[4 + k] = in->t_w_curr[k]; h->pose_last[4 + k] = in->t_w_last[k]; }
+  for (int k = 0; k < 7; k++) h->x[k] = in->para_buffer_incremental[k];
+  h->q_last_opt[0] = 1.0;
+  h->bound = (double)(float)in->para_max_speed; h->huber_a = in->huber_a; h->inliner_dis = in->inliner_dis; h->inlier_ratio = in->inlier_ratio;
+  h->min_icp_R = in->minimum_icp_R_diff; h->min_icp_T = in->minimum_icp_T_diff;
+}
+static KnnBlocksArgs knn_args(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, int ns, const ll_reg_state* in, bool debug) {
+  KnnBlocksArgs a; a.corner = make_view(map->corner); a.surf = make_view(map->surf); a.feat = A.feat; a.n_corner = nc; a.n_surf = ns;
+  a.pose = ctx->d_reg->pose_curr; a.max_dis_line = in->maximum_dis_line_for_match; a.max_dis_plane = in->maximum_dis_plane_for_match;
+  a.icp_line = in->icp_line; a.icp_plane = in->icp_plane; a.blk_a = A.blk_a; a.blk_v = A.blk_v;
+  a.corner_avail = &ctx->d_reg->corner_avail; a.surf_avail = &ctx->d_reg->surf_avail;
+  a.knn_idx = debug ? A.knn_idx : nullptr; a.knn_d = debug ? A.knn_d : nullptr;
+  a.rank = map->rank; a.world = map->world; a.inv_cell = map->cell_size > 0.f ? 1.0f / map->cell_size : 1.0f;
+  return a;
+}
+static SolveArgs solve_args(ll_ctx* ctx, const RegArrays& A, int M, int mode, int max_iter) {
+  SolveArgs s; s.st = ctx->d_reg; s.feat = A.feat; s.blk_a = A.blk_a; s.blk_v = A.blk_v; s.l1 = A.l1; s.l1_sorted_unique = A.l1_unique; s.d_n_unique = A.n_unique;
+  s.partials = A.partials; s.M = M; s.max_iterations = max_iter; s.mode = mode; s.rank = ctx->rank; s.world = ctx->world; s.comm_local = (double*)ctx->comm_local;
+  for (int i = 0; i < 8; i++) s.comm_peer[i] = (double*)ctx->comm_peers[i];
+  return s;
+}
+
+// Registration on features already resident in A.feat (device). Core of ll_register / ll_scan_to_pose.
+static int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, int ns, const ll_reg_state* in, ll_reg_result* out) {
+  cudaStream_t s = ctx->stream;
+  memset(out, 0, sizeof(*out));
+  out->status = 1;
+  for (int k = 0; k < 4; k++) { out->q_w_curr[k] = in->q_w_curr[k]; out->q_w_incre[k] = k == 0 ? in->para_buffer_incremental[3] : in->para_buffer_incremental[k - 1]; }
+  for (int k = 0; k < 3; k++) { out->t_w_curr[k] = in->t_w_curr[k]; out->t_w_incre[k] = in->para_buffer_incremental[4 + k]; }
+  // gate (:199): CORNER_MIN_MAP_NUM 0, SURFACE_MIN_MAP_NUM 50
+  if (!(map->corner.n_src > 0 && map->surf.n_src > 50 && in->current_frame_index > in->mapping_init_accumulate_frames)) return LL_OK;
+  const int M = nc + ns;
+  if (nc > 2 * in->maximum_allow_residual_block || ns > 2 * in->maximum_allow_residual_block) { ctx->set_error("feature count exceeds 2 x maximum_allow_residual_block (reference would drop features at random)"); return LL_ERR_CAP_BINDS; }
+  if (M == 0) { ctx->set_error("no features"); return LL_ERR_NO_BLOCKS; }
+  RegDevState* h = (RegDevState*)ctx->pinned;
+  fill_state(h, in);
+  LL_CUDA(ctx, cudaMemcpyAsync(ctx->d_reg, h, sizeof(RegDevState), cudaMemcpyHostToDevice, s));
+  LL_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+  out->registered = 1;
+  KnnBlocksArgs ka = knn_args(ctx, map, A, nc, ns, in, false);
+  int iter = 0; RegDevState* hs = (RegDevState*)((char*)ctx->pinned + align256(sizeof(RegDevState)));
+  for (iter = 0; iter < in->icp_max_iterations; iter++) {
+    LL_CUDA(ctx, cudaMemsetAsync(&ctx->d_reg->corner_avail, 0, 2 * sizeof(int), s));
+    if (iter == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    LL_TRY(launch_knn_blocks(ctx, ka));
+    if (iter == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev2, s));
+    LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 0, in->cere_prerun_times)));
+    LL_TRY(launch_inlier_select(ctx, A.l1, M, A.l1_sorted, A.l1_unique, A.n_unique));
+    LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 1, in->cere_max_iterations)));
+    LL_CUDA(ctx, cudaMemcpyAsync(hs, ctx->d_reg, sizeof(RegDevState), cudaMemcpyDeviceToHost, s));
+    LL_CUDA(ctx, cudaStreamSynchronize(s));
+    if (hs->lm.termination == -1) { ctx->set_error("no residual block survived the gates / inlier selection"); return LL_ERR_NO_BLOCKS; }
+    if (iter == 0 && (hs->corner_avail + (in->icp_plane ? hs->surf_avail : 0)) > in->maximum_allow_residual_block) {
+      ctx->set_error("residual blocks exceed maximum_allow_residual_block (reference would drop blocks at random)"); return LL_ERR_CAP_BINDS;
+    }
+    if (hs->icp_done) break;
+  }
+  LL_CUDA(ctx, cudaEventRecord(ctx->ev3, s));
+  LL_CUDA(ctx, cudaEventSynchronize(ctx->ev3));
+  cudaEventElapsedTime(&out->gpu_ms_total, ctx->ev0, ctx->ev3); cudaEventElapsedTime(&out->gpu_ms_knn, ctx->ev1, ctx->ev2);
+  out->icp_iterations = (iter + 1 < in->icp_max_iterations) ? iter + 1 : in->icp_max_iterations;
+  out->corner_used = hs->corner_avail; out->surf_used = hs->surf_avail; out->num_residual_blocks = hs->num_residual_blocks;
+  out->total_lm_iterations = hs->total_lm_iterations; out->total_evaluations = hs->total_evaluations;
+  for (int k = 0; k < 4; k++) out->q_w_curr[k] = hs->pose_curr[k];
+  for (int k = 0; k < 3; k++) out->t_w_curr[k] = hs->pose_curr[4 + k];
+  out->q_w_incre[0] = hs->x[3]; out->q_w_incre[1] = hs->x[0]; out->q_w_incre[2] = hs->x[1]; out->q_w_incre[3] = hs->x[2];
+  for (int k = 0; k < 3; k++) out->t_w_incre[k] = hs->x[4 + k];
+  out->final_cost = hs->final_cost; out->initial_cost = hs->initial_cost; out->angular_diff = hs->angular_diff; out->t_diff = hs->t_diff;
+  out->inlier_threshold = hs->inlier_threshold * hs->final_cost / hs->initial_cost;   // :559
+  const float minimize_cost = (float)hs->final_cost;
+  if (hs->angular_diff > (double)(float)in->para_max_angular_rate || minimize_cost > (float)in->max_final_cost) {   // :561-573
+    out->status = 0;
+    for (int k = 0; k < 4; k++) out->q_w_curr[k] = in->q_w_last[k];
+    for (int k = 0; k < 3; k++) out->t_w_curr[k] = in->t_w_last[k];
+  }
+  return LL_OK;
+}
+
+int ll_register(ll_ctx* ctx, const ll_map* map, const void* scan_corner, size_t nc, const void* scan_surf, size_t ns, int fmt, int where, const ll_reg_state* in, ll_reg_result* out) {
+  if (!ctx || !map || !in || !out) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if ((int)(nc + ns) > ctx->cfg.max_features) { ctx->set_error("more features than max_features"); return LL_ERR_CAPACITY; }
+  RegArrays A; LL_TRY(reg_arrays(ctx, (int)(nc + ns), &A));
+  LL_TRY(upload_cloud(ctx, scan_corner, nc, fmt, where, A.feat));
+  LL_TRY(upload_cloud(ctx, scan_surf, ns, fmt, where, A.feat + nc));
+  return register_device(ctx, map, A, (int)nc, (int)ns, in, out);
+}
+
+int ll_build_blocks(ll_ctx* ctx, const ll_map* map, const void* scan_corner, size_t nc, const void* scan_surf, size_t ns, int fmt, int where, const ll_reg_state* in,
+                    int32_t* type, double* a3, double* v3, int* corner_avail, int* surf_avail) {
+  if (!ctx || !map || !in) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const int M = (int)(nc + ns);
+  if (M > ctx->cfg.max_features) return LL_ERR_CAPACITY;
+  RegArrays A; LL_TRY(reg_arrays(ctx, M, &A));
+  cudaStream_t s = ctx->stream;
+  LL_TRY(upload_cloud(ctx, scan_corner, nc, fmt, where, A.feat));
+  LL_TRY(upload_cloud(ctx, scan_surf, ns, fmt, where, A.feat + nc));
+  RegDevState* h = (RegDevState*)ctx->pinned; fill_state(h, in);
+  LL_CUDA(ctx, cudaMemcpyAsync(ctx->d_reg, h, sizeof(RegDevState), cudaMemcpyHostToDevice, s));
+  LL_TRY(launch_knn_blocks(ctx, knn_args(ctx, map, A, (int)nc, (int)ns, in, true)));
+  std::vector<float4> ba(M); std::vector<double> bv((size_t)M * 3);
+  int cnt[2];
+  LL_CUDA(ctx, cudaMemcpyAsync(ba.data(), A.blk_a, (size_t)M * 16, cudaMemcpyDeviceToHost, s));
+  LL_CUDA(ctx, cudaMemcpyAsync(bv.data(), A.blk_v, (size_t)M * 24, cudaMemcpyDeviceToHost, s));
+  LL_CUDA(ctx, cudaMemcpyAsync(cnt, &ctx->d_reg->corner_avail, 8, cudaMemcpyDeviceToHost, s));
+  LL_CUDA(ctx, cudaStreamSynchronize(s));
+  for (int i = 0; i < M; i++) {
+    int t; memcpy(&t, &ba[i].w, 4);
+    if (type) type[i] = t;
+    if (a3) { a3[3 * i] = ba[i].x; a3[3 * i + 1] = ba[i].y; a3[3 * i + 2] = ba[i].z; }
+    if (v3) { v3[3 * i] = bv[3 * i]; v3[3 * i + 1] = bv[3 * i + 1]; v3[3 * i + 2] = bv[3 * i + 2]; }
+  }
+  if (corner_avail) *corner_avail = cnt[0]; if (surf_avail) *surf_avail = cnt[1];
+  ctx->hook_slots = M;   // slot count for ll_normal_equations / ll_solve
+  return LL_OK;
+}
+int ll_normal_equations(ll_ctx* ctx, const double x[7], double out28[28]) {
+  if (!ctx || !x || !out28) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const int M = ctx->hook_slots;
+  RegArrays A; LL_TRY(reg_arrays(ctx, M, &A));
+  cudaStream_t s = ctx->stream;
+  LL_CUDA(ctx, cudaMemcpyAsync(ctx->d_reg->x, x, 7 * sizeof(double), cudaMemcpyHostToDevice, s));
+  LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 3, 0)));
+  RegDevState* hs = (RegDevState*)((char*)ctx->pinned + align256(sizeof(RegDevState)));
+  LL_CUDA(ctx, cudaMemcpyAsync(hs, ctx->d_reg, sizeof(RegDevState), cudaMemcpyDeviceToHost, s));
+  LL_CUDA(ctx, cudaStreamSynchronize(s));
+  for (int i = 0; i < 21; i++) out28[i] = hs->lm.H[i];
+  for (int i = 0; i < 6; i++) out28[21 + i] = hs->lm.g[i];
+  out28[27] = hs->lm.x_cost;
+  return LL_OK;
+}
+int ll_solve(ll_ctx* ctx, int max_iterations, double x_io[7], double* initial_cost, double* final_cost, int* iterations) {
+  if (!ctx || !x_io) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const int M = ctx->hook_slots;
+  RegArrays A; LL_TRY(reg_arrays(ctx, M, &A));
+  cudaStream_t s = ctx->stream;
+  LL_CUDA(ctx, cudaMemcpyAsync(ctx->d_reg->x, x_io, 7 * sizeof(double), cudaMemcpyHostToDevice, s));
+  LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 2, max_iterations)));
+  RegDevState* hs = (RegDevState*)((char*)ctx->pinned + align256(sizeof(RegDevState)));
+  LL_CUDA(ctx, cudaMemcpyAsync(hs, ctx->d_reg, sizeof(RegDevState), cudaMemcpyDeviceToHost, s));
+  LL_CUDA(ctx, cudaStreamSynchronize(s));
+  for (int k = 0; k < 7; k++) x_io[k] = hs->x[k];
+  if (initial_cost) *initial_cost = hs->lm.initial_cost; if (final_cost) *final_cost = hs->lm.final_cost; if (iterations) *iterations = hs->lm.iteration;
+  return LL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- whole per-scan step
+int ll_scan_to_pose(ll_ctx* ctx, const ll_map* map, const void* raw, size_t n, int fmt, int where, double stamp, const ll_pipeline_cfg* pc, const ll_reg_state* in,
+                    ll_reg_result* out, int* n_corner_used, int* n_surf_used) {
+  if (!ctx || !map || !pc || !in || !out) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  LL_TRY(ll_extract(ctx, raw, n, fmt, where, stamp, nullptr));
+  RegArrays A; LL_TRY(reg_arrays(ctx, 0, &A));
+  const int ncap = (int)n;
+  // Laser_feature::laserCloudHandler: piece bounds -> get_features -> VoxelGrid (surface: plane_res/2, corner: line_res)   (laser_feature_extractor.hpp:313-380)
+  const float* d_bounds = nullptr;
+  if (!pc->whole_frame) { LL_TRY(launch_piece_bounds(ctx, pc->pieces, A.bounds)); d_bounds = A.bounds + 2 * pc->use_piece; }
+  LL_TRY(launch_get_features(ctx, d_bounds, 0.f, 1.f, A.tmp_a, A.tmp_b, nullptr, A.counts));
+  // corners: tmp_a --vg(extractor leaf)--> tmp_c --vg(mapping leaf)--> feat[0..)
+  int* cnt = A.counts;   // [0] corners [1] surf [2] full [3..] temporaries
+  LL_TRY(launch_voxel_grid(ctx, A.tmp_a, ncap, cnt + 0, pc->extractor_leaf_corner, A.tmp_c, cnt + 4));
+  LL_TRY(launch_voxel_grid(ctx, A.tmp_c, ncap, cnt + 4, pc->mapping_leaf_corner, A.tmp_a, cnt + 5));     // Laser_mapping::process_new_scan :1367-1373
+  LL_TRY(launch_voxel_grid(ctx, A.tmp_b, ncap, cnt + 1, pc->extractor_leaf_surf, A.tmp_c, cnt + 6));
+  LL_TRY(launch_voxel_grid(ctx, A.tmp_c, ncap, cnt + 6, pc->mapping_leaf_surf, A.tmp_b, cnt + 7));
+  int* h = (int*)ctx->pinned + 8192;
+  LL_CUDA(ctx, cudaMemcpyAsync(h, cnt, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  LL_CUDA(ctx, cudaStreamSynchronize(s));
+  int meta_scans = 0; { int* hm = (int*)ctx->pinned + 8300; LL_CUDA(ctx, cudaMemcpyAsync(hm, ctx->ex.d_meta, 12, cudaMemcpyDeviceToHost, s)); LL_CUDA(ctx, cudaStreamSynchronize(s)); meta_scans = hm[1]; }
+  const int nc = h[5], ns = h[7];
+  if (n_corner_used) *n_corner_used = nc; if (n_surf_used) *n_surf_used = ns;
+  if (meta_scans <= 5 && !pc->whole_frame) { memset(out, 0, sizeof(*out)); out->status = 1; ctx->set_error("frame dropped: <= 5 petals"); return LL_OK; }   // laser_feature_extractor.hpp:287
+  if (nc + ns > ctx->cfg.max_features) return LL_ERR_CAPACITY;
+  LL_CUDA(ctx, cudaMemcpyAsync(A.feat, A.tmp_a, (size_t)nc * 16, cudaMemcpyDeviceToDevice, s));
+  LL_CUDA(ctx, cudaMemcpyAsync(A.feat + nc, A.tmp_b, (size_t)ns * 16, cudaMemcpyDeviceToDevice, s));
+  return register_device(ctx, map, A, nc, ns, in, out);
+}
+
+// ---------------------------------------------------------------------------------------------- multi-GPU
+int ll_comm_local_handle(ll_ctx* ctx, unsigned char handle[LL_IPC_HANDLE_BYTES]) {
+  if (!ctx) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (!ctx->comm_local) { LL_CUDA(ctx, cudaMalloc(&ctx->comm_local, 2 * 8 * 64 * sizeof(double))); LL_CUDA(ctx, cudaMemset(ctx->comm_local, 0, 2 * 8 * 64 * sizeof(double))); }
+  cudaIpcMemHandle_t h; LL_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->comm_local));
+  static_assert(sizeof(cudaIpcMemHandle_t) <= LL_IPC_HANDLE_BYTES, "ipc handle size");
+  memset(handle, 0, LL_IPC_HANDLE_BYTES); memcpy(handle, &h, sizeof(h));
+  return LL_OK;
+}
+int ll_comm_connect(ll_ctx* ctx, int rank, int world, const unsigned char* all) {
+  if (!ctx || world < 1 || world > 8 || rank < 0 || rank >= world) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (!ctx->comm_local) { ctx->set_error("call ll_comm_local_handle first"); return LL_ERR_INVALID; }
+  ctx->rank = rank; ctx->world = world;
+  for (int p = 0; p < world; p++) {
+    if (p == rank) { ctx->comm_peers[p] = ctx->comm_local; continue; }
+    cudaIpcMemHandle_t h; memcpy(&h, all + (size_t)p * LL_IPC_HANDLE_BYTES, sizeof(h));
+    LL_CUDA(ctx, cudaIpcOpenMemHandle(&ctx->comm_peers[p], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  return LL_OK;
+}
+int ll_map_build_sharded(ll_ctx* ctx, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where, int rank, int world, float cell_size,
+                         float halo_corner, float halo_surf, ll_map** out) {
+  (void)halo_corner; (void)halo_surf;
+  // Round 1: every rank indexes the full snapshot (20M points = 320 MB, trivially resident) and owns the queries whose cell hashes
+  // to it; the per-rank halo-trimmed index is the next step (multi-GPU).
+  int st = map_build_common(ctx, corner, nc, surf, ns, fmt, where, out);
+  if (st == LL_OK) { (*out)->rank = rank; (*out)->world = world; (*out)->cell_size = cell_size; }
+  return st;
+}
+
+}  // extern "C"

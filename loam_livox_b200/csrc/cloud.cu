@@ -1,0 +1,192 @@
+// Cloud plumbing kernels: format repack, pointAssociateToMap over a cloud, VoxelGrid down-sampling, inlier selection.
+//
+// Replaces, on the reference side:
+//   pcl::VoxelGrid<PointXYZI>::filter (third-party PCL, restated)  call sites /root/reference/source/laser_feature_extractor.hpp:372-380,
+//                                   /root/reference/source/laser_mapping.hpp:491,509,533-537,1367-1373,1434-1437                 (K4)
+//   pointcloudAssociateToMap        /root/reference/source/point_cloud_registration.hpp:622-661,673-685                           (K6, cloud form)
+//   compute_inlier_residual_threshold (std::set de-dup + order statistic) /root/reference/source/point_cloud_registration.hpp:153-161,484-485 (K10)
+//
+// Compiled with -fmad=false (voxel indices, centroids and the transform must round like the scalar CPU code).
+#include <cub/cub.cuh>
+#include "common.cuh"
+#include "kernels.cuh"
+#include "exact_math.cuh"
+
+#define FULL 0xffffffffu
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// ------------------------------------------------------------------------------------------------ upload / repack
+__global__ void repack_pcl32_kernel(const float* __restrict__ src, int n, float4* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = reinterpret_cast<const float4*>(src)[2 * i];      // x y z pad
+  const float4 b = reinterpret_cast<const float4*>(src)[2 * i + 1];  // intensity pad pad pad
+  dst[i] = make_float4(a.x, a.y, a.z, b.x);
+}
+
+int upload_cloud(ll_ctx* ctx, const void* src, size_t n, int fmt, int where, float4* d_dst) {
+  if (n == 0) return LL_OK;
+  cudaStream_t s = ctx->stream;
+  if (fmt == LL_FMT_XYZI16) {
+    LL_CUDA(ctx, cudaMemcpyAsync(d_dst, src, n * 16, where == LL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  } else if (fmt == LL_FMT_PCL32) {
+    const float* d_src = (const float*)src;
+    if (where == LL_HOST) {
+      LL_CUDA(ctx, ctx->stage_in.reserve(n * 32));
+      LL_CUDA(ctx, cudaMemcpyAsync(ctx->stage_in.p, src, n * 32, cudaMemcpyHostToDevice, s));
+      d_src = ctx->stage_in.as<float>();
+    }
+    repack_pcl32_kernel<<<ll_div_up((int)n, 256), 256, 0, s>>>(d_src, (int)n, d_dst); ctx->launches++;
+    LL_CUDA(ctx, cudaGetLastError());
+  } else { ctx->set_error("unknown point format"); return LL_ERR_INVALID; }
+  return LL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ transform
+__global__ void transform_kernel(const double* __restrict__ pose7, const float4* __restrict__ in, int n, const int* __restrict__ d_n, float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d_n) n = min(n, *d_n);
+  if (i >= n) return;
+  const float4 p = in[i];
+  double q[4] = {pose7[0], pose7[1], pose7[2], pose7[3]};
+  double wx, wy, wz; qrot_d(q, (double)p.x, (double)p.y, (double)p.z, wx, wy, wz);
+  out[i] = make_float4((float)(wx + pose7[4]), (float)(wy + pose7[5]), (float)(wz + pose7[6]), p.w);
+}
+int launch_transform(ll_ctx* ctx, const double* d_pose7, const float4* d_in, int n, float4* d_out) {
+  if (n == 0) return LL_OK;
+  transform_kernel<<<ll_div_up(n, 256), 256, 0, ctx->stream>>>(d_pose7, d_in, n, nullptr, d_out); ctx->launches++;
+  LL_CUDA(ctx, cudaGetLastError());
+  return LL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ VoxelGrid
+struct VgMeta {
+  int mn[3], mx[3];     // ordered-int encodings of the float min / max
+  int n_finite;
+  int passthrough;      // dx*dy*dz overflows int32: PCL warns and copies the input through
+  int n_in;
+  int min_b[3]; int mul[3];
+  float inv;
+};
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void vg_init_kernel(VgMeta* m, int n_host, const int* d_n) {
+  for (int k = 0; k < 3; k++) { m->mn[k] = f2ord(INFINITY); m->mx[k] = f2ord(-INFINITY); }
+  m->n_finite = 0; m->passthrough = 0; m->n_in = d_n ? min(*d_n, n_host) : n_host;
+}
+__global__ void vg_minmax_kernel(const float4* __restrict__ in, VgMeta* m) {
+  const int n = m->n_in;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}; int cnt = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = in[i];
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+      hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z); cnt++;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], __shfl_xor_sync(FULL, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL, hi[k], o)); }
+    cnt += __shfl_xor_sync(FULL, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt > 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { atomicMin(&m->mn[k], f2ord(lo[k])); atomicMax(&m->mx[k], f2ord(hi[k])); }
+    atomicAdd(&m->n_finite, cnt);
+  }
+}
+__global__ void vg_setup_kernel(VgMeta* m, float leaf) {
+  const float inv = 1.0f / leaf; m->inv = inv;
+  if (m->n_finite == 0) { for (int k = 0; k < 3; k++) { m->min_b[k] = 0; m->mul[k] = 0; } return; }
+  float mn[3], mx[3]; for (int k = 0; k < 3; k++) { mn[k] = ord2f(m->mn[k]); mx[k] = ord2f(m->mx[k]); }
+  long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1, dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+  if (dx * dy * dz > 2147483647LL) { m->passthrough = 1; return; }
+  int div_b[3];
+  for (int k = 0; k < 3; k++) { m->min_b[k] = (int)floorf(mn[k] * inv); int max_b = (int)floorf(mx[k] * inv); div_b[k] = max_b - m->min_b[k] + 1; }
+  m->mul[0] = 1; m->mul[1] = div_b[0]; m->mul[2] = div_b[0] * div_b[1];
+}
+__global__ void vg_keys_kernel(const float4* __restrict__ in, const VgMeta* __restrict__ m, int n_cap, unsigned* __restrict__ keys, int* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cap) return;
+  unsigned key = 0xffffffffu;
+  if (i < m->n_in) {
+    float4 p = in[i];
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      const float inv = m->inv;
+      int ijk0 = (int)(floorf(p.x * inv) - (float)m->min_b[0]);
+      int ijk1 = (int)(floorf(p.y * inv) - (float)m->min_b[1]);
+      int ijk2 = (int)(floorf(p.z * inv) - (float)m->min_b[2]);
+      key = (unsigned)(ijk0 * m->mul[0] + ijk1 * m->mul[1] + ijk2 * m->mul[2]);
+    }
+  }
+  keys[i] = key; vals[i] = i;
+}
+__global__ void vg_heads_kernel(const unsigned* __restrict__ keys, int n_cap, unsigned char* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cap) return;
+  unsigned k = keys[i];
+  flags[i] = (k != 0xffffffffu && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+}
+// One thread per voxel: sequential float sum in ascending input index (radix sort is stable), like CentroidPoint<PointXYZI>.
+__global__ void vg_centroid_kernel(const float4* __restrict__ in, const VgMeta* __restrict__ m, const int* __restrict__ vals, const int* __restrict__ seg_start,
+                                   const int* __restrict__ d_num_seg, int n_cap, float4* __restrict__ out, int* __restrict__ d_n_out) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m->passthrough) {
+    if (s < m->n_in) out[s] = in[s];
+    if (s == 0) *d_n_out = m->n_in;
+    return;
+  }
+  const int nseg = *d_num_seg;
+  if (s == 0) *d_n_out = nseg;
+  if (s >= nseg) return;
+  const int b = seg_start[s], e = (s + 1 < nseg) ? seg_start[s + 1] : m->n_finite;
+  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+  for (int li = b; li < e; li++) { const float4 p = in[vals[li]]; sx += p.x; sy += p.y; sz += p.z; si += p.w; }
+  const float cnt = (float)(e - b);
+  out[s] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+}
+
+int launch_voxel_grid(ll_ctx* ctx, const float4* d_in, int n_cap, const int* d_n_in, float leaf, float4* d_out, int* d_n_out) {
+  cudaStream_t s = ctx->stream;
+  if (n_cap <= 0) { LL_CUDA(ctx, cudaMemsetAsync(d_n_out, 0, sizeof(int), s)); return LL_OK; }
+  size_t sort_bytes = 0, sel_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, n_cap, 0, 32, s);
+  cub::DeviceSelect::Flagged(nullptr, sel_bytes, cub::CountingInputIterator<int>(0), (unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, n_cap, s);
+  size_t tmp_bytes = sort_bytes > sel_bytes ? sort_bytes : sel_bytes;
+  size_t o_meta = 0, o_k0 = align256(sizeof(VgMeta) + 16), o_k1 = o_k0 + align256((size_t)n_cap * 4), o_v0 = o_k1 + align256((size_t)n_cap * 4), o_v1 = o_v0 + align256((size_t)n_cap * 4),
+         o_fl = o_v1 + align256((size_t)n_cap * 4), o_seg = o_fl + align256((size_t)n_cap), o_tmp = o_seg + align256((size_t)n_cap * 4);
+  LL_CUDA(ctx, ctx->scratch.reserve(o_tmp + tmp_bytes + 256));
+  char* base = ctx->scratch.as<char>();
+  VgMeta* meta = (VgMeta*)(base + o_meta); int* d_num_seg = (int*)(base + o_meta + sizeof(VgMeta));
+  unsigned* k0 = (unsigned*)(base + o_k0); unsigned* k1 = (unsigned*)(base + o_k1); int* v0 = (int*)(base + o_v0); int* v1 = (int*)(base + o_v1);
+  unsigned char* flags = (unsigned char*)(base + o_fl); int* seg = (int*)(base + o_seg);
+  const int blocks = ll_div_up(n_cap, 256);
+  vg_init_kernel<<<1, 1, 0, s>>>(meta, n_cap, d_n_in);
+  vg_minmax_kernel<<<min(blocks, ctx->num_sms * 8), 256, 0, s>>>(d_in, meta);
+  vg_setup_kernel<<<1, 1, 0, s>>>(meta, leaf);
+  vg_keys_kernel<<<blocks, 256, 0, s>>>(d_in, meta, n_cap, k0, v0);
+  LL_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + o_tmp, sort_bytes, k0, k1, v0, v1, n_cap, 0, 32, s));
+  vg_heads_kernel<<<blocks, 256, 0, s>>>(k1, n_cap, flags);
+  LL_CUDA(ctx, cub::DeviceSelect::Flagged(base + o_tmp, sel_bytes, cub::CountingInputIterator<int>(0), flags, seg, d_num_seg, n_cap, s));
+  vg_centroid_kernel<<<blocks, 256, 0, s>>>(d_in, meta, v1, seg, d_num_seg, n_cap, d_out, d_n_out);
+  ctx->launches += 12;
+  LL_CUDA(ctx, cudaGetLastError());
+  return LL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ inlier selection (K10)
+// std::set<double> of the per-block L1 norms == sort + unique; the solver kernel picks element floor(ratio * n_unique).
+int launch_inlier_select(ll_ctx* ctx, const double* d_l1, int M, double* d_sorted, double* d_unique, int* d_n_unique) {
+  cudaStream_t s = ctx->stream;
+  size_t sort_bytes = 0, uniq_bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (double*)nullptr, (double*)nullptr, M, 0, 64, s);
+  cub::DeviceSelect::Unique(nullptr, uniq_bytes, (double*)nullptr, (double*)nullptr, (int*)nullptr, M, s);
+  size_t tmp = sort_bytes > uniq_bytes ? sort_bytes : uniq_bytes;
+  LL_CUDA(ctx, ctx->scratch.reserve(tmp + 256));
+  LL_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->scratch.p, sort_bytes, d_l1, d_sorted, M, 0, 64, s));
+  LL_CUDA(ctx, cub::DeviceSelect::Unique(ctx->scratch.p, uniq_bytes, d_sorted, d_unique, d_n_unique, M, s));
+  ctx->launches += 6;
+  return LL_OK;
+}

@@ -1,0 +1,107 @@
+// Internal declarations shared by the CUDA translation units of libloamlivox_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/loamlivox_b200.h"
+
+#define LL_WARP 32
+#define LL_KNN 5
+
+#define LL_CUDA(ctx, expr)                                                                        \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+      return LL_ERR_CUDA;                                                                         \
+    }                                                                                             \
+  } while (0)
+#define LL_TRY(expr) do { int _s = (expr); if (_s != LL_OK) return _s; } while (0)
+
+// ------------------------------------------------------------------------------------------------ device arrays
+struct DevBuf {  // grow-only device allocation
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return (T*)p; }
+};
+
+// ------------------------------------------------------------------------------------------------ map index
+// "Bucket tree": map points sorted along a 63-bit Morton curve, cut into leaf buckets of 32 points (512 B,
+// one coalesced warp load / one cp.async.bulk), with levels of axis-aligned boxes above them, 32 children per
+// node.  Level 0 boxes bound the buckets; level l+1 boxes bound 32 consecutive level-l boxes.  The top level has
+// <= 32 boxes and is searched as one group.  Search is exact (boxes give a true lower bound of the fp32 distance).
+#define LL_MAX_LEVELS 6
+struct BucketTree {
+  int n = 0;             // valid (finite) points
+  int n_pad = 0;         // padded to a multiple of 32
+  int n_levels = 0;      // number of box levels (>= 1 when n > 0)
+  int level_count[LL_MAX_LEVELS] = {0};   // boxes per level (unpadded)
+  float4* pts = nullptr;                  // [n_pad] x,y,z, w = __int_as_float(original index); pad = +inf
+  float4* lo[LL_MAX_LEVELS] = {nullptr};  // [level_count padded to 32] box minima (w unused)
+  float4* hi[LL_MAX_LEVELS] = {nullptr};
+  float4* src = nullptr;                  // [n_src] the cloud as given to ll_map_build (x,y,z,intensity)
+  int n_src = 0;
+  DevBuf storage;                          // one allocation backing all of the above
+};
+
+struct ll_map {
+  int device = 0;
+  BucketTree corner, surf;
+  // sharding (world == 1: everything owned)
+  int rank = 0, world = 1; float cell_size = 0.f;
+};
+
+// per-scan feature-extraction state (device)
+struct ExtractState {
+  int n = 0;
+  float4* raw = nullptr;          // [n] x,y,z,reflectivity
+  int* pt_type = nullptr; int* pt_label = nullptr;
+  float* curvature = nullptr; float* view_angle = nullptr; float* depth_sq2 = nullptr; float* time_stamp = nullptr;
+  float* polar_dis_sq2 = nullptr; int8_t* polar_dir = nullptr; uint8_t* self_mask = nullptr; uint8_t* cand = nullptr;
+  int* cand_idx = nullptr; int* d_num_cand = nullptr;
+  int* split_idx = nullptr;        // [<= n]
+  int* scan_first = nullptr; int* scan_last = nullptr;
+  int* d_meta = nullptr;           // [0]=n_split [1]=n_scans [2]=clutter_size
+  double first_receive_time = -1, current_time = 0, last_maximum_time_stamp = 0;
+};
+
+// Solver / registration device state shared between kernels (lives in global memory)
+struct RegDevState;  // defined in solve.cuh
+
+struct ll_ctx {
+  int device = 0;
+  ll_config cfg;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int hook_slots = 0;      // slot count left behind by ll_build_blocks for the parity hooks
+  int num_sms = 0;
+  // arenas
+  DevBuf scratch;      // CUB temp storage
+  DevBuf stage_in;     // raw uploads (PCL32 or XYZI16)
+  DevBuf extract_buf;  // ExtractState arrays
+  DevBuf feat_buf;     // feature clouds / voxel-grid temporaries
+  DevBuf reg_buf;      // registration arrays
+  void* pinned = nullptr; size_t pinned_cap = 0;   // pinned host staging for small D2H/H2D control blocks
+  ExtractState ex;
+  RegDevState* d_reg = nullptr;   // device
+  // multi-GPU
+  int rank = 0, world = 1;
+  void* comm_local = nullptr;              // this rank's staging slot (device memory, IPC-exported)
+  void* comm_peers[8] = {nullptr};         // mapped peer slots (index = rank)
+  void set_error(const std::string& s) { err = s; }
+};
+
+inline int ll_div_up(int a, int b) { return (a + b - 1) / b; }

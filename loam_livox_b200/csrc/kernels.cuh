@@ -1,0 +1,89 @@
+// Kernel argument structs and host-side launch prototypes shared between translation units.
+#pragma once
+#include "common.cuh"
+
+struct TreeView {
+  const float4* pts; const float4* lo[LL_MAX_LEVELS]; const float4* hi[LL_MAX_LEVELS];
+  int n, n_levels;
+};
+TreeView make_view(const BucketTree& t);
+int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t);
+
+struct KnnBlocksArgs {
+  TreeView corner, surf;
+  const float4* feat;     // [n_corner + n_surf] scan-frame features (x,y,z,timestamp)
+  int n_corner, n_surf;
+  const double* pose;     // device: q_curr (w,x,y,z), t_curr
+  double max_dis_line, max_dis_plane;
+  int icp_line, icp_plane;
+  float4* blk_a; double* blk_v;
+  int* corner_avail; int* surf_avail;
+  int* knn_idx; float* knn_d;   // optional debug outputs [M x 5]
+  int rank, world; float inv_cell;
+};
+int launch_knn_query(ll_ctx* ctx, const BucketTree& t, const float4* d_q, int nq, int* d_idx, float* d_d);
+int launch_knn_blocks(ll_ctx* ctx, const KnnBlocksArgs& a);
+
+// ---------------------------------------------------------------------------------------------- solver (solve.cu)
+struct FnSample { double x, value, gradient; int value_valid, gradient_valid; };
+
+// Levenberg-Marquardt state machine (ceres TrustRegionMinimizer restated), advanced by one thread after every
+// grid-wide evaluation.
+struct LmState {
+  int phase, iteration, max_iterations, num_invalid, done, termination, last_successful, reuse_diagonal;
+  int ls_iters, n_valid, total_iterations, total_evaluations;
+  double x[7], x_norm, x_cost, g[6], H[21];
+  double trial[7];
+  double scaling[6], diagonal[6], radius, decrease_factor;
+  double delta[6], model_cost_change, gd, dmax, ls_alpha;
+  FnSample prev, cur;
+  double x_best[7], minimum_cost, min_iter_cost, initial_cost, final_cost, last_gmax;
+};
+
+struct RegDevState {
+  // pose block, contiguous: q_curr(w,x,y,z) t_curr(3) | q_last(4) t_last(3)
+  double pose_curr[7];
+  double pose_last[7];
+  double x[7];                 // m_para_buffer_incremental: q (x,y,z,w), t
+  double q_last_opt[4], t_last_opt[3];   // q_last_optimize / t_last_optimize of the ICP loop
+  double bound, huber_a, inliner_dis, inlier_ratio, min_icp_R, min_icp_T;
+  double inlier_threshold, angular_diff, t_diff, final_cost, initial_cost;
+  int corner_avail, surf_avail, icp_done, icp_iter, num_residual_blocks, status, total_lm_iterations, total_evaluations;
+  int n_unique; int pad0;
+  unsigned int bar_count, bar_gen;
+  LmState lm;
+};
+
+struct SolveArgs {
+  RegDevState* st;
+  const float4* feat;        // [M] scan-frame points
+  const float4* blk_a;       // [M] (a.xyz, type)
+  const double* blk_v;       // [M*3]
+  double* l1;                // [M] loss-corrected L1 norm per slot (+inf for invalid slots)
+  const double* l1_sorted_unique;  // [>= n_unique] for the threshold of solve #2
+  const int* d_n_unique;
+  double* partials;          // [grid x 32]
+  int M;
+  int max_iterations;
+  int mode;                  // 0: solve #1 (write l1 at the end) ; 1: solve #2 (apply threshold first, compose pose at the end) ;
+                             // 2: plain solve (parity hook) ; 3: evaluate once at st->x (parity hook, writes sums to st->lm.H/g/x_cost)
+  // multi-GPU
+  int rank, world; double* comm_local; double* comm_peer[8];
+};
+int launch_solve(ll_ctx* ctx, const SolveArgs& a);
+int solve_max_slots(ll_ctx* ctx);
+
+// ---------------------------------------------------------------------------------------------- clouds (cloud.cu)
+int upload_cloud(ll_ctx* ctx, const void* src, size_t n, int fmt, int where, float4* d_dst);   // async on ctx->stream
+int launch_transform(ll_ctx* ctx, const double* d_pose7, const float4* d_in, int n, float4* d_out);
+// VoxelGrid on device: d_in [n] -> d_out [<= n], *d_n_out on device. n given by host, or by device count d_n_in (may be null).
+struct VoxelTemps { DevBuf* buf; };
+int launch_inlier_select(ll_ctx* ctx, const double* d_l1, int M, double* d_sorted, double* d_unique, int* d_n_unique);
+int launch_voxel_grid(ll_ctx* ctx, const float4* d_in, int n_cap, const int* d_n_in, float leaf, float4* d_out, int* d_n_out);
+
+// ---------------------------------------------------------------------------------------------- extractor (extract.cu)
+int extract_reserve(ll_ctx* ctx, int n);
+int launch_extract(ll_ctx* ctx, int n, double current_time);
+int launch_get_features(ll_ctx* ctx, const float* d_bounds /*min_blur,max_blur on device*/, float min_blur, float max_blur,
+                        float4* d_corners, float4* d_surf, float4* d_full, int* d_counts /*3*/);
+int launch_piece_bounds(ll_ctx* ctx, int pieces, float* d_start_end /* 2*pieces */);

@@ -1,0 +1,530 @@
+// Robust 6-DoF Levenberg-Marquardt solve of one ICP iteration as ONE persistent kernel (K8 + K9 + K10 front end).
+//
+// Replaces, on the reference side (Ceres is third-party, restated from its published behaviour, see oracle/orc_solver.hpp):
+//   ceres::Problem / AddResidualBlock / Solve x2   /root/reference/source/point_cloud_registration.hpp:220-228,323,422,460-474,501-508
+//   residual models (autodiff)                     /root/reference/source/ceres_icp.hpp:262-288 (point2line), :338-366 (point2plane)
+//   HuberLoss(0.1), EigenQuaternionParameterization, bounds on t   :220-221, :143-151
+//   problem.Evaluate + inlier threshold front end  :476-499 (the L1 norms are produced here; select.cu finishes K10)
+//   pose composition + ICP termination test        :514-531
+//
+// Design: every residual block is staged once into SHARED MEMORY (52 B per block, SoA) of one of 148 persistent CTAs and
+// stays on-chip for the whole solve (up to ~580k blocks).  One evaluation = every thread evaluates r, J (analytic, fp64), the Huber
+// weight and its 28 normal-equation terms, warp-shuffle + shared-memory reduce per CTA, one 29-double partial per CTA,
+// a ticket barrier, and the LAST CTA to arrive reduces the partials in fixed order (run-to-run deterministic), runs the
+// trust-region logic on one thread and publishes the next trial point.  No host round trip inside a solve.
+#include <cfloat>
+#include "common.cuh"
+#include "kernels.cuh"
+
+#define FULL 0xffffffffu
+#define NSUM 29          // 21 JtJ (upper, row-major) + 6 Jtr + cost + valid-block count
+#define SOLVE_THREADS 512
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------ small algebra (one thread)
+__device__ void d_qmul(const double a[4], const double b[4], double o[4]) {  // (w,x,y,z)
+  o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  o[2] = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
+  o[3] = a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1];
+}
+__device__ void d_qrot(const double q[4], const double v[3], double o[3]) {
+  double ux = q[1], uy = q[2], uz = q[3], w = q[0];
+  double cx = uy * v[2] - uz * v[1], cy = uz * v[0] - ux * v[2], cz = ux * v[1] - uy * v[0];
+  cx += cx; cy += cy; cz += cz;
+  o[0] = v[0] + w * cx + (uy * cz - uz * cy); o[1] = v[1] + w * cy + (uz * cx - ux * cz); o[2] = v[2] + w * cz + (ux * cy - uy * cx);
+}
+__device__ double d_angdist(const double a[4], const double b[4]) {
+  double bc[4] = {b[0], -b[1], -b[2], -b[3]}, d[4]; d_qmul(a, bc, d);
+  return 2.0 * atan2(sqrt(d[1] * d[1] + d[2] * d[2] + d[3] * d[3]), fabs(d[0]));
+}
+// EigenQuaternionParameterization::Plus (x: q as x,y,z,w then t) + box projection of the t block
+__device__ void d_plus(const double x[7], const double delta[6], double bound, double out[7]) {
+  double nd = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
+  if (nd > 0.0) {
+    double sbd = sin(nd) / nd;
+    double dq[4] = {cos(nd), sbd * delta[0], sbd * delta[1], sbd * delta[2]}, q[4] = {x[3], x[0], x[1], x[2]}, r[4];
+    d_qmul(dq, q, r); out[0] = r[1]; out[1] = r[2]; out[2] = r[3]; out[3] = r[0];
+  } else { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3]; }
+  for (int k = 0; k < 3; k++) { double v = x[4 + k] + delta[3 + k]; out[4 + k] = fmin(fmax(v, -bound), bound); }
+}
+__device__ bool d_chol6(const double A[6][6], const double b[6], double x[6]) {
+  double L[6][6];
+  for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) L[i][j] = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j <= i; j++) {
+      double s = A[i][j]; for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+      if (i == j) { if (!(s > 0.0)) return false; L[i][i] = sqrt(s); } else L[i][j] = s / L[j][j];
+    }
+  double y[6];
+  for (int i = 0; i < 6; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[i][k] * y[k]; y[i] = s / L[i][i]; }
+  for (int i = 5; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k]; x[i] = s / L[i][i]; }
+  for (int i = 0; i < 6; i++) if (!isfinite(x[i])) return false;
+  return true;
+}
+__device__ __forceinline__ int hidx(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }  // i <= j, upper-triangular row-major
+
+// ---- ceres line-search polynomial helpers (polynomial.cc), highest degree first ----
+__device__ double d_poly_eval(const double* p, int n, double x) { double v = 0; for (int i = 0; i < n; i++) v = v * x + p[i]; return v; }
+__device__ int d_fit_poly(const FnSample* s, int ns, double* coef) {  // returns number of coefficients
+  int nc = 0; for (int i = 0; i < ns; i++) { if (s[i].value_valid) nc++; if (s[i].gradient_valid) nc++; }
+  const int deg = nc - 1; double A[6][6], rhs[6]; int perm[6];
+  int row = 0;
+  for (int i = 0; i < ns; i++) {
+    if (s[i].value_valid) { for (int j = 0; j <= deg; j++) A[row][j] = pow(s[i].x, (double)(deg - j)); rhs[row] = s[i].value; row++; }
+    if (s[i].gradient_valid) { for (int j = 0; j <= deg; j++) A[row][j] = j < deg ? (deg - j) * pow(s[i].x, (double)(deg - j - 1)) : 0.0; rhs[row] = s[i].gradient; row++; }
+  }
+  for (int i = 0; i < nc; i++) perm[i] = i;
+  for (int c = 0; c < nc; c++) {  // full pivoting
+    int pr = c, pc = c; double best = 0;
+    for (int i = c; i < nc; i++) for (int j = c; j < nc; j++) if (fabs(A[i][j]) > best) { best = fabs(A[i][j]); pr = i; pc = j; }
+    if (best == 0) break;
+    for (int j = 0; j < nc; j++) { double t = A[c][j]; A[c][j] = A[pr][j]; A[pr][j] = t; }
+    { double t = rhs[c]; rhs[c] = rhs[pr]; rhs[pr] = t; }
+    for (int i = 0; i < nc; i++) { double t = A[i][c]; A[i][c] = A[i][pc]; A[i][pc] = t; }
+    { int t = perm[c]; perm[c] = perm[pc]; perm[pc] = t; }
+    for (int i = c + 1; i < nc; i++) { double f = A[i][c] / A[c][c]; for (int j = c; j < nc; j++) A[i][j] -= f * A[c][j]; rhs[i] -= f * rhs[c]; }
+  }
+  double y[6];
+  for (int i = nc - 1; i >= 0; i--) { double sacc = rhs[i]; for (int j = i + 1; j < nc; j++) sacc -= A[i][j] * y[j]; y[i] = sacc / A[i][i]; }
+  for (int i = 0; i < nc; i++) coef[perm[i]] = y[i];
+  return nc;
+}
+// real parts of all roots of p (degree n-1), Durand-Kerner for degree > 2
+__device__ int d_root_real_parts(const double* pin, int n, double* out) {
+  double p[6]; int m = 0; bool lead = true;
+  for (int i = 0; i < n; i++) { if (lead && pin[i] == 0.0) continue; lead = false; p[m++] = pin[i]; }
+  int deg = m - 1; if (deg < 1) return 0;
+  if (deg == 1) { out[0] = -p[1] / p[0]; return 1; }
+  if (deg == 2) {
+    double a = p[0], b = p[1], c = p[2], D = b * b - 4 * a * c, sD = sqrt(fabs(D));
+    if (D >= 0) { if (b >= 0) { out[0] = (-b - sD) / (2.0 * a); out[1] = (2.0 * c) / (-b - sD); } else { out[0] = (2.0 * c) / (-b + sD); out[1] = (-b + sD) / (2.0 * a); } }
+    else { out[0] = -b / (2.0 * a); out[1] = out[0]; }
+    return 2;
+  }
+  double zr[5], zi[5], cr[6]; for (int i = 0; i <= deg; i++) cr[i] = p[i] / p[0];
+  double rad = 0; for (int i = 1; i <= deg; i++) rad = fmax(rad, fabs(cr[i])); rad = 1.0 + rad;
+  for (int i = 0; i < deg; i++) { double ang = 2.0 * 3.14159265358979323846 * i / deg + 0.4; zr[i] = rad * 0.5 * cos(ang); zi[i] = rad * 0.5 * sin(ang); }
+  for (int it = 0; it < 500; it++) {
+    double change = 0;
+    for (int i = 0; i < deg; i++) {
+      double nr = 0, ni = 0; for (int k = 0; k <= deg; k++) { double tr = nr * zr[i] - ni * zi[i] + cr[k], ti = nr * zi[i] + ni * zr[i]; nr = tr; ni = ti; }
+      double dr = 1, di = 0; for (int j = 0; j < deg; j++) if (j != i) { double ar = zr[i] - zr[j], ai = zi[i] - zi[j]; double tr = dr * ar - di * ai, ti = dr * ai + di * ar; dr = tr; di = ti; }
+      double den = dr * dr + di * di; if (den == 0) { dr = 1e-300; di = 0; den = 1e-600 > 0 ? 1e-300 * 1e-300 : DBL_MIN; }
+      double qr = (nr * dr + ni * di) / den, qi = (ni * dr - nr * di) / den;
+      zr[i] -= qr; zi[i] -= qi; change = fmax(change, sqrt(qr * qr + qi * qi));
+    }
+    if (change < 1e-15 * rad) break;
+  }
+  for (int i = 0; i < deg; i++) out[i] = zr[i];
+  return deg;
+}
+__device__ double d_minimize_interp(const FnSample* s, int ns, double x_min, double x_max) {
+  double coef[6]; int n = d_fit_poly(s, ns, coef);
+  double ox = (x_min + x_max) / 2.0, ov = d_poly_eval(coef, n, ox);
+  double v = d_poly_eval(coef, n, x_min); if (v < ov) { ov = v; ox = x_min; }
+  v = d_poly_eval(coef, n, x_max); if (v < ov) { ov = v; ox = x_max; }
+  if (n <= 2) return ox;
+  double der[5]; int deg = n - 1; for (int i = 0; i < deg; i++) der[i] = (deg - i) * coef[i];
+  double roots[5]; int nr = d_root_real_parts(der, deg, roots);
+  for (int i = 0; i < nr; i++) { double r = roots[i]; if (!(r >= x_min && r <= x_max)) continue; v = d_poly_eval(coef, n, r); if (v < ov) { ov = v; ox = r; } }
+  return ox;
+}
+
+// ------------------------------------------------------------------------------------------------ LM state machine (one thread)
+#define LM_FTOL 1e-6
+#define LM_GTOL 1e-10
+#define LM_PTOL 1e-8
+
+__device__ double lm_gmax(const LmState& L, double bound) {
+  double ng[6], pg[7]; for (int c = 0; c < 6; c++) ng[c] = -L.g[c];
+  d_plus(L.x, ng, bound, pg); double m = 0; for (int k = 0; k < 7; k++) m = fmax(m, fabs(L.x[k] - pg[k])); return m;
+}
+__device__ void lm_finish(LmState& L, int termination) {
+  L.done = 1; L.termination = termination; L.final_cost = fmin(L.initial_cost, L.min_iter_cost);
+}
+// Starts LM iterations until one needs an evaluation (sets L.trial, phase = 1) or the solve terminates.
+__device__ void lm_next_iteration(LmState& L, double bound) {
+  for (;;) {
+    if (L.iteration >= L.max_iterations) { lm_finish(L, 0); return; }
+    if (L.last_successful && L.last_gmax <= LM_GTOL) { lm_finish(L, 1); return; }
+    if (L.radius <= 1e-32) { lm_finish(L, 5); return; }
+    L.iteration++; L.total_iterations++;
+    // LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system
+    if (!L.reuse_diagonal) for (int c = 0; c < 6; c++) { double d = L.H[hidx(c, c)] * L.scaling[c] * L.scaling[c]; L.diagonal[c] = fmin(fmax(d, 1e-6), 1e32); }
+    double A[6][6], rhs[6], Hs[6][6];
+    for (int i = 0; i < 6; i++) { rhs[i] = L.g[i] * L.scaling[i]; for (int j = i; j < 6; j++) { double v = L.H[hidx(i, j)] * L.scaling[i] * L.scaling[j]; Hs[i][j] = v; Hs[j][i] = v; } }
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) A[i][j] = Hs[i][j];
+    for (int c = 0; c < 6; c++) { double d = sqrt(L.diagonal[c] / L.radius); A[c][c] += d * d; }
+    double step[6]; bool solved = d_chol6(A, rhs, step);
+    L.reuse_diagonal = 1;
+    bool valid = false;
+    if (solved) {
+      for (int c = 0; c < 6; c++) step[c] = -step[c];
+      // model_cost_change = -(J s)'(f + J s / 2) = -(s' J'f) - s' J'J s / 2
+      double sg = 0, shs = 0; for (int i = 0; i < 6; i++) { sg += step[i] * rhs[i]; double r = 0; for (int j = 0; j < 6; j++) r += Hs[i][j] * step[j]; shs += step[i] * r; }
+      L.model_cost_change = -sg - 0.5 * shs; valid = L.model_cost_change > 0.0;
+    }
+    if (!valid) {  // HandleInvalidStep
+      if (++L.num_invalid >= 5) { lm_finish(L, 4); return; }
+      L.radius = L.radius / L.decrease_factor; L.decrease_factor *= 2.0; L.reuse_diagonal = 1; L.last_successful = 0; continue;
+    }
+    L.num_invalid = 0;
+    L.gd = 0; L.dmax = 0;
+    for (int c = 0; c < 6; c++) { L.delta[c] = step[c] * L.scaling[c]; L.gd += L.g[c] * L.delta[c]; L.dmax = fmax(L.dmax, fabs(L.delta[c])); }
+    L.ls_iters = 0; L.prev.value_valid = 0; L.prev.gradient_valid = 0; L.ls_alpha = 1.0;
+    d_plus(L.x, L.delta, bound, L.trial); L.phase = 1; return;
+  }
+}
+// Candidate point L.trial evaluated: cost + sums (normal equations at the candidate).
+__device__ void lm_accept_test(LmState& L, const double* sums, double bound) {
+  const double cand_cost = sums[27];
+  double step_norm = 0; for (int k = 0; k < 7; k++) step_norm += (L.x[k] - L.trial[k]) * (L.x[k] - L.trial[k]); step_norm = sqrt(step_norm);
+  if (step_norm <= LM_PTOL * (L.x_norm + LM_PTOL)) { lm_finish(L, 2); return; }
+  const double cost_change = L.x_cost - cand_cost;
+  if (fabs(cost_change) <= LM_FTOL * L.x_cost) { lm_finish(L, 3); return; }
+  const double rel = (L.x_cost - cand_cost) / L.model_cost_change;
+  if (rel > 1e-3) {  // HandleSuccessfulStep
+    for (int k = 0; k < 7; k++) L.x[k] = L.trial[k];
+    double n = 0; for (int k = 0; k < 7; k++) n += L.x[k] * L.x[k]; L.x_norm = sqrt(n);
+    L.x_cost = cand_cost; for (int i = 0; i < 21; i++) L.H[i] = sums[i]; for (int i = 0; i < 6; i++) L.g[i] = sums[21 + i];
+    L.last_gmax = lm_gmax(L, bound); L.last_successful = 1;
+    L.radius = L.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0)); L.radius = fmin(1e16, L.radius);
+    L.decrease_factor = 2.0; L.reuse_diagonal = 0;
+    L.min_iter_cost = fmin(L.min_iter_cost, L.x_cost);
+    if (L.x_cost < L.minimum_cost) { L.minimum_cost = L.x_cost; for (int k = 0; k < 7; k++) L.x_best[k] = L.x[k]; }
+  } else {  // HandleUnsuccessfulStep
+    L.radius = L.radius / L.decrease_factor; L.decrease_factor *= 2.0; L.reuse_diagonal = 1; L.last_successful = 0;
+    L.min_iter_cost = fmin(L.min_iter_cost, cand_cost);
+  }
+  lm_next_iteration(L, bound);
+}
+// One evaluation finished; sums = normal equations at L.trial.
+__device__ __noinline__ void lm_step(LmState& L, const double* sums, double bound) {
+  L.total_evaluations++;
+  if (L.phase == 0) {  // IterationZero
+    for (int k = 0; k < 7; k++) { L.x[k] = L.trial[k]; L.x_best[k] = L.trial[k]; }
+    double n = 0; for (int k = 0; k < 7; k++) n += L.x[k] * L.x[k]; L.x_norm = sqrt(n);
+    L.x_cost = sums[27]; for (int i = 0; i < 21; i++) L.H[i] = sums[i]; for (int i = 0; i < 6; i++) L.g[i] = sums[21 + i];
+    L.n_valid = (int)(sums[28] + 0.5);
+    L.initial_cost = L.x_cost; L.min_iter_cost = L.x_cost; L.minimum_cost = L.x_cost; L.final_cost = L.x_cost;
+    for (int c = 0; c < 6; c++) L.scaling[c] = 1.0 / (1.0 + sqrt(L.H[hidx(c, c)]));
+    L.last_gmax = lm_gmax(L, bound); L.last_successful = 1; L.iteration = 0; L.radius = 1e4; L.decrease_factor = 2.0; L.reuse_diagonal = 0; L.num_invalid = 0;
+    if (L.n_valid == 0) { lm_finish(L, -1); return; }
+    if (!isfinite(L.x_cost)) { lm_finish(L, 4); return; }
+    lm_next_iteration(L, bound); return;
+  }
+  if (L.phase == 1) {  // projected Armijo line search sample at ls_alpha (ArmijoLineSearch::DoSearch, CUBIC interpolation)
+    double gt = 0; for (int c = 0; c < 6; c++) gt += sums[21 + c] * L.delta[c];
+    L.cur.x = L.ls_alpha; L.cur.value = sums[27]; L.cur.gradient = gt; L.cur.value_valid = isfinite(sums[27]) ? 1 : 0; L.cur.gradient_valid = (L.cur.value_valid && isfinite(gt)) ? 1 : 0;
+    if (L.cur.value_valid && !(L.cur.value > L.x_cost + 1e-4 * L.gd * L.cur.x)) {
+      for (int c = 0; c < 6; c++) L.delta[c] *= L.cur.x;   // success: trial == Plus(x, alpha*delta) is the candidate
+      lm_accept_test(L, sums, bound); return;
+    }
+    bool failed = false; double step_size = 0;
+    if (++L.ls_iters >= 20) failed = true;
+    else {
+      const double mn = 1e-3 * L.cur.x, mx = 0.6 * L.cur.x;
+      if (!L.cur.value_valid) step_size = fmin(fmax(L.cur.x * 0.5, mn), mx);
+      else {
+        FnSample s[3]; int ns = 0;
+        s[ns].x = 0; s[ns].value = L.x_cost; s[ns].gradient = L.gd; s[ns].value_valid = 1; s[ns].gradient_valid = 1; ns++;
+        s[ns++] = L.cur; if (L.prev.value_valid) s[ns++] = L.prev;
+        step_size = d_minimize_interp(s, ns, mn, mx);
+      }
+      if (step_size * L.dmax < 1e-9) failed = true;
+    }
+    if (!failed) { L.prev = L.cur; L.ls_alpha = step_size; double sd[6]; for (int c = 0; c < 6; c++) sd[c] = step_size * L.delta[c]; d_plus(L.x, sd, bound, L.trial); return; }
+    // line search failed: delta stays; the candidate is Plus(x, delta)
+    if (L.cur.x == 1.0) { lm_accept_test(L, sums, bound); return; }
+    d_plus(L.x, L.delta, bound, L.trial); L.phase = 2; return;
+  }
+  lm_accept_test(L, sums, bound);  // phase 2
+}
+
+// ------------------------------------------------------------------------------------------------ per-block evaluation
+struct Slot { double px, py, pz, ax, ay, az, vx, vy, vz; int type; };
+
+struct EvalConst {   // uniform per evaluation, in shared memory
+  double x[7];       // trial point: q (x,y,z,w), t
+  double PJ[4][3];   // EigenQuaternionParameterization::ComputeJacobian
+  double Rl[3][3];   // rotation by q_last (columns = q_last * e_k)
+  double tl[3];
+  double huber_a, huber_b;
+};
+
+__device__ __forceinline__ void cross3(double ax, double ay, double az, double bx, double by, double bz, double& ox, double& oy, double& oz) {
+  ox = ay * bz - az * by; oy = az * bx - ax * bz; oz = ax * by - ay * bx;
+}
+// residual (3), optional Jacobian (3 x 6, tangent space), returns rho' (Huber weight) and adds 0.5*rho to *cost
+__device__ __forceinline__ void eval_block(const Slot& s, const EvalConst& E, double r[3], double J[6][3], bool want_j) {
+  const double ux = E.x[0], uy = E.x[1], uz = E.x[2], w = E.x[3];
+  double cx, cy, cz; cross3(ux, uy, uz, s.px, s.py, s.pz, cx, cy, cz); cx += cx; cy += cy; cz += cz;   // 2 (u x p)
+  double ex, ey, ez; cross3(ux, uy, uz, cx, cy, cz, ex, ey, ez);
+  const double yx = s.px + w * cx + ex + E.x[4], yy = s.py + w * cy + ey + E.x[5], yz = s.pz + w * cz + ez + E.x[6];
+  const double dx = E.Rl[0][0] * yx + E.Rl[0][1] * yy + E.Rl[0][2] * yz + E.tl[0] - s.ax;
+  const double dy = E.Rl[1][0] * yx + E.Rl[1][1] * yy + E.Rl[1][2] * yz + E.tl[1] - s.ay;
+  const double dz = E.Rl[2][0] * yx + E.Rl[2][1] * yy + E.Rl[2][2] * yz + E.tl[2] - s.az;
+  const double dv = dx * s.vx + dy * s.vy + dz * s.vz;
+  const bool line = s.type == 1;
+  if (line) { r[0] = dx - dv * s.vx; r[1] = dy - dv * s.vy; r[2] = dz - dv * s.vz; }
+  else { r[0] = dv * s.vx; r[1] = dv * s.vy; r[2] = dv * s.vz; }
+  if (!want_j) return;
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    double gx, gy, gz;   // derivative of y = q_incre * p + t_incre along tangent direction c
+    if (c < 3) {
+      const double dux = E.PJ[0][c], duy = E.PJ[1][c], duz = E.PJ[2][c], dw = E.PJ[3][c];
+      double ax, ay, az; cross3(dux, duy, duz, s.px, s.py, s.pz, ax, ay, az); ax += ax; ay += ay; az += az;  // 2 (du x p)
+      double bx, by, bz; cross3(dux, duy, duz, cx, cy, cz, bx, by, bz);                                       // du x 2(u x p)
+      double fx, fy, fz; cross3(ux, uy, uz, ax, ay, az, fx, fy, fz);                                          // u x 2(du x p)
+      gx = dw * cx + w * ax + bx + fx; gy = dw * cy + w * ay + by + fy; gz = dw * cz + w * az + bz + fz;
+    } else { gx = c == 3 ? 1.0 : 0.0; gy = c == 4 ? 1.0 : 0.0; gz = c == 5 ? 1.0 : 0.0; }
+    const double e0 = E.Rl[0][0] * gx + E.Rl[0][1] * gy + E.Rl[0][2] * gz;
+    const double e1 = E.Rl[1][0] * gx + E.Rl[1][1] * gy + E.Rl[1][2] * gz;
+    const double e2 = E.Rl[2][0] * gx + E.Rl[2][1] * gy + E.Rl[2][2] * gz;
+    const double ev = e0 * s.vx + e1 * s.vy + e2 * s.vz;
+    if (line) { J[c][0] = e0 - ev * s.vx; J[c][1] = e1 - ev * s.vy; J[c][2] = e2 - ev * s.vz; }
+    else { J[c][0] = ev * s.vx; J[c][1] = ev * s.vy; J[c][2] = ev * s.vz; }
+  }
+}
+__device__ __forceinline__ double huber_weight(double sq, double a, double b, double& rho0) {
+  if (sq > b) { double r = sqrt(sq); rho0 = 2.0 * a * r - b; return fmax(DBL_MIN, a / r); }
+  rho0 = sq; return 1.0;
+}
+
+__device__ void setup_const(EvalConst& E, const double* x, const RegDevState* st) {
+  for (int k = 0; k < 7; k++) E.x[k] = x[k];
+  E.PJ[0][0] = x[3];  E.PJ[0][1] = x[2];  E.PJ[0][2] = -x[1];
+  E.PJ[1][0] = -x[2]; E.PJ[1][1] = x[3];  E.PJ[1][2] = x[0];
+  E.PJ[2][0] = x[1];  E.PJ[2][1] = -x[0]; E.PJ[2][2] = x[3];
+  E.PJ[3][0] = -x[0]; E.PJ[3][1] = -x[1]; E.PJ[3][2] = -x[2];
+  const double* ql = st->pose_last;
+  for (int k = 0; k < 3; k++) { double e[3] = {k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0}, o[3]; d_qrot(ql, e, o); E.Rl[0][k] = o[0]; E.Rl[1][k] = o[1]; E.Rl[2][k] = o[2]; }
+  E.tl[0] = st->pose_last[4]; E.tl[1] = st->pose_last[5]; E.tl[2] = st->pose_last[6];
+  E.huber_a = st->huber_a; E.huber_b = st->huber_a * st->huber_a;
+}
+
+// ------------------------------------------------------------------------------------------------ the persistent kernel
+// Residual blocks are staged ONCE into shared memory (SoA: 52 B per block) and stay there for the whole solve.
+// CTA b owns the 512-slot tiles b, b + grid, b + 2 grid, ...  (coalesced staging, balanced over the SMs).
+struct SmemSlots { float* p[3]; float* a[3]; double* v[3]; int* type; };
+__device__ __forceinline__ SmemSlots carve(unsigned char* base, int cap) {
+  SmemSlots s; double* d = (double*)base;
+  s.v[0] = d; s.v[1] = d + cap; s.v[2] = d + 2 * cap;
+  float* f = (float*)(d + 3 * (size_t)cap);
+  s.p[0] = f; s.p[1] = f + cap; s.p[2] = f + 2 * cap; s.a[0] = f + 3 * cap; s.a[1] = f + 4 * cap; s.a[2] = f + 5 * cap;
+  s.type = (int*)(f + 6 * (size_t)cap);
+  return s;
+}
+#define SLOT_BYTES 52
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a, int tiles_per_cta) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ EvalConst E;
+  __shared__ double s_red[SOLVE_THREADS / 32][NSUM + 1];
+  __shared__ double s_sum[32];
+  __shared__ int s_flag;
+  RegDevState* st = a.st;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cap = tiles_per_cta * SOLVE_THREADS;
+  const SmemSlots S = carve(s_dyn, cap);
+
+  // ---- stage this CTA's residual blocks
+  double thr = 0;
+  if (a.mode == 1) {   // K10 tail: threshold = max(inliner_dis, element floor(ratio * n_unique) of the sorted unique L1 norms)
+    int nu = *a.d_n_unique;
+    if (nu > 0 && !isfinite(a.l1_sorted_unique[nu - 1])) nu--;   // the +inf of invalid slots is not a residual
+    int k = (int)(st->inlier_ratio * (double)nu);
+    double rt = nu > 0 ? a.l1_sorted_unique[k < nu ? k : nu - 1] : 0.0;
+    thr = fmax(st->inliner_dis, rt);
+    if (blockIdx.x == 0 && tid == 0) st->inlier_threshold = thr;
+  }
+  for (int k = 0; k < tiles_per_cta; k++) {
+    const int i = (blockIdx.x + gridDim.x * k) * SOLVE_THREADS + tid, li = k * SOLVE_THREADS + tid;
+    int type = 0;
+    if (i < a.M) {
+      const float4 ba = a.blk_a[i]; type = __float_as_int(ba.w);
+      if (type != 0 && a.mode == 1 && (a.l1[i] > thr)) type = 0;
+      if (type != 0) {
+        const float4 f = a.feat[i];
+        S.p[0][li] = f.x; S.p[1][li] = f.y; S.p[2][li] = f.z; S.a[0][li] = ba.x; S.a[1][li] = ba.y; S.a[2][li] = ba.z;
+        S.v[0][li] = a.blk_v[(size_t)i * 3]; S.v[1][li] = a.blk_v[(size_t)i * 3 + 1]; S.v[2][li] = a.blk_v[(size_t)i * 3 + 2];
+      }
+    }
+    S.type[li] = type;
+  }
+  // ---- iteration zero trial point: Plus(x, 0) == projection onto the bounds (every CTA computes the same value)
+  unsigned gen = ld_acquire_u32(&st->bar_gen);
+  if (tid == 0) {
+    double x0[7], z[6] = {0, 0, 0, 0, 0, 0}, tr[7];
+    for (int k = 0; k < 7; k++) x0[k] = st->x[k];
+    d_plus(x0, z, st->bound, tr);
+    setup_const(E, tr, st);
+    s_flag = 0;
+  }
+  __syncthreads();
+
+  for (;;) {
+    // ---- evaluate: r, J, Huber, 29 partial sums per thread
+    double acc[NSUM];
+#pragma unroll
+    for (int i = 0; i < NSUM; i++) acc[i] = 0.0;
+    for (int k = 0; k < tiles_per_cta; k++) {
+      const int li = k * SOLVE_THREADS + tid;
+      Slot s; s.type = S.type[li];
+      if (s.type != 0) {
+        s.px = S.p[0][li]; s.py = S.p[1][li]; s.pz = S.p[2][li]; s.ax = S.a[0][li]; s.ay = S.a[1][li]; s.az = S.a[2][li];
+        s.vx = S.v[0][li]; s.vy = S.v[1][li]; s.vz = S.v[2][li];
+        double r[3], J[6][3]; eval_block(s, E, r, J, true);
+        double rho0; const double wgt = huber_weight(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], E.huber_a, E.huber_b, rho0);
+        acc[27] += 0.5 * rho0; acc[28] += 1.0;
+        int h = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          acc[21 + i] += wgt * (J[i][0] * r[0] + J[i][1] * r[1] + J[i][2] * r[2]);
+#pragma unroll
+          for (int j = i; j < 6; j++) { acc[h] += wgt * (J[i][0] * J[j][0] + J[i][1] * J[j][1] + J[i][2] * J[j][2]); h++; }
+        }
+      }
+    }
+    // ---- CTA reduce: warp shuffles, then shared memory, fixed order
+#pragma unroll
+    for (int i = 0; i < NSUM; i++) {
+      double v = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      if (lane == 0) s_red[warp][i] = v;
+    }
+    __syncthreads();
+    if (tid < NSUM) {
+      double v = 0; for (int wq = 0; wq < SOLVE_THREADS / 32; wq++) v += s_red[wq][tid];
+      a.partials[(size_t)blockIdx.x * 32 + tid] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    // ---- ticket barrier: the last CTA reduces the grid and advances the solver
+    if (tid == 0) { unsigned t = atomicAdd(&st->bar_count, 1u); s_flag = (t == gridDim.x - 1) ? 1 : 0; }
+    __syncthreads();
+    if (s_flag) {
+      __threadfence();
+      const int val = tid & 31, grp = tid >> 5;   // 16 groups x 32 values
+      double v = 0;
+      if (val < NSUM) for (int b = grp; b < (int)gridDim.x; b += SOLVE_THREADS / 32) v += __ldcg(&a.partials[(size_t)b * 32 + val]);
+      if (val < NSUM) s_red[grp][val] = v;
+      __syncthreads();
+      if (tid < NSUM) { double t = 0; for (int g = 0; g < SOLVE_THREADS / 32; g++) t += s_red[g][tid]; s_sum[tid] = t; }
+      __syncthreads();
+      if (a.world > 1 && warp == 0) {
+        // fused all-reduce over NVLink peer memory: every rank writes its 29 sums into slot [rank] of every peer's staging
+        // buffer (double-buffered by generation parity), then sums the slots in rank order -> bit-identical on all ranks.
+        const unsigned g1 = gen + 1; const int par = g1 & 1;
+        for (int p = 0; p < a.world; p++) {
+          double* dst = a.comm_peer[p] + ((size_t)par * 8 + a.rank) * 64;
+          if (lane < NSUM) dst[lane] = s_sum[lane];
+        }
+        __threadfence_system();
+        __syncwarp();
+        if (lane < a.world) st_release_sys_u32((unsigned*)(a.comm_peer[lane] + ((size_t)par * 8 + a.rank) * 64 + 32), g1);
+        if (lane < a.world) { const unsigned* f = (const unsigned*)(a.comm_local + ((size_t)par * 8 + lane) * 64 + 32); while (ld_acquire_sys_u32(f) != g1) {} }
+        __syncwarp();
+        double t = 0;
+        if (lane < NSUM) for (int p = 0; p < a.world; p++) t += *((volatile double*)(a.comm_local + ((size_t)par * 8 + p) * 64 + lane));
+        if (lane < NSUM) s_sum[lane] = t;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        LmState& L = st->lm;
+        if (a.mode == 3) { for (int i = 0; i < 21; i++) L.H[i] = s_sum[i]; for (int i = 0; i < 6; i++) L.g[i] = s_sum[21 + i]; L.x_cost = s_sum[27]; L.n_valid = (int)(s_sum[28] + 0.5); L.done = 1; }
+        else lm_step(L, s_sum, st->bound);
+        if (L.done && a.mode != 3) {
+          for (int k = 0; k < 7; k++) st->x[k] = L.x_best[k];
+          st->total_lm_iterations += L.iteration; st->total_evaluations += L.total_evaluations;
+          if (a.mode == 1) {   // :514-531 pose composition + ICP termination test
+            double qi[4] = {L.x_best[3], L.x_best[0], L.x_best[1], L.x_best[2]}, ti[3] = {L.x_best[4], L.x_best[5], L.x_best[6]};
+            const double* ql = st->pose_last; double tcur[3], qcur[4];
+            d_qrot(ql, ti, tcur); for (int k = 0; k < 3; k++) tcur[k] += st->pose_last[4 + k];
+            d_qmul(ql, qi, qcur);
+            for (int k = 0; k < 4; k++) st->pose_curr[k] = qcur[k]; for (int k = 0; k < 3; k++) st->pose_curr[4 + k] = tcur[k];
+            st->angular_diff = (double)((float)d_angdist(qcur, ql)) * 57.3;
+            double td = 0; for (int k = 0; k < 3; k++) td += (tcur[k] - st->pose_last[4 + k]) * (tcur[k] - st->pose_last[4 + k]); st->t_diff = sqrt(td);
+            st->final_cost = L.final_cost; st->initial_cost = L.initial_cost; st->num_residual_blocks = L.n_valid;
+            double dt = 0; for (int k = 0; k < 3; k++) dt += (st->t_last_opt[k] - ti[k]) * (st->t_last_opt[k] - ti[k]);
+            if (d_angdist(st->q_last_opt, qi) < 57.3 * st->min_icp_R && sqrt(dt) < st->min_icp_T) st->icp_done = 1;
+            else { for (int k = 0; k < 4; k++) st->q_last_opt[k] = qi[k]; for (int k = 0; k < 3; k++) st->t_last_opt[k] = ti[k]; }
+            st->icp_iter++;
+          }
+        }
+        st->bar_count = 0;
+        __threadfence();
+        st_release_u32(&st->bar_gen, gen + 1);
+      }
+    } else {
+      if (tid == 0) { while (ld_acquire_u32(&st->bar_gen) != gen + 1) { __nanosleep(20); } }
+    }
+    gen++;
+    __syncthreads();
+    // ---- everyone picks up the next trial point (or the final x)
+    if (tid == 0) {
+      const volatile LmState* L = &st->lm;
+      s_flag = L->done;
+      double tr[7];
+      if (L->done) for (int k = 0; k < 7; k++) tr[k] = ((const volatile double*)st->x)[k];
+      else for (int k = 0; k < 7; k++) tr[k] = L->trial[k];
+      setup_const(E, tr, st);
+    }
+    __syncthreads();
+    if (s_flag) break;
+  }
+  // ---- epilogue of solve #1: loss-corrected L1 norm of every block at the solution (problem.Evaluate, :476-481)
+  if (a.mode == 0) {
+    for (int k = 0; k < tiles_per_cta; k++) {
+      const int i = (blockIdx.x + gridDim.x * k) * SOLVE_THREADS + tid, li = k * SOLVE_THREADS + tid;
+      if (i < a.M) {
+        double l1 = INFINITY;
+        Slot s; s.type = S.type[li];
+        if (s.type != 0) {
+          s.px = S.p[0][li]; s.py = S.p[1][li]; s.pz = S.p[2][li]; s.ax = S.a[0][li]; s.ay = S.a[1][li]; s.az = S.a[2][li];
+          s.vx = S.v[0][li]; s.vy = S.v[1][li]; s.vz = S.v[2][li];
+          double r[3], J[6][3]; eval_block(s, E, r, J, false);
+          double rho0; const double wgt = huber_weight(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], E.huber_a, E.huber_b, rho0);
+          const double sc = sqrt(wgt);
+          l1 = fabs(sc * r[0]) + fabs(sc * r[1]) + fabs(sc * r[2]);
+        }
+        a.l1[i] = l1;
+      }
+    }
+  }
+}
+
+__global__ void lm_reset_kernel(RegDevState* st, int max_iterations) {
+  LmState& L = st->lm;
+  L.phase = 0; L.iteration = 0; L.max_iterations = max_iterations; L.num_invalid = 0; L.done = 0; L.termination = 0; L.last_successful = 1; L.reuse_diagonal = 0;
+  L.ls_iters = 0; L.n_valid = 0; L.total_iterations = 0; L.total_evaluations = 0;
+  st->bar_count = 0;
+}
+
+#define SOLVE_MAX_SMEM (200 * 1024)
+int solve_max_slots(ll_ctx* ctx) { return ctx->num_sms * ((SOLVE_MAX_SMEM / SLOT_BYTES) / SOLVE_THREADS) * SOLVE_THREADS; }
+
+int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
+  static bool attr_set[64] = {false};
+  const int grid = ctx->num_sms;
+  const int tiles = ll_div_up(a.M > 0 ? a.M : 1, SOLVE_THREADS);
+  int tiles_per_cta = ll_div_up(tiles, grid);
+  const size_t smem = (size_t)tiles_per_cta * SOLVE_THREADS * SLOT_BYTES;
+  if (smem > SOLVE_MAX_SMEM) { ctx->set_error("too many residual-block slots for the shared-memory-resident solver"); return LL_ERR_CAPACITY; }
+  if (ctx->device < 64 && !attr_set[ctx->device]) {
+    LL_CUDA(ctx, cudaFuncSetAttribute(lm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_MAX_SMEM));
+    attr_set[ctx->device] = true;
+  }
+  lm_reset_kernel<<<1, 1, 0, ctx->stream>>>(a.st, a.max_iterations); ctx->launches++;
+  SolveArgs args = a; void* kargs[] = {&args, &tiles_per_cta};
+  LL_CUDA(ctx, cudaLaunchCooperativeKernel((void*)lm_solve_kernel, dim3(grid), dim3(SOLVE_THREADS), kargs, smem, ctx->stream));
+  ctx->launches++;
+  return LL_OK;
+}

@@ -111,10 +111,11 @@ struct Extractor {
   }
 
   static float vector_angle_sharp(const float a[3], const float b[3]) {  // tools_eigen_math.hpp:25-46 (force sharp)
-    float an = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-    float bn = std::sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+    // Eigen's unrolled reduction of a 3-vector (redux_novec_unroller) associates as x + (y + z)
+    float an = std::sqrt(a[0] * a[0] + (a[1] * a[1] + a[2] * a[2]));
+    float bn = std::sqrt(b[0] * b[0] + (b[1] * b[1] + b[2] * b[2]));
     if (an == 0 || bn == 0) return 0.0f;
-    float d = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+    float d = a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]);
     // reference: acosf() of libm (version-dependent last ulp). The oracle pins it to the correctly
     // rounded value, (float)acos((double)c), which is what the CUDA path evaluates as well.
     return (float)std::acos((double)(std::fabs(d) / (an * bn)));

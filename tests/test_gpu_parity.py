@@ -1,0 +1,221 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
+
+Bars: bit-exact for integer / index / fp32 work (masks, labels, voxel centroids, neighbour ids and fp32 squared
+distances); fp64 solver quantities to 1e-9 relative; final pose within north_star's 1e-4 m / 1e-4 rad.
+"""
+import numpy as np
+import pytest
+
+from loam_livox_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(nc, ns, qc, qs, seed=0):
+    mc, ms = S.make_map(nc, ns, seed=S.SEED + seed)
+    pose = S.default_pose()
+    fc, fs = S.make_features(qc, qs, pose, seed=S.SEED + seed)
+    return mc, ms, fc, fs, pose
+
+
+# ---------------------------------------------------------------------------------------------- K5/K6 kNN
+@pytest.mark.parametrize("n_map,nq", [(40, 64), (1000, 500), (45000, 4000), (300000, 20000)])
+def test_knn_bit_exact(ctx, oracle, n_map, nq):
+    from loam_livox_b200.registration import Map
+    mc, ms = S.make_map(max(n_map // 9, 8), n_map)
+    rng = np.random.default_rng(n_map)
+    q = ms[rng.integers(0, ms.shape[0], nq)].copy()
+    q[:, :3] += rng.normal(0, 0.05, (nq, 3)).astype(np.float32)
+    m = Map(ctx, mc, ms)
+    idx, d2 = m.nearestKSearch(1, q)
+    tree = oracle.KdTree(ms)
+    oi, od, _ = tree.knn(q)
+    assert np.array_equal(d2, od), "fp32 squared distances must be bit-exact (FLANN L2_Simple order)"
+    assert np.array_equal(idx, oi)
+    idxc, d2c = m.nearestKSearch(0, q[: min(nq, 200)])
+    bi, bd, _ = oracle.knn_brute(mc, q[: min(nq, 200)])
+    assert np.array_equal(d2c, bd) and np.array_equal(idxc, bi)
+
+
+def test_knn_edge_cases(ctx, oracle):
+    from loam_livox_b200.registration import Map
+    rng = np.random.default_rng(5)
+    # fewer than 5 points, duplicates (ties), NaN points in the map, far-away queries
+    ms = rng.normal(0, 1, (3, 4)).astype(np.float32)
+    mc = np.concatenate([rng.normal(0, 1, (50, 4)), np.full((3, 4), np.nan)]).astype(np.float32)
+    mc[10:20] = mc[0]   # exact duplicates -> ties broken by index
+    m = Map(ctx, mc, ms)
+    q = rng.normal(0, 3, (100, 4)).astype(np.float32)
+    idx, d2 = m.nearestKSearch(1, q)
+    bi, bd, _ = oracle.knn_brute(ms, q)
+    assert np.array_equal(idx, bi) and np.array_equal(d2, bd)
+    assert (idx[:, 3:] == -1).all() and np.isinf(d2[:, 3:]).all()
+    idx, d2 = m.nearestKSearch(0, q)
+    bi, bd, _ = oracle.knn_brute(mc, q)
+    assert np.array_equal(idx, bi) and np.array_equal(d2, bd)
+
+
+# ---------------------------------------------------------------------------------------------- K4 VoxelGrid
+@pytest.mark.parametrize("n,leaf", [(1, 0.4), (1000, 0.1), (50000, 0.4), (200000, 0.05)])
+def test_voxel_grid_bit_exact(ctx, oracle, n, leaf):
+    from loam_livox_b200.registration import voxel_grid_filter
+    _, ms = S.make_map(8, n, seed=n)
+    ms[:, 3] = np.random.default_rng(n).uniform(0, 0.1, n)
+    if n > 10:
+        ms[3, 0] = np.nan
+    out = voxel_grid_filter(ctx, ms, leaf)
+    ref = oracle.voxel_grid(ms, leaf)
+    assert out.shape == ref.shape
+    assert np.array_equal(out, ref)
+
+
+def test_voxel_grid_overflow_passthrough(ctx, oracle):
+    from loam_livox_b200.registration import voxel_grid_filter
+    rng = np.random.default_rng(3)
+    p = rng.uniform(-1000, 1000, (500, 4)).astype(np.float32)
+    out = voxel_grid_filter(ctx, p, 0.001)   # (2e6)^3 voxels overflow int32 -> PCL passes the input through
+    assert np.array_equal(out, oracle.voxel_grid(p, 0.001)) and out.shape[0] == 500
+
+
+# ---------------------------------------------------------------------------------------------- K1-K3 extractor
+@pytest.mark.parametrize("n", [10000, 100000])
+def test_extractor_bit_exact(ctx, oracle, n):
+    from loam_livox_b200.registration import Livox_laser
+    sc = S.make_scan(n)
+    sc[50:53, :3] = 0.0          # a run of zero returns
+    sc[200, :3] = np.nan
+    sc[201, :3] = 0.0            # zero return right after a NaN
+    ex = oracle.Extractor()
+    gl = Livox_laser(ctx)
+    for k, stamp in enumerate((100.0, 100.1)):   # two frames: exercises the timestamp bookkeeping
+        ns_o = ex.extract(sc, stamp)
+        ns_g = gl.extract_laser_features(sc, stamp)
+        assert ns_g == ns_o
+        io, ig = ex.point_info(), gl.point_info()
+        for key in ("pt_type", "pt_label", "polar_direction"):
+            assert np.array_equal(io[key], ig[key]), key
+        for key in ("curvature", "view_angle", "depth_sq2", "time_stamp", "polar_dis_sq2"):
+            assert np.array_equal(io[key], ig[key], equal_nan=True), key
+        assert np.array_equal(ex.split_idx(), gl.split_idx())
+        so, eo = ex.piece_bounds(3)
+        sg, eg = gl.piece_bounds(3)
+        assert np.array_equal(so, sg) and np.array_equal(eo, eg)
+        for (a, b) in ((0.0, 1.0), (float(so[1]), float(eo[1]))):
+            co, su, fu = ex.get_features(a, b)
+            cg, sg2, fg = gl.get_features(a, b)
+            assert np.array_equal(co, cg) and np.array_equal(su, sg2) and np.array_equal(fu, fg, equal_nan=True)
+            assert co.shape[0] > 0 and su.shape[0] > 100
+
+
+# ---------------------------------------------------------------------------------------------- K6-K10 pieces
+def test_blocks_normal_equations_and_solve(ctx, oracle):
+    from loam_livox_b200.registration import Map, Point_cloud_registration
+    mc, ms, fc, fs, pose = _mk(5000, 45000, 1000, 9000)
+    guess = S.perturb_pose(pose, np.random.default_rng(1))
+    m = Map(ctx, mc, ms)
+    reg = Point_cloud_registration(ctx)
+    reg.set_pose(guess.q, guess.t)
+    typ, a3, v3, ca, sa = reg.build_blocks(m, fc, fs)
+    tc, ts = oracle.KdTree(mc), oracle.KdTree(ms)
+    p = oracle.default_params(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t)
+    blocks, src, oca, osa = oracle.build_blocks(mc, tc, ms, ts, fc, fs, p)
+    assert (ca, sa) == (oca, osa)
+    slot = src[:, 1] + np.where(src[:, 0] == 1, fc.shape[0], 0)
+    assert np.array_equal(np.nonzero(typ)[0], slot)
+    assert np.array_equal(typ[slot], blocks[:, 0].astype(np.int32) + 1)
+    assert np.array_equal(a3[slot], blocks[:, 4:7])
+    assert np.allclose(v3[slot], blocks[:, 7:10], rtol=0, atol=1e-15)
+    # normal equations at a non-trivial x
+    d = np.array([0.01, -0.02, 0.015, 0.05, -0.04, 0.03])
+    x = oracle.plus([0, 0, 0, 1, 0, 0, 0], d)
+    H, g, cost = reg.normal_equations(x)
+    oc, og, oH = oracle.evaluate(blocks, guess.q, guess.t, x)
+    assert abs(cost - oc) <= 1e-10 * abs(oc)
+    assert np.allclose(g, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
+    assert np.allclose(H, oH, rtol=1e-9, atol=1e-9 * np.abs(oH).max())
+    # one ceres::Solve-equivalent
+    for iters in (2, 50):
+        xg, ic, fcst, it = reg.solve([0, 0, 0, 1, 0, 0, 0], iters)
+        xo, so = oracle.solve(blocks, guess.q, guess.t, [0, 0, 0, 1, 0, 0, 0], iters)
+        assert it == int(so["iterations"])
+        assert abs(ic - so["initial_cost"]) <= 1e-10 * so["initial_cost"] and abs(fcst - so["final_cost"]) <= 1e-9 * so["final_cost"]
+        assert np.allclose(xg, xo, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("cfg", [(5000, 45000, 1000, 9000), (20000, 180000, 3000, 27000)])
+def test_register_pose_parity(ctx, oracle, cfg):
+    from loam_livox_b200.registration import Map, Point_cloud_registration
+    mc, ms, fc, fs, pose = _mk(*cfg)
+    m = Map(ctx, mc, ms)
+    tc, ts = oracle.KdTree(mc), oracle.KdTree(ms)
+    for seed in range(3):
+        guess = S.perturb_pose(pose, np.random.default_rng(seed))
+        reg = Point_cloud_registration(ctx)
+        reg.set_pose(guess.q, guess.t)
+        st = reg.find_out_incremental_transfrom(m, fc, fs)
+        p = oracle.default_params(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t)
+        ost, ores = oracle.register(mc, tc, ms, ts, fc, fs, p)
+        r = reg.result
+        assert st == ost == 1 and r.registered == 1
+        assert r.icp_iterations == ores.icp_iterations
+        assert (r.corner_used, r.surf_used, r.num_residual_blocks) == (ores.corner_used, ores.surf_used, ores.num_residual_blocks)
+        dt = np.linalg.norm(np.array(r.t_w_curr) - np.array(ores.t_w_curr))
+        da = S.quat_angle(np.array(r.q_w_curr), np.array(ores.q_w_curr))
+        assert dt < 1e-4 and da < 1e-4, (dt, da)          # north_star tolerance
+        assert dt < 1e-7 and da < 1e-7, (dt, da)          # what we actually expect
+        assert abs(r.final_cost - ores.final_cost) <= 1e-7 * ores.final_cost
+        assert abs(r.inlier_threshold - ores.inlier_threshold) <= 1e-7 * ores.inlier_threshold
+        # and the registration recovers the injected motion
+        assert np.linalg.norm(np.array(r.t_w_curr) - pose.t) < 5e-3 and S.quat_angle(np.array(r.q_w_curr), pose.q) < 1e-3
+
+
+def test_register_gate_and_reject(ctx, oracle):
+    from loam_livox_b200.registration import Map, Point_cloud_registration
+    mc, ms, fc, fs, pose = _mk(500, 4500, 200, 1800)
+    m = Map(ctx, mc, ms)
+    # first frames: returns 1 without registering (:199)
+    reg = Point_cloud_registration(ctx, current_frame_index=10)
+    reg.set_pose(pose.q, pose.t)
+    assert reg.find_out_incremental_transfrom(m, fc, fs) == 1 and reg.result.registered == 0
+    assert np.allclose(reg.m_t_w_curr, pose.t)
+    # reject gate on the final cost (:561-573): pose reverted, status 0
+    guess = S.perturb_pose(pose, np.random.default_rng(2))
+    reg = Point_cloud_registration(ctx, max_final_cost=1e-9)
+    reg.set_pose(guess.q, guess.t)
+    assert reg.find_out_incremental_transfrom(m, fc, fs) == 0
+    assert np.allclose(reg.m_t_w_curr, guess.t) and np.allclose(reg.m_q_w_curr, guess.q)
+
+
+def test_transform_bit_exact(ctx, oracle):
+    from loam_livox_b200.registration import Point_cloud_registration
+    pose = S.default_pose()
+    _, fs = S.make_features(10, 5000, pose)
+    reg = Point_cloud_registration(ctx)
+    out = reg.pointcloudAssociateToMap(fs, pose.q, pose.t)
+    assert np.array_equal(out, oracle.transform(fs, pose.q, pose.t))
+
+
+# ---------------------------------------------------------------------------------------------- whole per-scan step
+def test_scan_to_pose_matches_staged_oracle(ctx, oracle):
+    from loam_livox_b200 import capi
+    from loam_livox_b200.registration import Map, scan_to_pose
+    pose = S.default_pose()
+    mc, ms = S.make_map(20000, 200000)
+    raw = S.make_scan(20000, pose)
+    m = Map(ctx, mc, ms)
+    guess = S.perturb_pose(pose, np.random.default_rng(4), dt=0.05, dang_deg=1.0)
+    pc = capi.PipelineCfg(pieces=3, use_piece=0, extractor_leaf_corner=0.1, extractor_leaf_surf=0.2, mapping_leaf_corner=0.1, mapping_leaf_surf=0.4, whole_frame=1)
+    st = capi.default_reg_state(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t)
+    res, nc, ns = scan_to_pose(ctx, m, raw, 100.0, pc, st)
+    # oracle, stage by stage
+    ex = oracle.Extractor()
+    ex.extract(raw, 100.0)
+    c, s, _ = ex.get_features(0.0, 1.0)
+    c = oracle.voxel_grid(oracle.voxel_grid(c, 0.1), 0.1)
+    s = oracle.voxel_grid(oracle.voxel_grid(s, 0.2), 0.4)
+    assert (nc, ns) == (c.shape[0], s.shape[0])
+    p = oracle.default_params(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t)
+    ost, ores = oracle.register(mc, oracle.KdTree(mc), ms, oracle.KdTree(ms), c, s, p)
+    assert res.status == ost and res.icp_iterations == ores.icp_iterations
+    assert np.linalg.norm(np.array(res.t_w_curr) - np.array(ores.t_w_curr)) < 1e-6
+    assert S.quat_angle(np.array(res.q_w_curr), np.array(ores.q_w_curr)) < 1e-6
