@@ -73,6 +73,8 @@ int  ll_ctx_sync(ll_ctx* ctx);
  * *n_scans receives laserCloudScans.size() (the caller drops the frame when it is <= 5,
  * laser_feature_extractor.hpp:287).  Per-scan state stays on the device for ll_get_features. */
 int ll_extract(ll_ctx* ctx, const void* raw, size_t n, int fmt, int where, double stamp, int* n_scans);
+/* Forget the cross-scan state of the extractor (m_first_receive_time, m_last_maximum_time_stamp): a fresh Livox_laser object. */
+int ll_extract_reset(ll_ctx* ctx);
 /* Piece bounds of laser_feature_extractor.hpp:313-323 (fraction of the frame covered by each piece). */
 int ll_piece_bounds(ll_ctx* ctx, int pieces, float* start, float* end);
 /* Replaces Livox_laser::get_features (livox_feature_extractor.hpp:219-272).  Host outputs, each sized n. */

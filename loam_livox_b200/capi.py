@@ -19,7 +19,7 @@ LL_OK, LL_ERR_INVALID, LL_ERR_CUDA, LL_ERR_CAPACITY, LL_ERR_NO_BLOCKS, LL_ERR_CA
 LL_IPC_HANDLE_BYTES = 64
 
 EXPORTS = [
-    "ll_config_default", "ll_ctx_create", "ll_ctx_destroy", "ll_last_error", "ll_ctx_stream", "ll_ctx_sync", "ll_extract", "ll_piece_bounds",
+    "ll_config_default", "ll_ctx_create", "ll_ctx_destroy", "ll_last_error", "ll_ctx_stream", "ll_ctx_sync", "ll_extract", "ll_extract_reset", "ll_piece_bounds",
     "ll_get_features", "ll_extract_point_info", "ll_extract_split_idx", "ll_voxel_downsample", "ll_map_build", "ll_map_release", "ll_map_size",
     "ll_map_build_sharded", "ll_knn", "ll_reg_state_default", "ll_register", "ll_build_blocks", "ll_normal_equations", "ll_solve", "ll_transform",
     "ll_scan_to_pose", "ll_comm_local_handle", "ll_comm_connect", "ll_launch_count",
@@ -79,6 +79,7 @@ def lib():
     L.ll_ctx_stream.restype = vp
     L.ll_ctx_sync.argtypes = [vp]
     L.ll_extract.argtypes = [vp, vp, sz, ci, ci, cd, C.POINTER(ci)]
+    L.ll_extract_reset.argtypes = [vp]
     L.ll_piece_bounds.argtypes = [vp, ci, vp, vp]
     L.ll_get_features.argtypes = [vp, cf, cf, vp, C.POINTER(sz), vp, C.POINTER(sz), vp, C.POINTER(sz)]
     L.ll_extract_point_info.argtypes = [vp] + [vp] * 8

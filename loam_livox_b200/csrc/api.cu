@@ -110,6 +110,11 @@ int ll_extract(ll_ctx* ctx, const void* raw, size_t n, int fmt, int where, doubl
   }
   return LL_OK;
 }
+int ll_extract_reset(ll_ctx* ctx) {
+  if (!ctx) return LL_ERR_INVALID;
+  ctx->ex.first_receive_time = -1; ctx->ex.current_time = 0; ctx->ex.last_maximum_time_stamp = 0; ctx->ex.n = 0;
+  return LL_OK;
+}
 int ll_piece_bounds(ll_ctx* ctx, int pieces, float* start, float* end) {
   if (!ctx || pieces < 1 || pieces > 16) return LL_ERR_INVALID;
   cudaSetDevice(ctx->device);

@@ -358,12 +358,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
     }
     S.type[li] = type;
   }
-  // ---- iteration zero trial point: Plus(x, 0) == projection onto the bounds (every CTA computes the same value)
+  // ---- iteration zero trial point
   unsigned gen = ld_acquire_u32(&st->bar_gen);
   if (tid == 0) {
-    double x0[7], z[6] = {0, 0, 0, 0, 0, 0}, tr[7];
-    for (int k = 0; k < 7; k++) x0[k] = st->x[k];
-    d_plus(x0, z, st->bound, tr);
+    double tr[7];
+    for (int k = 0; k < 7; k++) tr[k] = st->lm.trial[k];   // written by lm_reset_kernel (stream-ordered before this kernel)
     setup_const(E, tr, st);
     s_flag = 0;
   }
@@ -505,6 +504,10 @@ __global__ void lm_reset_kernel(RegDevState* st, int max_iterations) {
   LmState& L = st->lm;
   L.phase = 0; L.iteration = 0; L.max_iterations = max_iterations; L.num_invalid = 0; L.done = 0; L.termination = 0; L.last_successful = 1; L.reuse_diagonal = 0;
   L.ls_iters = 0; L.n_valid = 0; L.total_iterations = 0; L.total_evaluations = 0;
+  // iteration zero evaluates Plus(x, 0): the projection of the start point onto the bounds (TrustRegionMinimizer::IterationZero)
+  double x0[7], z[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < 7; k++) x0[k] = st->x[k];
+  d_plus(x0, z, st->bound, L.trial);
   st->bar_count = 0;
 }
 

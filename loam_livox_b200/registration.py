@@ -63,6 +63,7 @@ class Livox_laser:
     def __init__(self, ctx: Context):
         self.ctx = ctx
         self.n = 0
+        ctx.check(ctx._lib.ll_extract_reset(ctx.h))   # a new Livox_laser object has no cross-scan history
 
     def extract_laser_features(self, laserCloudIn, time_stamp: float) -> int:
         """Returns laserCloudScans.size() (number of petals handed back; the caller drops the frame if <= 5)."""

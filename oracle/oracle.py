@@ -93,9 +93,7 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    so = os.path.join(_HERE, "liboracle.so")
-    if not os.path.exists(so):
-        build()
+    so = build()   # rebuilds only when a source is newer than the library
     L = C.CDLL(so)
     L.orc_hw_threads.restype = C.c_int
     L.orc_voxel_grid.argtypes = [f32p, C.c_int, C.c_float, f32p]
