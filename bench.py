@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the scan-to-map registration hot path (BASELINE.json config[1]: 100k-pt scan vs 5M-pt map, 1xB200).
+
+A step = one synthetic Livox scan through the whole per-scan path (ll_scan_to_pose): feature extraction (K1-K3),
+VoxelGrid x2 per feature class (K4), then the ICP loop against the HBM-resident map: transform + exact 5-NN + residual
+blocks (K6-K7), robust LM solve x2 with inlier selection (K8-K10).  The map index (K5) is built once, outside the steps.
+
+  value : scans/s with the raw scans already resident in HBM, timed with CUDA events on the context's stream.
+  e2e   : scans/s through the same C-ABI call with the raw scan in pinned HOST memory (H2D inside the timed region,
+          pose read back to the host), host wall clock around the call.
+L2 is flushed (256 MiB write) between timed steps, outside the timed regions.
+
+`--impl reference` times the CPU restatement of the reference (oracle/) on the host cores instead (no GPU used).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from loam_livox_b200 import synthetic as S  # noqa: E402
+
+WORKLOAD = "C2: 100k-pt Livox scan vs 5M-pt map (0.5M corner + 4.5M surface), extract + VoxelGrid + 5-NN + LM registration"
+N_SCAN = 100_000
+N_MAP_CORNER, N_MAP_SURF = 500_000, 4_500_000
+# leaves scaled from the precision YAML (0.1 / 0.4 m on a ~0.2 m map) to this map's ~0.02 m point spacing
+PIPE = dict(pieces=3, use_piece=0, extractor_leaf_corner=0.01, extractor_leaf_surf=0.01, mapping_leaf_corner=0.01, mapping_leaf_surf=0.02, whole_frame=1)
+N_DISTINCT_SCANS = 6
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def depth_levels(n):
+    return int(np.ceil(np.log2(max(n, 16) / 15.0)))
+
+
+def knn_algorithmic_bytes(qc, qs, nmc, nms):
+    """per query 16 (query) + 16*D(N) (root-to-leaf path) + 240 (home leaf)."""
+    return qc * (16 * depth_levels(nmc) + 256) + qs * (16 * depth_levels(nms) + 256)
+
+
+class ClockSampler:
+    def __init__(self, device=0):
+        self.rows = []
+        self._stop = False
+        self.device = device
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.t.start()
+
+    def stop(self):
+        self._stop = True
+        self.t.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nme in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(rank=0):
+    """Map + a few distinct scans (different sensor poses) + perturbed initial guesses, all seeded."""
+    mc, ms = S.make_map(N_MAP_CORNER, N_MAP_SURF)
+    rng = np.random.default_rng(S.SEED + 100 + rank)
+    scans, guesses, truths = [], [], []
+    for k in range(N_DISTINCT_SCANS):
+        pose = S.Pose(S.quat_from_euler(0.01 * k, -0.02, 0.05 + 0.03 * k), np.array([0.3 + 0.5 * k, 0.2 - 0.1 * k, 0.1]))
+        scans.append(S.make_scan(N_SCAN, pose, seed=S.SEED + 1000 * rank + k))
+        guesses.append(S.perturb_pose(pose, rng))
+        truths.append(pose)
+    return mc, ms, scans, guesses, truths
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def oracle_step(O, ex, trees, mc, ms, raw, guess, threads):
+    """The same per-scan path on the host: oracle extractor -> VoxelGrid x2 -> registration."""
+    ex.extract(raw, 100.0)
+    c, s, _ = ex.get_features(0.0, 1.0)
+    c = O.voxel_grid(O.voxel_grid(c, PIPE["extractor_leaf_corner"]), PIPE["mapping_leaf_corner"])
+    s = O.voxel_grid(O.voxel_grid(s, PIPE["extractor_leaf_surf"]), PIPE["mapping_leaf_surf"])
+    p = O.default_params(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t, num_threads=threads)
+    st, res = O.register(mc, trees[0], ms, trees[1], c, s, p)
+    return res, c.shape[0], s.shape[0]
+
+
+def cpu_baseline(threads, n_scans, inputs=None, quiet=True):
+    from oracle import oracle as O
+    mc, ms, scans, guesses, _ = inputs or make_inputs()
+    t0 = time.perf_counter()
+    trees = (O.KdTree(mc), O.KdTree(ms))
+    t_build = time.perf_counter() - t0
+    ex = O.Extractor()
+    oracle_step(O, ex, trees, mc, ms, scans[0], guesses[0], threads)  # warm-up
+    times = []
+    for k in range(n_scans):
+        t0 = time.perf_counter()
+        res, nc, ns = oracle_step(O, ex, trees, mc, ms, scans[k % len(scans)], guesses[k % len(scans)], threads)
+        times.append(time.perf_counter() - t0)
+    per = float(np.mean(times))
+    return {"value": 1.0 / per, "unit": "scans/s", "cores": threads, "kind": "port",
+            "sample": f"{n_scans} scans of the same workload (oracle/ = CPU restatement of the reference; PCL/Ceres/Eigen are not installed), "
+                      f"{threads} thread(s), map index build {t_build:.1f} s not included", "ms_per_scan": per * 1e3, "index_build_s": t_build,
+            "features": [nc, ns], "icp_iterations": res.icp_iterations}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    threads = O.lib().orc_hw_threads()
+    inputs = make_inputs()
+    n = max(1, min(args.steps, 4))
+    t0 = time.perf_counter()
+    cb = cpu_baseline(threads, n, inputs)
+    line = {"impl": "reference", "metric": "scans_per_sec", "value": cb["value"], "unit": "scans/s", "n_gpus": args.gpus, "steps": n, "warmup": 1,
+            "ms_per_step": cb["ms_per_scan"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 kNN / f64 solve", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pipeline": PIPE, "features": cb["features"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from loam_livox_b200 import capi
+    from loam_livox_b200.registration import Context, Map, scan_to_pose
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mc, ms, scans, guesses, truths = make_inputs(rank)
+    ctx = Context(local, max_scan_points=N_SCAN, max_features=N_SCAN)
+    t0 = time.perf_counter()
+    m = Map(ctx, mc, ms)
+    t_index = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    m2 = Map(ctx, mc, ms)
+    t_index = min(t_index, time.perf_counter() - t0)
+    m2.release()
+    pc = capi.PipelineCfg(**PIPE)
+    states = [capi.default_reg_state(q_w_last=g.q, t_w_last=g.t, q_w_curr=g.q, t_w_curr=g.t) for g in guesses]
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=local)
+    dev_scans = [torch.from_numpy(s).cuda() for s in scans]
+    pin_scans = [torch.from_numpy(s).pin_memory() for s in scans]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+
+    def step_dev(k):
+        return scan_to_pose(ctx, m, dev_scans[k].data_ptr(), 100.0 + 0.1 * k, pc, states[k], where=capi.LL_DEVICE, n=N_SCAN, fmt=capi.LL_FMT_XYZI16)
+
+    def _host(k):
+        import ctypes as C
+        res = capi.RegResult()
+        nc, ns = C.c_int(), C.c_int()
+        ctx.check(ctx._lib.ll_scan_to_pose(ctx.h, m.h, pin_scans[k].data_ptr(), N_SCAN, capi.LL_FMT_XYZI16, capi.LL_HOST, 100.0 + 0.1 * k, C.byref(pc), C.byref(states[k]),
+                                           C.byref(res), C.byref(nc), C.byref(ns)))
+        return res, nc.value, ns.value
+
+    def do_flush():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+
+    nd = len(scans)
+    for w in range(args.warmup):
+        step_dev(w % nd)
+        _host(w % nd)
+    # pose sanity on every distinct scan (the timed work must be real work)
+    for k in range(nd):
+        res, nc, ns = step_dev(k)
+        terr = float(np.linalg.norm(np.array(res.t_w_curr) - truths[k].t))
+        assert res.status == 1 and res.registered == 1 and terr < 0.02, (k, res.status, terr)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- value: device-resident inputs, CUDA events on the context stream
+    l0 = ctx.launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    icp_iters, knn_ms, reg_ms, feats = [], [], [], []
+    for i in range(args.steps):
+        k = i % nd
+        do_flush()
+        ev[i][0].record(stream)
+        res, nc, ns = step_dev(k)
+        ev[i][1].record(stream)
+        icp_iters.append(res.icp_iterations); knn_ms.append(res.gpu_ms_knn); reg_ms.append(res.gpu_ms_total); feats.append((nc, ns))
+    torch.cuda.synchronize()
+    launches = ctx.launches() - l0
+    dev_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(np.sum(dev_ms))
+    # ---- e2e: pinned host inputs through the same public call, host wall clock, H2D + result D2H inside
+    e2e_s = 0.0
+    for i in range(args.steps):
+        k = i % nd
+        do_flush()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _host(k)
+        e2e_s += time.perf_counter() - t0
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        peak, peak_src = peaks()
+        qc = float(np.mean([f[0] for f in feats])); qs = float(np.mean([f[1] for f in feats]))
+        alg = knn_algorithmic_bytes(qc, qs, N_MAP_CORNER, N_MAP_SURF)
+        knn_mean_ms = float(np.mean(knn_ms))
+        achieved = alg / (knn_mean_ms * 1e-3) / 1e9
+        line = {
+            "metric": "scans_per_sec", "value": world * args.steps / (total_ms * 1e-3), "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 kNN / f64 solve", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pipeline": PIPE, "features_per_scan": [qc, qs], "l2": "flushed (256 MiB write) between timed steps, outside the timed regions",
+                       "parallelism": f"scan-parallel x{world} (one map replica per GPU, no data-path collective)" if world > 1 else "1 GPU",
+                       "map_index_build_ms": t_index * 1e3},
+            "ms_per_icp_iter": float(np.sum(reg_ms) / max(1, np.sum(icp_iters))), "icp_iterations_mean": float(np.mean(icp_iters)),
+            "clocks": clocks,
+            "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": N_SCAN * 16, "d2h_bytes_per_step": int(np.mean(icp_iters) + 1) * 1400,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "knn_blocks_kernel (transform + exact 5-NN + residual blocks), first ICP iteration of each step (cold L2)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg, "kernel_ms": knn_mean_ms},
+        }
+        if not args.no_cpu:
+            cb = cpu_baseline(1, args.cpu_scans, (mc, ms, scans, guesses, truths))
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-scans", type=int, default=5)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
