@@ -146,7 +146,8 @@ typedef struct {
   double inlier_threshold;       /* m_inlier_threshold after the final/initial cost rescale (:559)      */
   double final_cost, initial_cost;
   double angular_diff, t_diff;   /* m_angular_diff (deg), m_t_diff                                      */
-  float  gpu_ms_total, gpu_ms_knn;  /* CUDA-event timings of this call (0 when timing is disabled)      */
+  float  gpu_ms_total, gpu_ms_knn;  /* CUDA-event timings of this call; gpu_ms_knn = first kNN launch     */
+  float  gpu_ms_knn_all, gpu_ms_solve_all, gpu_ms_select_all, gpu_ms_sort; /* sums over the ICP iterations */
 } ll_reg_result;
 
 /* Replaces Point_cloud_registration::find_out_incremental_transfrom (point_cloud_registration.hpp:163-583):

@@ -46,7 +46,8 @@ class RegResult(C.Structure):
                                        "total_evaluations")] + \
                [("q_w_curr", C.c_double * 4), ("t_w_curr", C.c_double * 3), ("q_w_incre", C.c_double * 4), ("t_w_incre", C.c_double * 3)] + \
                [(n, C.c_double) for n in ("inlier_threshold", "final_cost", "initial_cost", "angular_diff", "t_diff")] + \
-               [("gpu_ms_total", C.c_float), ("gpu_ms_knn", C.c_float)]
+               [("gpu_ms_total", C.c_float), ("gpu_ms_knn", C.c_float), ("gpu_ms_knn_all", C.c_float), ("gpu_ms_solve_all", C.c_float),
+                ("gpu_ms_select_all", C.c_float), ("gpu_ms_sort", C.c_float)]
 
 
 class PipelineCfg(C.Structure):

@@ -5,6 +5,7 @@
 // four kernels: kNN+blocks, solve #1, inlier select, solve #2 + pose/termination), the threshold rescale :559 and the reject gate :561-573.
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -14,14 +15,14 @@ static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct RegArrays {
   float4* feat; float4* blk_a; double* blk_v; double* l1; double* l1_sorted; double* l1_unique; double* partials;
-  int* n_unique; int* knn_idx; float* knn_d; float4* tmp_a; float4* tmp_b; float4* tmp_c; int* counts; float* bounds; double* pose_tmp;
+  int* n_unique; int* knn_idx; float* knn_d; int* perm; float* tile_r2; float4* tmp_a; float4* tmp_b; float4* tmp_c; int* counts; float* bounds; double* pose_tmp;
   int cap;
 };
 static int reg_arrays(ll_ctx* ctx, int M, RegArrays* A) {
   int cap = M > ctx->cfg.max_features ? M : ctx->cfg.max_features;
   int scap = ctx->cfg.max_scan_points > cap ? ctx->cfg.max_scan_points : cap;
   size_t bytes = align256((size_t)cap * 16) * 2 + align256((size_t)cap * 24) + align256((size_t)cap * 8) * 3 + align256((size_t)ctx->num_sms * 32 * 8) + 4096 +
-                 align256((size_t)cap * 20) * 2 + align256((size_t)scap * 16) * 3;
+                 align256((size_t)cap * 20) * 2 + align256((size_t)cap * 4) * 2 + align256((size_t)scap * 16) * 3;
   LL_CUDA(ctx, ctx->reg_buf.reserve(bytes));
   char* p = ctx->reg_buf.as<char>();
   auto take = [&](size_t b) { char* r = p; p += align256(b); return r; };
@@ -30,7 +31,7 @@ static int reg_arrays(ll_ctx* ctx, int M, RegArrays* A) {
   A->l1 = (double*)take((size_t)cap * 8); A->l1_sorted = (double*)take((size_t)cap * 8); A->l1_unique = (double*)take((size_t)cap * 8);
   A->partials = (double*)take((size_t)ctx->num_sms * 32 * 8);
   A->n_unique = (int*)take(256); A->counts = (int*)take(256); A->bounds = (float*)take(256); A->pose_tmp = (double*)take(256);
-  A->knn_idx = (int*)take((size_t)cap * 20); A->knn_d = (float*)take((size_t)cap * 20);
+  A->knn_idx = (int*)take((size_t)cap * 20); A->knn_d = (float*)take((size_t)cap * 20); A->perm = (int*)take((size_t)cap * 4); A->tile_r2 = (float*)take((size_t)cap * 4);
   A->tmp_a = (float4*)take((size_t)scap * 16); A->tmp_b = (float4*)take((size_t)scap * 16); A->tmp_c = (float4*)take((size_t)scap * 16);
   return LL_OK;
 }
@@ -63,6 +64,7 @@ int ll_ctx_create(const ll_config* cfg, int device, ll_ctx** out) {
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device); ctx->num_sms = prop.multiProcessorCount;
   cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2); cudaEventCreate(&ctx->ev3);
+  for (int i = 0; i < 5 * 16 + 2; i++) cudaEventCreate(&ctx->evp[i]);
   ctx->pinned_cap = 1 << 16; cudaHostAlloc(&ctx->pinned, ctx->pinned_cap, cudaHostAllocDefault);
   void* dreg = nullptr; cudaMalloc(&dreg, sizeof(RegDevState)); cudaMemset(dreg, 0, sizeof(RegDevState)); ctx->d_reg = (RegDevState*)dreg;
   cudaError_t e = cudaGetLastError();
@@ -78,6 +80,7 @@ void ll_ctx_destroy(ll_ctx* ctx) {
   if (ctx->d_reg) cudaFree(ctx->d_reg);
   if (ctx->comm_local) cudaFree(ctx->comm_local);
   for (int i = 0; i < 8; i++) if (ctx->comm_peers[i] && i != ctx->rank) cudaIpcCloseMemHandle(ctx->comm_peers[i]);
+  for (int i = 0; i < 5 * 16 + 2; i++) if (ctx->evp[i]) cudaEventDestroy(ctx->evp[i]);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -259,7 +262,7 @@ static KnnBlocksArgs knn_args(ll_ctx* ctx, const ll_map* map, const RegArrays& A
   a.pose = ctx->d_reg->pose_curr; a.max_dis_line = in->maximum_dis_line_for_match; a.max_dis_plane = in->maximum_dis_plane_for_match;
   a.icp_line = in->icp_line; a.icp_plane = in->icp_plane; a.blk_a = A.blk_a; a.blk_v = A.blk_v;
   a.corner_avail = &ctx->d_reg->corner_avail; a.surf_avail = &ctx->d_reg->surf_avail;
-  a.knn_idx = debug ? A.knn_idx : nullptr; a.knn_d = debug ? A.knn_d : nullptr;
+  a.knn_idx = debug ? A.knn_idx : nullptr; a.knn_d = debug ? A.knn_d : nullptr; a.perm = A.perm; a.tile_r2 = A.tile_r2; a.stats = &ctx->d_reg->knn_tiles;
   a.rank = map->rank; a.world = map->world; a.inv_cell = map->cell_size > 0.f ? 1.0f / map->cell_size : 1.0f;
   return a;
 }
@@ -288,15 +291,26 @@ static int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, i
   LL_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
   out->registered = 1;
   KnnBlocksArgs ka = knn_args(ctx, map, A, nc, ns, in, false);
+  LL_CUDA(ctx, cudaMemsetAsync(A.tile_r2, 0, (size_t)M * 4, s));
+  LL_CUDA(ctx, cudaEventRecord(ctx->evp[80], s));
+  LL_TRY(launch_query_sort(ctx, ka, A.perm));   // spatial tiles of features (Hilbert order at the initial pose)
+  LL_CUDA(ctx, cudaEventRecord(ctx->evp[81], s));
   int iter = 0; RegDevState* hs = (RegDevState*)((char*)ctx->pinned + align256(sizeof(RegDevState)));
   for (iter = 0; iter < in->icp_max_iterations; iter++) {
+    cudaEvent_t* e = iter < 16 ? &ctx->evp[5 * iter] : nullptr;
     LL_CUDA(ctx, cudaMemsetAsync(&ctx->d_reg->corner_avail, 0, 2 * sizeof(int), s));
+    LL_CUDA(ctx, cudaMemsetAsync(&ctx->d_reg->knn_tiles, 0, 4 * sizeof(int), s));
     if (iter == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    if (e) LL_CUDA(ctx, cudaEventRecord(e[0], s));
     LL_TRY(launch_knn_blocks(ctx, ka));
+    if (e) LL_CUDA(ctx, cudaEventRecord(e[1], s));
     if (iter == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev2, s));
     LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 0, in->cere_prerun_times)));
+    if (e) LL_CUDA(ctx, cudaEventRecord(e[2], s));
     LL_TRY(launch_inlier_select(ctx, A.l1, M, A.l1_sorted, A.l1_unique, A.n_unique));
+    if (e) LL_CUDA(ctx, cudaEventRecord(e[3], s));
     LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 1, in->cere_max_iterations)));
+    if (e) LL_CUDA(ctx, cudaEventRecord(e[4], s));
     LL_CUDA(ctx, cudaMemcpyAsync(hs, ctx->d_reg, sizeof(RegDevState), cudaMemcpyDeviceToHost, s));
     LL_CUDA(ctx, cudaStreamSynchronize(s));
     if (hs->lm.termination == -1) { ctx->set_error("no residual block survived the gates / inlier selection"); return LL_ERR_NO_BLOCKS; }
@@ -308,6 +322,11 @@ static int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, i
   LL_CUDA(ctx, cudaEventRecord(ctx->ev3, s));
   LL_CUDA(ctx, cudaEventSynchronize(ctx->ev3));
   cudaEventElapsedTime(&out->gpu_ms_total, ctx->ev0, ctx->ev3); cudaEventElapsedTime(&out->gpu_ms_knn, ctx->ev1, ctx->ev2);
+  cudaEventElapsedTime(&out->gpu_ms_sort, ctx->evp[80], ctx->evp[81]);
+  { const int done_iters = (iter < in->icp_max_iterations ? iter + 1 : in->icp_max_iterations);
+    for (int i = 0; i < done_iters && i < 16; i++) { float a = 0, b = 0, c = 0, d = 0; cudaEvent_t* e = &ctx->evp[5 * i];
+      cudaEventElapsedTime(&a, e[0], e[1]); cudaEventElapsedTime(&b, e[1], e[2]); cudaEventElapsedTime(&c, e[2], e[3]); cudaEventElapsedTime(&d, e[3], e[4]);
+      out->gpu_ms_knn_all += a; out->gpu_ms_solve_all += b + d; out->gpu_ms_select_all += c; } }
   out->icp_iterations = (iter + 1 < in->icp_max_iterations) ? iter + 1 : in->icp_max_iterations;
   out->corner_used = hs->corner_avail; out->surf_used = hs->surf_avail; out->num_residual_blocks = hs->num_residual_blocks;
   out->total_lm_iterations = hs->total_lm_iterations; out->total_evaluations = hs->total_evaluations;
@@ -317,6 +336,7 @@ static int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, i
   for (int k = 0; k < 3; k++) out->t_w_incre[k] = hs->x[4 + k];
   out->final_cost = hs->final_cost; out->initial_cost = hs->initial_cost; out->angular_diff = hs->angular_diff; out->t_diff = hs->t_diff;
   out->inlier_threshold = hs->inlier_threshold * hs->final_cost / hs->initial_cost;   // :559
+  if (getenv("LL_DEBUG_KNN")) fprintf(stderr, "[knn] last iteration: tile rounds %d overflow %d candidate buckets %d second rounds %d\n", hs->knn_tiles, hs->knn_overflow_tiles, hs->knn_candidates, hs->knn_frontier_max);
   const float minimize_cost = (float)hs->final_cost;
   if (hs->angular_diff > (double)(float)in->para_max_angular_rate || minimize_cost > (float)in->max_final_cost) {   // :561-573
     out->status = 0;
@@ -348,7 +368,7 @@ int ll_build_blocks(ll_ctx* ctx, const ll_map* map, const void* scan_corner, siz
   LL_TRY(upload_cloud(ctx, scan_surf, ns, fmt, where, A.feat + nc));
   RegDevState* h = (RegDevState*)ctx->pinned; fill_state(h, in);
   LL_CUDA(ctx, cudaMemcpyAsync(ctx->d_reg, h, sizeof(RegDevState), cudaMemcpyHostToDevice, s));
-  LL_TRY(launch_knn_blocks(ctx, knn_args(ctx, map, A, (int)nc, (int)ns, in, true)));
+  { KnnBlocksArgs ka = knn_args(ctx, map, A, (int)nc, (int)ns, in, true); LL_CUDA(ctx, cudaMemsetAsync(A.tile_r2, 0, (size_t)M * 4, s)); LL_TRY(launch_query_sort(ctx, ka, A.perm)); LL_TRY(launch_knn_blocks(ctx, ka)); }
   std::vector<float4> ba(M); std::vector<double> bv((size_t)M * 3);
   int cnt[2];
   LL_CUDA(ctx, cudaMemcpyAsync(ba.data(), A.blk_a, (size_t)M * 16, cudaMemcpyDeviceToHost, s));

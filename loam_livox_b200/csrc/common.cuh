@@ -37,11 +37,11 @@ struct DevBuf {  // grow-only device allocation
 };
 
 // ------------------------------------------------------------------------------------------------ map index
-// "Bucket tree": map points sorted along a 63-bit Morton curve, cut into leaf buckets of 32 points (512 B,
-// one coalesced warp load / one cp.async.bulk), with levels of axis-aligned boxes above them, 32 children per
-// node.  Level 0 boxes bound the buckets; level l+1 boxes bound 32 consecutive level-l boxes.  The top level has
-// <= 32 boxes and is searched as one group.  Search is exact (boxes give a true lower bound of the fp32 distance).
-#define LL_MAX_LEVELS 6
+// "Bucket tree": map points sorted along a 63-bit Hilbert curve (isotropic cells), cut into leaf buckets of 8 points
+// (128 B = one line), with a 4-ary tree of axis-aligned boxes above them (a node record = its 4 children's boxes, 96 B).
+// The top levels are bulk-copied (TMA) into shared memory by the search kernels.  Search is exact: a box gives a true
+// lower bound of the fp32 distance.  lo[l] holds level l's node records; hi[0] the base of the node array.
+#define LL_MAX_LEVELS 14
 struct BucketTree {
   int n = 0;             // valid (finite) points
   int n_pad = 0;         // padded to a multiple of 32
@@ -52,6 +52,7 @@ struct BucketTree {
   float4* hi[LL_MAX_LEVELS] = {nullptr};
   float4* src = nullptr;                  // [n_src] the cloud as given to ll_map_build (x,y,z,intensity)
   int n_src = 0;
+  float bbox[6] = {0, 0, 0, 0, 0, 0};     // min xyz, max xyz of the finite points
   DevBuf storage;                          // one allocation backing all of the above
 };
 
@@ -84,6 +85,7 @@ struct ll_ctx {
   ll_config cfg;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t evp[5 * 16 + 2] = {nullptr};   // per-ICP-iteration phase events
   std::string err;
   uint64_t launches = 0;
   int hook_slots = 0;      // slot count left behind by ll_build_blocks for the parity hooks

@@ -3,8 +3,12 @@
 #include "common.cuh"
 
 struct TreeView {
-  const float4* pts; const float4* lo[LL_MAX_LEVELS]; const float4* hi[LL_MAX_LEVELS];
-  int n, n_levels;
+  const float4* pts;                    // [n_pad] Hilbert-ordered points, w = original index
+  const float4* src;                    // [n_src] the cloud in its original order
+  const float4* nodes[LL_MAX_LEVELS];   // node records per level (6 float4 each); level 0's children are the 8-point buckets
+  const float4* node_base;              // start of the node array (top level first): its prefix is staged into shared memory
+  int n, n_levels, staged_levels, staged_f4;
+  float bbox[6];                        // map bounding box (min xyz, max xyz)
 };
 TreeView make_view(const BucketTree& t);
 int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t);
@@ -19,10 +23,14 @@ struct KnnBlocksArgs {
   float4* blk_a; double* blk_v;
   int* corner_avail; int* surf_avail;
   int* knn_idx; float* knn_d;   // optional debug outputs [M x 5]
+  float* tile_r2;               // [M] per-feature search radius^2 hint carried from one ICP iteration to the next (may be null)
+  int* stats;                   // [4] tiles, overflow tiles, candidate buckets, max frontier (may be null)
+  const int* perm;              // spatially sorted feature order (corners then surfaces), or null = caller order
   int rank, world; float inv_cell;
 };
 int launch_knn_query(ll_ctx* ctx, const BucketTree& t, const float4* d_q, int nq, int* d_idx, float* d_d);
 int launch_knn_blocks(ll_ctx* ctx, const KnnBlocksArgs& a);
+int launch_query_sort(ll_ctx* ctx, const KnnBlocksArgs& a, int* d_perm);
 
 // ---------------------------------------------------------------------------------------------- solver (solve.cu)
 struct FnSample { double x, value, gradient; int value_valid, gradient_valid; };
@@ -50,6 +58,7 @@ struct RegDevState {
   double inlier_threshold, angular_diff, t_diff, final_cost, initial_cost;
   int corner_avail, surf_avail, icp_done, icp_iter, num_residual_blocks, status, total_lm_iterations, total_evaluations;
   int n_unique; int pad0;
+  int knn_tiles, knn_overflow_tiles, knn_candidates, knn_frontier_max;   // search statistics of the last kNN launch
   unsigned int bar_count, bar_gen;
   LmState lm;
 };

@@ -10,11 +10,15 @@
 // Compiled with -fmad=false: the float distance (FLANN L2_Simple<float>: ((dx*dx)+dy*dy)+dz*dz), the fp64
 // transform and the fp64 line/plane geometry must round exactly like the scalar CPU code.
 #include <cub/cub.cuh>
+#include <cstring>
 #include "common.cuh"
 #include "kernels.cuh"
 #include "exact_math.cuh"
 
 #define FULL 0xffffffffu
+#define BUCKET 8        // points per leaf bucket: 8 x 16 B = one 128-B line
+#define FANOUT 8        // children per node; a node record holds its 8 children's boxes, child c = rec[2c] (lo.xyz) + rec[2c+1] (hi.xyz): 256 B
+#define NODE_F4 16
 
 // ------------------------------------------------------------------------------------------------ build
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -60,22 +64,36 @@ __device__ __forceinline__ unsigned long long spread21(unsigned v) {
   x = (x | x << 2) & 0x1249249249249249ull;
   return x;
 }
-__global__ void morton_kernel(const float4* __restrict__ src, int n, const int* __restrict__ bbox, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+// 63-bit Hilbert index (Skilling's transpose form, 21 bits per axis) on an ISOTROPIC grid (one scale for all axes):
+// consecutive runs along a Hilbert curve are connected blobs, so fixed-size buckets get tight, nearly cubic boxes.
+__global__ void hilbert_kernel(const float4* __restrict__ src, int n, const int* __restrict__ bbox, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = src[i];
   unsigned long long key = ~0ull;
   if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-    float lo[3] = {ord2f(bbox[0]), ord2f(bbox[1]), ord2f(bbox[2])}, hi[3] = {ord2f(bbox[3]), ord2f(bbox[4]), ord2f(bbox[5])};
-    float c[3] = {p.x, p.y, p.z}; unsigned q[3];
+    const float lo[3] = {ord2f(bbox[0]), ord2f(bbox[1]), ord2f(bbox[2])}, hi[3] = {ord2f(bbox[3]), ord2f(bbox[4]), ord2f(bbox[5])};
+    const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    const float c[3] = {p.x, p.y, p.z}; unsigned X[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      float ext = hi[k] - lo[k];
       float u = ext > 0.f ? (c[k] - lo[k]) / ext : 0.f;
       u = fminf(fmaxf(u, 0.f), 1.f);
-      q[k] = (unsigned)fminf(u * 2097152.0f, 2097151.0f);
+      X[k] = (unsigned)fminf(u * 2097152.0f, 2097151.0f);
     }
-    key = spread21(q[0]) | (spread21(q[1]) << 1) | (spread21(q[2]) << 2);
+    for (unsigned Q = 1u << 20; Q > 1; Q >>= 1) {
+      const unsigned P = Q - 1;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (X[k] & Q) X[0] ^= P;
+        else { unsigned t = (X[0] ^ X[k]) & P; X[0] ^= t; X[k] ^= t; }
+      }
+    }
+    X[1] ^= X[0]; X[2] ^= X[1];
+    unsigned t = 0;
+    for (unsigned Q = 1u << 20; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    key = (spread21(X[0]) << 2) | (spread21(X[1]) << 1) | spread21(X[2]);
   }
   keys[i] = key; vals[i] = i;
 }
@@ -85,21 +103,30 @@ __global__ void gather_kernel(const float4* __restrict__ src, const int* __restr
   if (i < n_valid) { int j = order[i]; float4 p = src[j]; p.w = __int_as_float(j); pts[i] = p; }
   else pts[i] = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0x7fffffff));
 }
-// One warp per box: level 0 boxes bound 32 points, higher levels bound 32 child boxes. Pads are neutral (+inf / -inf).
-__global__ void box_kernel(const float4* __restrict__ child_lo, const float4* __restrict__ child_hi, int n_child, int n_box_pad, int n_box, float4* __restrict__ lo, float4* __restrict__ hi) {
-  int box = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (box >= n_box_pad) return;
-  float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
-  int c = box * 32 + lane;
-  if (box < n_box && c < n_child) {
-    float4 a = child_lo[c]; float4 b = child_hi ? child_hi[c] : a;
-    l[0] = a.x; l[1] = a.y; l[2] = a.z; h[0] = b.x; h[1] = b.y; h[2] = b.z;
+// One thread per (node, child).  Level 0: the children are buckets of 8 points.  Level l > 0: the children are level l-1 nodes
+// (box = union of that node's 8 child boxes).  Missing children get the neutral box (+inf, -inf).
+__global__ void node_kernel(const float4* __restrict__ pts, int n_valid, const float4* __restrict__ child_nodes, int n_child, int n_nodes, float4* __restrict__ nodes) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = g / FANOUT, c = g % FANOUT;
+  if (j >= n_nodes) return;
+  float l0 = INFINITY, l1 = INFINITY, l2 = INFINITY, h0 = -INFINITY, h1 = -INFINITY, h2 = -INFINITY;
+  const int ci = j * FANOUT + c;
+  if (ci < n_child) {
+    if (child_nodes == nullptr) {
+      for (int k = 0; k < BUCKET; k++) {
+        const int pi = ci * BUCKET + k;
+        if (pi < n_valid) { const float4 p = pts[pi]; l0 = fminf(l0, p.x); l1 = fminf(l1, p.y); l2 = fminf(l2, p.z); h0 = fmaxf(h0, p.x); h1 = fmaxf(h1, p.y); h2 = fmaxf(h2, p.z); }
+      }
+    } else {
+      const float4* r = child_nodes + (size_t)ci * NODE_F4;
+      for (int k = 0; k < FANOUT; k++) {
+        const float4 a = r[2 * k], b = r[2 * k + 1];
+        l0 = fminf(l0, a.x); l1 = fminf(l1, a.y); l2 = fminf(l2, a.z); h0 = fmaxf(h0, b.x); h1 = fmaxf(h1, b.y); h2 = fmaxf(h2, b.z);
+      }
+    }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int k = 0; k < 3; k++) { l[k] = fminf(l[k], __shfl_xor_sync(FULL, l[k], o)); h[k] = fmaxf(h[k], __shfl_xor_sync(FULL, h[k], o)); }
-  if (lane == 0) { lo[box] = make_float4(l[0], l[1], l[2], 0.f); hi[box] = make_float4(h[0], h[1], h[2], 0.f); }
+  float4* o = nodes + (size_t)j * NODE_F4;
+  o[2 * c] = make_float4(l0, l1, l2, 0.f); o[2 * c + 1] = make_float4(h0, h1, h2, 0.f);
 }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -123,57 +150,59 @@ int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t
   if (n_src > 0) {
     int grid = min(ll_div_up(n_src, 256), ctx->num_sms * 8);
     bbox_kernel<<<grid, 256, 0, s>>>(d_src, n_src, bbox); ctx->launches++;
-    morton_kernel<<<ll_div_up(n_src, 256), 256, 0, s>>>(d_src, n_src, bbox, k0, v0); ctx->launches++;
+    hilbert_kernel<<<ll_div_up(n_src, 256), 256, 0, s>>>(d_src, n_src, bbox, k0, v0); ctx->launches++;
     LL_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + off_tmp, temp_bytes, k0, k1, v0, v1, n_src, 0, 63, s)); ctx->launches += 8;
-    LL_CUDA(ctx, cudaMemcpyAsync(&n_valid, bbox + 6, sizeof(int), cudaMemcpyDeviceToHost, s));
+    int hb[8];
+    LL_CUDA(ctx, cudaMemcpyAsync(hb, bbox, 7 * sizeof(int), cudaMemcpyDeviceToHost, s));
     LL_CUDA(ctx, cudaStreamSynchronize(s));
+    n_valid = hb[6];
+    for (int k = 0; k < 6; k++) { int v = hb[k]; v = v >= 0 ? v : v ^ 0x7fffffff; memcpy(&t->bbox[k], &v, 4); }
   }
-  t->n = n_valid; t->n_pad = ll_div_up(n_valid > 0 ? n_valid : 1, 32) * 32;
-  // level sizes
-  int cnt = t->n_pad / 32; t->n_levels = 0;
-  for (;;) { t->level_count[t->n_levels++] = cnt; if (cnt <= 32 || t->n_levels == LL_MAX_LEVELS) break; cnt = ll_div_up(cnt, 32); }
-  if (t->level_count[t->n_levels - 1] > 32) { ctx->set_error("map too large for LL_MAX_LEVELS"); return LL_ERR_CAPACITY; }
-  size_t bytes = align256((size_t)t->n_pad * 16) + align256((size_t)n_src * 16);
-  for (int l = 0; l < t->n_levels; l++) bytes += 2 * align256((size_t)ll_div_up(t->level_count[l], 32) * 32 * 16);
+  t->n = n_valid; t->n_pad = ll_div_up(n_valid > 0 ? n_valid : 1, BUCKET) * BUCKET;
+  // level sizes: level 0 nodes have buckets as children; the top level has exactly one node
+  int cnt = ll_div_up(t->n_pad / BUCKET, FANOUT); t->n_levels = 0;
+  for (;;) { t->level_count[t->n_levels++] = cnt; if (cnt <= 1) break; if (t->n_levels == LL_MAX_LEVELS) { ctx->set_error("map too large for LL_MAX_LEVELS"); return LL_ERR_CAPACITY; } cnt = ll_div_up(cnt, FANOUT); }
+  // node storage is laid out TOP level first, so that the top levels form one contiguous prefix (bulk-copied to shared memory)
+  size_t node_total = 0; for (int l = 0; l < t->n_levels; l++) node_total += (size_t)t->level_count[l];
+  size_t bytes = align256((size_t)t->n_pad * 16) + align256((size_t)n_src * 16) + align256(node_total * NODE_F4 * 16);
   LL_CUDA(ctx, t->storage.reserve(bytes));
   char* p = t->storage.as<char>();
   t->pts = (float4*)p; p += align256((size_t)t->n_pad * 16);
-  for (int l = 0; l < t->n_levels; l++) { size_t b = align256((size_t)ll_div_up(t->level_count[l], 32) * 32 * 16); t->lo[l] = (float4*)p; p += b; t->hi[l] = (float4*)p; p += b; }
+  float4* nodes = (float4*)p; p += align256(node_total * NODE_F4 * 16);
+  { size_t off = 0; for (int l = t->n_levels - 1; l >= 0; l--) { t->lo[l] = nodes + off * NODE_F4; off += (size_t)t->level_count[l]; } }
+  t->hi[0] = nodes;   // base of the node array (top level first)
   t->src = (float4*)p;
   if (n_src > 0) LL_CUDA(ctx, cudaMemcpyAsync(t->src, d_src, (size_t)n_src * 16, cudaMemcpyDeviceToDevice, s));
   gather_kernel<<<ll_div_up(t->n_pad, 256), 256, 0, s>>>(d_src, v1, n_valid, t->n_pad, t->pts); ctx->launches++;
   for (int l = 0; l < t->n_levels; l++) {
-    int n_box = t->level_count[l], n_box_pad = ll_div_up(n_box, 32) * 32;
-    const float4* clo = l == 0 ? t->pts : t->lo[l - 1]; const float4* chi = l == 0 ? nullptr : t->hi[l - 1];
-    int n_child = l == 0 ? n_valid : t->level_count[l - 1];
-    box_kernel<<<ll_div_up(n_box_pad * 32, 256), 256, 0, s>>>(clo, chi, n_child, n_box_pad, n_box, t->lo[l], t->hi[l]); ctx->launches++;
+    const int n_child = l == 0 ? t->n_pad / BUCKET : t->level_count[l - 1];
+    node_kernel<<<ll_div_up(t->level_count[l] * FANOUT, 128), 128, 0, s>>>(t->pts, n_valid, l == 0 ? nullptr : t->lo[l - 1], n_child, t->level_count[l], t->lo[l]); ctx->launches++;
   }
   LL_CUDA(ctx, cudaGetLastError());
   return LL_OK;
 }
 
 TreeView make_view(const BucketTree& t) {
-  TreeView v; v.pts = t.pts; v.n = t.n; v.n_levels = t.n_levels;
-  for (int l = 0; l < LL_MAX_LEVELS; l++) { v.lo[l] = t.lo[l]; v.hi[l] = t.hi[l]; }
+  TreeView v; v.pts = t.pts; v.src = t.src; v.n = t.n; v.n_levels = t.n_levels; v.node_base = t.hi[0];
+  for (int l = 0; l < LL_MAX_LEVELS; l++) v.nodes[l] = t.lo[l];
+  v.staged_levels = 0; v.staged_f4 = 0;
+  for (int k = 0; k < 6; k++) v.bbox[k] = t.bbox[k];
   return v;
 }
 
 // ------------------------------------------------------------------------------------------------ search
-struct Top5 { float d[LL_KNN]; int id[LL_KNN]; int pos[LL_KNN]; };
+// Eight lanes per query, four queries per warp.  A step of a query's best-first search pops one item from the group's stack
+// (shared memory) and handles it with all 8 lanes at once: a NODE -> lane c tests child c's box (two coalesced 16-B loads per lane,
+// 256 B per group) and the qualifying children are pushed far-to-near in one shot (rank by 7 shuffles); a BUCKET -> lane c takes
+// point c (one 16-B load, 128 B per group) and the candidates are merged into the group's top-5.  The top-5 and the stack pointer are
+// replicated in the 8 lanes.  Exact: a box gives a true lower bound of the fp32 distance and (d2, index) is a total order.
+#define GROUP 8
+#define KNN_THREADS 256
+#define GROUPS_PER_CTA (KNN_THREADS / GROUP)
+#define STACK_CAP 64
+#define ITEM_BUCKET 0x80000000u
 
 __device__ __forceinline__ bool lex_less(float d, int id, float d2, int id2) { return d < d2 || (d == d2 && id < id2); }
-
-__device__ __forceinline__ void top5_insert(Top5& t, float d, int id, int pos) {
-  t.d[4] = d; t.id[4] = id; t.pos[4] = pos;
-#pragma unroll
-  for (int j = 4; j > 0; --j) {
-    if (lex_less(t.d[j], t.id[j], t.d[j - 1], t.id[j - 1])) {
-      float td = t.d[j]; t.d[j] = t.d[j - 1]; t.d[j - 1] = td;
-      int ti = t.id[j]; t.id[j] = t.id[j - 1]; t.id[j - 1] = ti;
-      int tp = t.pos[j]; t.pos[j] = t.pos[j - 1]; t.pos[j - 1] = tp;
-    }
-  }
-}
 
 // FLANN L2_Simple<float>: result += diff*diff, x then y then z, float accumulation, no contraction.
 __device__ __forceinline__ float dist2_exact(float qx, float qy, float qz, float px, float py, float pz) {
@@ -182,77 +211,97 @@ __device__ __forceinline__ float dist2_exact(float qx, float qy, float qz, float
 }
 // Lower bound of dist2_exact over every point inside the box: same operation sequence on the per-axis gaps, and
 // round-to-nearest is monotone, so lb <= d2 holds bit-wise (the search stays exact).
-__device__ __forceinline__ float box_lb(const float4& lo, const float4& hi, float qx, float qy, float qz) {
-  float ex = fmaxf(fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)), 0.f);
-  float ey = fmaxf(fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)), 0.f);
-  float ez = fmaxf(fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)), 0.f);
+__device__ __forceinline__ float box_lb(float lox, float loy, float loz, float hix, float hiy, float hiz, float qx, float qy, float qz) {
+  float ex = fmaxf(fmaxf(__fsub_rn(lox, qx), __fsub_rn(qx, hix)), 0.f);
+  float ey = fmaxf(fmaxf(__fsub_rn(loy, qy), __fsub_rn(qy, hiy)), 0.f);
+  float ez = fmaxf(fmaxf(__fsub_rn(loz, qz), __fsub_rn(qz, hiz)), 0.f);
   return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
 }
 
-__device__ __forceinline__ void scan_bucket(const TreeView& tv, int leaf, float qx, float qy, float qz, Top5& t, int lane) {
-  const float4 p = __ldg(&tv.pts[leaf * 32 + lane]);   // 512 B coalesced: the whole bucket in one warp load
-  const float d = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-  const int id = __float_as_int(p.w);
-  bool c = d < INFINITY && lex_less(d, id, t.d[4], t.id[4]);
-  while (__any_sync(FULL, c)) {
-    unsigned key = c ? __float_as_uint(d) : 0xffffffffu;
-    unsigned mn = __reduce_min_sync(FULL, key);
-    bool tie = c && key == mn;
-    unsigned idk = tie ? (unsigned)id : 0xffffffffu;
-    unsigned mid = __reduce_min_sync(FULL, idk);
-    unsigned who = __ballot_sync(FULL, tie && idk == mid);
-    int sel = __ffs(who) - 1;
-    top5_insert(t, __uint_as_float(mn), (int)mid, leaf * 32 + sel);
-    if (lane == sel) c = false;
-    c = c && lex_less(d, id, t.d[4], t.id[4]);
-  }
-}
+struct Top5 { float d[LL_KNN]; int id[LL_KNN]; };
 
-template <int L>
-__device__ __forceinline__ void visit(const TreeView& tv, int group, float qx, float qy, float qz, Top5& t, int lane) {
-  const float4 lo = __ldg(&tv.lo[L][group * 32 + lane]);
-  const float4 hi = __ldg(&tv.hi[L][group * 32 + lane]);
-  const float lb = box_lb(lo, hi, qx, qy, qz);
-  bool todo = lb < INFINITY;
-  for (;;) {
-    bool act = todo && lb <= t.d[4];
-    unsigned key = act ? __float_as_uint(lb) : 0xffffffffu;
-    unsigned mn = __reduce_min_sync(FULL, key);
-    if (mn == 0xffffffffu) break;
-    unsigned who = __ballot_sync(FULL, act && key == mn);
-    int sel = __ffs(who) - 1;
-    if (lane == sel) todo = false;
-    int child = group * 32 + sel;
-    if constexpr (L == 0) scan_bucket(tv, child, qx, qy, qz, t, lane);
-    else visit<L - 1>(tv, child, qx, qy, qz, t, lane);
-  }
-}
-
-__device__ __forceinline__ void warp_knn5(const TreeView& tv, float qx, float qy, float qz, Top5& t, int lane) {
+__device__ __forceinline__ void top5_insert(Top5& t, float d, int id) {
+  t.d[4] = d; t.id[4] = id;
 #pragma unroll
-  for (int j = 0; j < LL_KNN; j++) { t.d[j] = INFINITY; t.id[j] = 0x7fffffff; t.pos[j] = -1; }
-  if (tv.n <= 0) return;
-  switch (tv.n_levels) {
-    case 1: visit<0>(tv, 0, qx, qy, qz, t, lane); break;
-    case 2: visit<1>(tv, 0, qx, qy, qz, t, lane); break;
-    case 3: visit<2>(tv, 0, qx, qy, qz, t, lane); break;
-    case 4: visit<3>(tv, 0, qx, qy, qz, t, lane); break;
-    case 5: visit<4>(tv, 0, qx, qy, qz, t, lane); break;
-    default: visit<5>(tv, 0, qx, qy, qz, t, lane); break;
+  for (int j = 4; j > 0; --j) {
+    if (lex_less(t.d[j], t.id[j], t.d[j - 1], t.id[j - 1])) {
+      float td = t.d[j]; t.d[j] = t.d[j - 1]; t.d[j - 1] = td;
+      int ti = t.id[j]; t.id[j] = t.id[j - 1]; t.id[j - 1] = ti;
+    }
   }
 }
 
-// Parity hook (ll_knn): world-frame queries, one warp each.
-__global__ void __launch_bounds__(256) knn_query_kernel(TreeView tv, const float4* __restrict__ q, int nq, int* __restrict__ idx5, float* __restrict__ d5) {
-  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= nq) return;
-  float4 p = __ldg(&q[w]);
-  Top5 t; warp_knn5(tv, p.x, p.y, p.z, t, lane);
-  if (lane < LL_KNN) {
+struct GroupStack { unsigned item[STACK_CAP]; float lb[STACK_CAP]; };
+
+// All 32 lanes of the warp must call this together (width-8 shuffles); `active` is uniform inside a group.
+__device__ __forceinline__ void group_knn5(const TreeView& tv, GroupStack& st, bool active, float qx, float qy, float qz, Top5& t) {
+  const int gl = threadIdx.x & (GROUP - 1);   // lane inside the group
+#pragma unroll
+  for (int j = 0; j < LL_KNN; j++) { t.d[j] = INFINITY; t.id[j] = 0x7fffffff; }
+  int sp = 0;
+  if (active && tv.n > 0) { if (gl == 0) { st.item[0] = (unsigned)(tv.n_levels - 1) << 26; st.lb[0] = 0.f; } sp = 1; }
+  __syncwarp();
+  while (__any_sync(FULL, sp > 0)) {
+    // ---- pop (skip items that the shrinking bound has made useless)
+    bool have = false; unsigned item = 0;
+    while (sp > 0) { sp--; if (st.lb[sp] <= t.d[4]) { item = st.item[sp]; have = true; break; } }
+    const bool is_bucket = have && (item & ITEM_BUCKET);
+    const bool is_node = have && !is_bucket;
+    const int lv = (int)((item >> 26) & 31u);
+    const int idx = (int)(is_bucket ? (item & 0x7fffffffu) : (item & 0x03ffffffu));
+    // ---- one batch of loads per step: child box (2 x 16 B) or point (16 B)
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
+    if (is_node) { const float4* r = tv.nodes[lv] + (size_t)idx * NODE_F4 + 2 * gl; A = __ldg(r); B = __ldg(r + 1); }
+    else if (is_bucket) A = __ldg(tv.pts + (size_t)idx * BUCKET + gl);
+    __syncwarp();   // stack reads above are complete before anyone pushes below
+    if (__any_sync(FULL, is_node)) {
+      const float lb = is_node ? box_lb(A.x, A.y, A.z, B.x, B.y, B.z, qx, qy, qz) : INFINITY;
+      const bool q = is_node && lb < INFINITY && lb <= t.d[4];
+      // rank among the qualifying children, far first (so the nearest ends on top of the stack)
+      int rank = 0, nq = 0;
+#pragma unroll
+      for (int o = 0; o < GROUP; o++) {
+        const float olb = __shfl_sync(FULL, lb, o, GROUP); const bool oq = __shfl_sync(FULL, q ? 1 : 0, o, GROUP) != 0;
+        nq += oq ? 1 : 0;
+        if (oq && o != gl && (olb > lb || (olb == lb && o < gl))) rank++;
+      }
+      if (q) { st.item[sp + rank] = (lv == 0 ? ITEM_BUCKET : ((unsigned)(lv - 1) << 26)) | (unsigned)(idx * FANOUT + gl); st.lb[sp + rank] = lb; }
+      if (is_node) sp += nq;
+    }
+    if (__any_sync(FULL, is_bucket)) {
+      const float d = is_bucket ? dist2_exact(qx, qy, qz, A.x, A.y, A.z) : INFINITY;
+      const int id = __float_as_int(A.w);
+      bool c = is_bucket && d < INFINITY && lex_less(d, id, t.d[4], t.id[4]);
+      while (__any_sync(FULL, c)) {
+        // group minimum of (d, id) among the remaining candidates
+        float md = c ? d : INFINITY; int mi = c ? id : 0x7fffffff;
+#pragma unroll
+        for (int o = GROUP / 2; o > 0; o >>= 1) {
+          const float od = __shfl_xor_sync(FULL, md, o, GROUP); const int oi = __shfl_xor_sync(FULL, mi, o, GROUP);
+          if (lex_less(od, oi, md, mi)) { md = od; mi = oi; }
+        }
+        if (md < INFINITY && lex_less(md, mi, t.d[4], t.id[4])) top5_insert(t, md, mi);
+        if (c && id == mi && d == md) c = false;
+        c = c && lex_less(d, id, t.d[4], t.id[4]);
+      }
+    }
+    __syncwarp();   // pushes are visible before the next pop
+  }
+}
+
+// Parity hook (ll_knn): world-frame queries in caller order.
+__global__ void __launch_bounds__(KNN_THREADS) knn_query_kernel(TreeView tv, const float4* __restrict__ q, int nq, int* __restrict__ idx5, float* __restrict__ d5) {
+  __shared__ GroupStack stacks[GROUPS_PER_CTA];
+  const int g = blockIdx.x * GROUPS_PER_CTA + (threadIdx.x / GROUP), gl = threadIdx.x & (GROUP - 1);
+  const bool have = g < nq;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f); if (have) p = __ldg(&q[g]);
+  const bool active = have && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+  Top5 t; group_knn5(tv, stacks[threadIdx.x / GROUP], active, p.x, p.y, p.z, t);
+  if (have && gl < LL_KNN) {
     float d = t.d[0]; int id = t.id[0];
 #pragma unroll
-    for (int j = 1; j < LL_KNN; j++) if (lane == j) { d = t.d[j]; id = t.id[j]; }
-    idx5[w * LL_KNN + lane] = (id == 0x7fffffff) ? -1 : id; d5[w * LL_KNN + lane] = d;
+    for (int j = 1; j < LL_KNN; j++) if (gl == j) { d = t.d[j]; id = t.id[j]; }
+    idx5[g * LL_KNN + gl] = (id == 0x7fffffff) ? -1 : id; d5[g * LL_KNN + gl] = d;
   }
 }
 
@@ -262,38 +311,70 @@ __device__ __forceinline__ unsigned cell_owner(float x, float y, float z, float 
   return h % (unsigned)world;
 }
 
-// K6 + K7 fused: one warp per scan feature. Slot i < n_corner is a corner feature, the rest are surface features.
-// Writes one residual-block slot per feature: blk_a[slot] = (a.x, a.y, a.z, type) with type 0 invalid / 1 line / 2 plane,
-// blk_v[slot*3..] = unit line direction or (un-normalised) plane normal, in fp64.
-__global__ void __launch_bounds__(256) knn_blocks_kernel(KnnBlocksArgs a) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// Spatial sort key of a feature at the current pose: class bit (corner/surface) | 30-bit Hilbert index inside the tree's box.
+// Neighbouring queries then sit in the same warp / CTA, walk the same tree nodes and buckets, and hit them in L1.
+__global__ void query_key_kernel(KnnBlocksArgs a, unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int M = a.n_corner + a.n_surf;
-  if (w >= M) return;
+  if (i >= M) return;
+  const bool is_corner = i < a.n_corner;
+  const float4 f = __ldg(&a.feat[i]);
+  double wx, wy, wz; qrot_d(a.pose, (double)f.x, (double)f.y, (double)f.z, wx, wy, wz);
+  const float c[3] = {(float)(wx + a.pose[4]), (float)(wy + a.pose[5]), (float)(wz + a.pose[6])};
+  const float* bb = is_corner ? a.corner.bbox : a.surf.bbox;
+  const float ext = fmaxf(fmaxf(bb[3] - bb[0], bb[4] - bb[1]), bb[5] - bb[2]);
+  unsigned X[3]; bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { if (!isfinite(c[k])) ok = false; float u = ext > 0.f ? (c[k] - bb[k]) / ext : 0.f; u = fminf(fmaxf(u, 0.f), 1.f); X[k] = (unsigned)fminf(u * 1024.0f, 1023.0f); }
+  for (unsigned Q = 1u << 9; Q > 1; Q >>= 1) {
+    const unsigned P = Q - 1;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { if (X[k] & Q) X[0] ^= P; else { unsigned tt = (X[0] ^ X[k]) & P; X[0] ^= tt; X[k] ^= tt; } }
+  }
+  X[1] ^= X[0]; X[2] ^= X[1];
+  unsigned tt = 0;
+  for (unsigned Q = 1u << 9; Q > 1; Q >>= 1) if (X[2] & Q) tt ^= Q - 1;
+  X[0] ^= tt; X[1] ^= tt; X[2] ^= tt;
+  unsigned h = 0;
+#pragma unroll
+  for (int b = 9; b >= 0; b--) h = (h << 3) | (((X[0] >> b) & 1u) << 2) | (((X[1] >> b) & 1u) << 1) | ((X[2] >> b) & 1u);
+  if (!ok) h = 0x3fffffffu;
+  keys[i] = (is_corner ? 0u : 0x40000000u) | h; vals[i] = i;
+}
+
+// K6 + K7 fused: eight lanes per scan feature, features taken in spatially sorted order (perm).
+// Writes one residual-block slot per feature (indexed by the ORIGINAL feature order): blk_a[slot] = (a.x, a.y, a.z, type) with
+// type 0 invalid / 1 line / 2 plane, blk_v[slot*3..] = unit line direction or (un-normalised) plane normal, in fp64.
+__global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a) {
+  __shared__ GroupStack stacks[GROUPS_PER_CTA];
+  const int j = blockIdx.x * GROUPS_PER_CTA + (threadIdx.x / GROUP), gl = threadIdx.x & (GROUP - 1);
+  const int M = a.n_corner + a.n_surf;
+  const bool have = j < M;
+  const int w = have ? (a.perm ? a.perm[j] : j) : 0;      // original feature index
   const bool is_corner = w < a.n_corner;
-  const float4 f = __ldg(&a.feat[w]);
+  const TreeView& tv = is_corner ? a.corner : a.surf;
+  float4 f = make_float4(0.f, 0.f, 0.f, 0.f); if (have) f = __ldg(&a.feat[w]);
   // pointAssociateToMap (non-deblur branch): p_w = q_curr * p + t_curr in fp64, stored as fp32
-  const double* qc = a.pose;      // q_curr w,x,y,z
-  const double* tc = a.pose + 4;  // t_curr
+  const double* qc = a.pose; const double* tc = a.pose + 4;
   double wx, wy, wz; qrot_d(qc, (double)f.x, (double)f.y, (double)f.z, wx, wy, wz);
   const float qx = (float)(wx + tc[0]), qy = (float)(wy + tc[1]), qz = (float)(wz + tc[2]);
-  int type = 0; double ax = 0, ay = 0, az = 0, vx = 0, vy = 0, vz = 0;
-  bool finite_in = isfinite(f.x) && isfinite(f.y) && isfinite(f.z);
+  const bool finite_in = isfinite(f.x) && isfinite(f.y) && isfinite(f.z);
   bool owned = true;
   if (a.world > 1) owned = cell_owner(qx, qy, qz, a.inv_cell, a.world) == (unsigned)a.rank;
-  if (owned && (finite_in || !is_corner)) {
-    const TreeView& tv = is_corner ? a.corner : a.surf;
-    Top5 t; warp_knn5(tv, qx, qy, qz, t, lane);
-    if (a.knn_idx && lane < LL_KNN) {
-      float d = t.d[0]; int id = t.id[0];
+  const bool active = have && owned && finite_in;
+  Top5 t; group_knn5(tv, stacks[threadIdx.x / GROUP], active, qx, qy, qz, t);
+  if (!have || gl != 0) return;
+  int type = 0; double ax = 0, ay = 0, az = 0, vx = 0, vy = 0, vz = 0;
+  if (active) {
+    if (a.knn_idx) {
 #pragma unroll
-      for (int j = 1; j < LL_KNN; j++) if (lane == j) { d = t.d[j]; id = t.id[j]; }
-      a.knn_idx[w * LL_KNN + lane] = (id == 0x7fffffff) ? -1 : id; a.knn_d[w * LL_KNN + lane] = d;
+      for (int k = 0; k < LL_KNN; k++) { a.knn_idx[w * LL_KNN + k] = (t.id[k] == 0x7fffffff) ? -1 : t.id[k]; a.knn_d[w * LL_KNN + k] = t.d[k]; }
     }
-    const bool found5 = t.pos[4] >= 0;
+    const bool found5 = t.id[4] != 0x7fffffff;
     if (is_corner) {
       if (found5 && (double)t.d[4] < a.max_dis_line) {
         if (a.icp_line) {
-          float4 p1 = __ldg(&tv.pts[t.pos[0]]), p2 = __ldg(&tv.pts[t.pos[1]]);
+          const float4 p1 = __ldg(&tv.src[t.id[0]]), p2 = __ldg(&tv.src[t.id[1]]);
           double d0 = (double)p1.x - (double)p2.x, d1 = (double)p1.y - (double)p2.y, d2 = (double)p1.z - (double)p2.z;
           double dn = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
           if (!(dn < 0.0001)) {
@@ -301,14 +382,14 @@ __global__ void __launch_bounds__(256) knn_blocks_kernel(KnnBlocksArgs a) {
             double u0 = (double)p2.x - (double)p1.x, u1 = (double)p2.y - (double)p1.y, u2 = (double)p2.z - (double)p1.z;
             double n = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
             vx = u0 / n; vy = u1 / n; vz = u2 / n; ax = p1.x; ay = p1.y; az = p1.z; type = 1;
-            if (lane == 0) atomicAdd(a.corner_avail, 1);
+            atomicAdd(a.corner_avail, 1);
           }
         }
       }
     } else {
       if (found5 && (double)t.d[4] < a.max_dis_plane) {
         if (a.icp_plane) {
-          float4 pa = __ldg(&tv.pts[t.pos[0]]), pb = __ldg(&tv.pts[t.pos[2]]), pc = __ldg(&tv.pts[t.pos[4]]);
+          const float4 pa = __ldg(&tv.src[t.id[0]]), pb = __ldg(&tv.src[t.id[2]]), pc = __ldg(&tv.src[t.id[4]]);
           double b0 = (double)pb.x - (double)pa.x, b1 = (double)pb.y - (double)pa.y, b2 = (double)pb.z - (double)pa.z;
           double nb = sqrt(b0 * b0 + b1 * b1 + b2 * b2); b0 = b0 / nb; b1 = b1 / nb; b2 = b2 / nb;
           double c0 = (double)pc.x - (double)pa.x, c1 = (double)pc.y - (double)pa.y, c2 = (double)pc.z - (double)pa.z;
@@ -316,26 +397,38 @@ __global__ void __launch_bounds__(256) knn_blocks_kernel(KnnBlocksArgs a) {
           vx = b1 * c2 - b2 * c1; vy = b2 * c0 - b0 * c2; vz = b0 * c1 - b1 * c0;   // NOT re-normalised (ceres_icp.hpp:334)
           ax = pa.x; ay = pa.y; az = pa.z; type = 2;
         }
-        if (lane == 0) atomicAdd(a.surf_avail, 1);
+        atomicAdd(a.surf_avail, 1);
       }
     }
   }
-  if (lane == 0) {
-    a.blk_a[w] = make_float4((float)ax, (float)ay, (float)az, __int_as_float(type));
-    a.blk_v[(size_t)w * 3 + 0] = vx; a.blk_v[(size_t)w * 3 + 1] = vy; a.blk_v[(size_t)w * 3 + 2] = vz;
-  }
+  a.blk_a[w] = make_float4((float)ax, (float)ay, (float)az, __int_as_float(type));
+  a.blk_v[(size_t)w * 3 + 0] = vx; a.blk_v[(size_t)w * 3 + 1] = vy; a.blk_v[(size_t)w * 3 + 2] = vz;
 }
 
 int launch_knn_query(ll_ctx* ctx, const BucketTree& t, const float4* d_q, int nq, int* d_idx, float* d_d) {
   if (nq == 0) return LL_OK;
-  knn_query_kernel<<<ll_div_up(nq * 32, 256), 256, 0, ctx->stream>>>(make_view(t), d_q, nq, d_idx, d_d); ctx->launches++;
+  knn_query_kernel<<<ll_div_up(nq, GROUPS_PER_CTA), KNN_THREADS, 0, ctx->stream>>>(make_view(t), d_q, nq, d_idx, d_d); ctx->launches++;
   LL_CUDA(ctx, cudaGetLastError());
+  return LL_OK;
+}
+// Sorts the features spatially (once per registration, at the initial pose): perm[] lists corner features then surface features.
+int launch_query_sort(ll_ctx* ctx, const KnnBlocksArgs& a, int* d_perm) {
+  const int M = a.n_corner + a.n_surf;
+  if (M == 0) return LL_OK;
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, M, 0, 31, ctx->stream);
+  size_t o_k0 = 0, o_k1 = align256((size_t)M * 4), o_v0 = o_k1 + align256((size_t)M * 4), o_t = o_v0 + align256((size_t)M * 4);
+  LL_CUDA(ctx, ctx->scratch.reserve(o_t + tmp + 256));
+  char* base = ctx->scratch.as<char>();
+  query_key_kernel<<<ll_div_up(M, 256), 256, 0, ctx->stream>>>(a, (unsigned*)(base + o_k0), (int*)(base + o_v0));
+  LL_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + o_t, tmp, (unsigned*)(base + o_k0), (unsigned*)(base + o_k1), (int*)(base + o_v0), d_perm, M, 0, 31, ctx->stream));
+  ctx->launches += 4;
   return LL_OK;
 }
 int launch_knn_blocks(ll_ctx* ctx, const KnnBlocksArgs& a) {
   int M = a.n_corner + a.n_surf;
   if (M == 0) return LL_OK;
-  knn_blocks_kernel<<<ll_div_up(M * 32, 256), 256, 0, ctx->stream>>>(a); ctx->launches++;
+  knn_blocks_kernel<<<ll_div_up(M, GROUPS_PER_CTA), KNN_THREADS, 0, ctx->stream>>>(a); ctx->launches++;
   LL_CUDA(ctx, cudaGetLastError());
   return LL_OK;
 }
