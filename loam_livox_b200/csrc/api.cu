@@ -262,7 +262,7 @@ static KnnBlocksArgs knn_args(ll_ctx* ctx, const ll_map* map, const RegArrays& A
   a.pose = ctx->d_reg->pose_curr; a.max_dis_line = in->maximum_dis_line_for_match; a.max_dis_plane = in->maximum_dis_plane_for_match;
   a.icp_line = in->icp_line; a.icp_plane = in->icp_plane; a.blk_a = A.blk_a; a.blk_v = A.blk_v;
   a.corner_avail = &ctx->d_reg->corner_avail; a.surf_avail = &ctx->d_reg->surf_avail;
-  a.knn_idx = debug ? A.knn_idx : nullptr; a.knn_d = debug ? A.knn_d : nullptr; a.perm = A.perm; a.tile_r2 = A.tile_r2; a.stats = &ctx->d_reg->knn_tiles;
+  a.seed_ids = A.knn_idx; a.knn_d = debug ? A.knn_d : nullptr; a.perm = A.perm; a.tile_r2 = A.tile_r2; a.stats = &ctx->d_reg->knn_tiles;
   a.rank = map->rank; a.world = map->world; a.inv_cell = map->cell_size > 0.f ? 1.0f / map->cell_size : 1.0f;
   return a;
 }
@@ -291,7 +291,7 @@ static int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, i
   LL_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
   out->registered = 1;
   KnnBlocksArgs ka = knn_args(ctx, map, A, nc, ns, in, false);
-  LL_CUDA(ctx, cudaMemsetAsync(A.tile_r2, 0, (size_t)M * 4, s));
+  LL_CUDA(ctx, cudaMemsetAsync(A.knn_idx, 0xff, (size_t)M * LL_KNN * 4, s));   // no seeds for the first ICP iteration
   LL_CUDA(ctx, cudaEventRecord(ctx->evp[80], s));
   LL_TRY(launch_query_sort(ctx, ka, A.perm));   // spatial tiles of features (Hilbert order at the initial pose)
   LL_CUDA(ctx, cudaEventRecord(ctx->evp[81], s));
@@ -368,7 +368,7 @@ int ll_build_blocks(ll_ctx* ctx, const ll_map* map, const void* scan_corner, siz
   LL_TRY(upload_cloud(ctx, scan_surf, ns, fmt, where, A.feat + nc));
   RegDevState* h = (RegDevState*)ctx->pinned; fill_state(h, in);
   LL_CUDA(ctx, cudaMemcpyAsync(ctx->d_reg, h, sizeof(RegDevState), cudaMemcpyHostToDevice, s));
-  { KnnBlocksArgs ka = knn_args(ctx, map, A, (int)nc, (int)ns, in, true); LL_CUDA(ctx, cudaMemsetAsync(A.tile_r2, 0, (size_t)M * 4, s)); LL_TRY(launch_query_sort(ctx, ka, A.perm)); LL_TRY(launch_knn_blocks(ctx, ka)); }
+  { KnnBlocksArgs ka = knn_args(ctx, map, A, (int)nc, (int)ns, in, true); LL_CUDA(ctx, cudaMemsetAsync(A.knn_idx, 0xff, (size_t)M * LL_KNN * 4, s)); LL_TRY(launch_query_sort(ctx, ka, A.perm)); LL_TRY(launch_knn_blocks(ctx, ka)); }
   std::vector<float4> ba(M); std::vector<double> bv((size_t)M * 3);
   int cnt[2];
   LL_CUDA(ctx, cudaMemcpyAsync(ba.data(), A.blk_a, (size_t)M * 16, cudaMemcpyDeviceToHost, s));

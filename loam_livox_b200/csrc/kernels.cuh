@@ -22,7 +22,8 @@ struct KnnBlocksArgs {
   int icp_line, icp_plane;
   float4* blk_a; double* blk_v;
   int* corner_avail; int* surf_avail;
-  int* knn_idx; float* knn_d;   // optional debug outputs [M x 5]
+  int* seed_ids;                // [M x 5] neighbour ids of the previous ICP iteration (-1 = none): seeds of the next search
+  float* knn_d;                 // optional debug output [M x 5]
   float* tile_r2;               // [M] per-feature search radius^2 hint carried from one ICP iteration to the next (may be null)
   int* stats;                   // [4] tiles, overflow tiles, candidate buckets, max frontier (may be null)
   const int* perm;              // spatially sorted feature order (corners then surfaces), or null = caller order

@@ -11,14 +11,18 @@
 // transform and the fp64 line/plane geometry must round exactly like the scalar CPU code.
 #include <cub/cub.cuh>
 #include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.cuh"
 #include "exact_math.cuh"
 
 #define FULL 0xffffffffu
-#define BUCKET 8        // points per leaf bucket: 8 x 16 B = one 128-B line
-#define FANOUT 8        // children per node; a node record holds its 8 children's boxes, child c = rec[2c] (lo.xyz) + rec[2c+1] (hi.xyz): 256 B
-#define NODE_F4 16
+#ifndef LL_GROUP
+#define LL_GROUP 32
+#endif
+#define BUCKET LL_GROUP  // points per leaf bucket (one per lane of a query group)
+#define FANOUT LL_GROUP  // children per node; a node record holds its 8 children's boxes, child c = rec[2c] (lo.xyz) + rec[2c+1] (hi.xyz): 256 B
+#define NODE_F4 (2 * LL_GROUP)
 
 // ------------------------------------------------------------------------------------------------ build
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -196,11 +200,12 @@ TreeView make_view(const BucketTree& t) {
 // 256 B per group) and the qualifying children are pushed far-to-near in one shot (rank by 7 shuffles); a BUCKET -> lane c takes
 // point c (one 16-B load, 128 B per group) and the candidates are merged into the group's top-5.  The top-5 and the stack pointer are
 // replicated in the 8 lanes.  Exact: a box gives a true lower bound of the fp32 distance and (d2, index) is a total order.
-#define GROUP 8
+#define GROUP LL_GROUP
 #define KNN_THREADS 256
 #define GROUPS_PER_CTA (KNN_THREADS / GROUP)
-#define STACK_CAP 64
+#define STACK_CAP (LL_GROUP == 32 ? 160 : 64)
 #define ITEM_BUCKET 0x80000000u
+#define LL_KNN_THREAD_MIN 1000000000   // measured crossover; env LL_KNN_LANES overrides
 
 __device__ __forceinline__ bool lex_less(float d, int id, float d2, int id2) { return d < d2 || (d == d2 && id < id2); }
 
@@ -233,13 +238,68 @@ __device__ __forceinline__ void top5_insert(Top5& t, float d, int id) {
 
 struct GroupStack { unsigned item[STACK_CAP]; float lb[STACK_CAP]; };
 
-// All 32 lanes of the warp must call this together (width-8 shuffles); `active` is uniform inside a group.
-__device__ __forceinline__ void group_knn5(const TreeView& tv, GroupStack& st, bool active, float qx, float qy, float qz, Top5& t) {
+// Merge this step's candidates (one per lane, flag c) into the group's top-5.  Warp-collective.  A candidate whose index is already
+// in the list is ignored, so seeding the list with real points (below) can never create duplicates.
+__device__ __forceinline__ void merge_candidates(Top5& t, float d, int id, bool c) {
+  c = c && d < INFINITY && lex_less(d, id, t.d[4], t.id[4]) && id != t.id[0] && id != t.id[1] && id != t.id[2] && id != t.id[3];
+  while (__any_sync(FULL, c)) {
+    float md = c ? d : INFINITY; int mi = c ? id : 0x7fffffff;   // group minimum of (d, id) among the remaining candidates
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(FULL, md, o, GROUP); const int oi = __shfl_xor_sync(FULL, mi, o, GROUP);
+      if (lex_less(od, oi, md, mi)) { md = od; mi = oi; }
+    }
+    if (md < INFINITY && lex_less(md, mi, t.d[4], t.id[4])) top5_insert(t, md, mi);
+    if (c && id == mi && d == md) c = false;
+    c = c && lex_less(d, id, t.d[4], t.id[4]);
+  }
+}
+
+// All 32 lanes of the warp must call this together (width-GROUP shuffles); `active` is uniform inside a group.
+// seed_ids: the query's 5 neighbours of the previous ICP iteration (or null / -1): their distances to the moved query seed the
+// list, so the bound is tight from the first step.  Without seeds a greedy walk (child with the smallest farthest-corner distance)
+// reaches a bucket next to the query and its points seed the list.
+__device__ __forceinline__ void group_knn5(const TreeView& tv, GroupStack& st, bool active, float qx, float qy, float qz, Top5& t, const int* seed_ids) {
   const int gl = threadIdx.x & (GROUP - 1);   // lane inside the group
 #pragma unroll
   for (int j = 0; j < LL_KNN; j++) { t.d[j] = INFINITY; t.id[j] = 0x7fffffff; }
+  const bool go = active && tv.n > 0;
+  // ---- seeds
+  int sid = -1;
+  if (go && seed_ids && gl < LL_KNN) sid = seed_ids[gl];
+  const bool seeded = __shfl_sync(FULL, sid, (threadIdx.x & 31) & ~(GROUP - 1), 32) >= 0;   // group-uniform: lane 0 of the group has a seed
+  if (__any_sync(FULL, go && seeded)) {
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sid >= 0) p = __ldg(tv.src + sid);
+    merge_candidates(t, sid >= 0 ? dist2_exact(qx, qy, qz, p.x, p.y, p.z) : INFINITY, sid, sid >= 0);
+  }
+  if (__any_sync(FULL, go && !seeded)) {
+    const bool walk = go && !seeded;
+    int idx = 0;
+    const int max_levels = __reduce_max_sync(FULL, tv.n_levels);   // corner / surface groups of one warp may use different trees
+    for (int lv = max_levels - 1; lv >= 0; lv--) {
+      float md = INFINITY;
+      if (walk && lv < tv.n_levels) {
+        const float4* r = tv.nodes[lv] + (size_t)idx * NODE_F4 + 2 * gl; const float4 A = __ldg(r), B = __ldg(r + 1);
+        if (A.x <= B.x) {   // a real child (the neutral box has lo = +inf > hi)
+          const float ex = fmaxf(fabsf(qx - A.x), fabsf(qx - B.x)), ey = fmaxf(fabsf(qy - A.y), fabsf(qy - B.y)), ez = fmaxf(fabsf(qz - A.z), fabsf(qz - B.z));
+          md = ex * ex + ey * ey + ez * ez;
+        }
+      }
+      float mm = md;
+#pragma unroll
+      for (int o = GROUP / 2; o > 0; o >>= 1) mm = fminf(mm, __shfl_xor_sync(FULL, mm, o, GROUP));
+      const unsigned gmask = (GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u)) << ((threadIdx.x & 31) & ~(GROUP - 1));
+      const unsigned who = __ballot_sync(FULL, walk && md == mm && md < INFINITY) & gmask;
+      if (walk && who) idx = idx * FANOUT + ((__ffs(who) - 1) & (GROUP - 1));
+    }
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (walk) p = __ldg(tv.pts + (size_t)idx * BUCKET + gl);
+    merge_candidates(t, walk ? dist2_exact(qx, qy, qz, p.x, p.y, p.z) : INFINITY, __float_as_int(p.w), walk);
+  }
+  // ---- exact best-first search, pruned by the (already tight) 5th distance
   int sp = 0;
-  if (active && tv.n > 0) { if (gl == 0) { st.item[0] = (unsigned)(tv.n_levels - 1) << 26; st.lb[0] = 0.f; } sp = 1; }
+  if (go) { if (gl == 0) { st.item[0] = (unsigned)(tv.n_levels - 1) << 26; st.lb[0] = 0.f; } sp = 1; }
   __syncwarp();
   while (__any_sync(FULL, sp > 0)) {
     // ---- pop (skip items that the shrinking bound has made useless)
@@ -257,38 +317,75 @@ __device__ __forceinline__ void group_knn5(const TreeView& tv, GroupStack& st, b
     if (__any_sync(FULL, is_node)) {
       const float lb = is_node ? box_lb(A.x, A.y, A.z, B.x, B.y, B.z, qx, qy, qz) : INFINITY;
       const bool q = is_node && lb < INFINITY && lb <= t.d[4];
-      // rank among the qualifying children, far first (so the nearest ends on top of the stack)
-      int rank = 0, nq = 0;
+      // push every qualifying child in one shot; the nearest one goes on top of the stack (it is popped next), the others in lane order
+      const unsigned wq = __ballot_sync(FULL, q);
+      const unsigned gmask = (GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u)) << ((threadIdx.x & 31) & ~(GROUP - 1));
+      const unsigned gq = wq & gmask;
+      const int nq = __popc(gq);
+      float mlb = q ? lb : INFINITY;
 #pragma unroll
-      for (int o = 0; o < GROUP; o++) {
-        const float olb = __shfl_sync(FULL, lb, o, GROUP); const bool oq = __shfl_sync(FULL, q ? 1 : 0, o, GROUP) != 0;
-        nq += oq ? 1 : 0;
-        if (oq && o != gl && (olb > lb || (olb == lb && o < gl))) rank++;
+      for (int o = GROUP / 2; o > 0; o >>= 1) mlb = fminf(mlb, __shfl_xor_sync(FULL, mlb, o, GROUP));
+      const unsigned near = __ballot_sync(FULL, q && lb == mlb) & gmask;
+      const int near_lane = __ffs(near) - 1;                       // warp lane of the nearest qualifying child (or -1)
+      const int me = threadIdx.x & 31;
+      if (q) {
+        const unsigned below = gq & ((1u << me) - 1u);
+        int pos = __popc(below); if (near_lane >= 0 && near_lane < me) pos--;   // rank among the non-nearest
+        if (me == near_lane) pos = nq - 1;
+        st.item[sp + pos] = (lv == 0 ? ITEM_BUCKET : ((unsigned)(lv - 1) << 26)) | (unsigned)(idx * FANOUT + gl); st.lb[sp + pos] = lb;
       }
-      if (q) { st.item[sp + rank] = (lv == 0 ? ITEM_BUCKET : ((unsigned)(lv - 1) << 26)) | (unsigned)(idx * FANOUT + gl); st.lb[sp + rank] = lb; }
       if (is_node) sp += nq;
     }
-    if (__any_sync(FULL, is_bucket)) {
-      const float d = is_bucket ? dist2_exact(qx, qy, qz, A.x, A.y, A.z) : INFINITY;
-      const int id = __float_as_int(A.w);
-      bool c = is_bucket && d < INFINITY && lex_less(d, id, t.d[4], t.id[4]);
-      while (__any_sync(FULL, c)) {
-        // group minimum of (d, id) among the remaining candidates
-        float md = c ? d : INFINITY; int mi = c ? id : 0x7fffffff;
-#pragma unroll
-        for (int o = GROUP / 2; o > 0; o >>= 1) {
-          const float od = __shfl_xor_sync(FULL, md, o, GROUP); const int oi = __shfl_xor_sync(FULL, mi, o, GROUP);
-          if (lex_less(od, oi, md, mi)) { md = od; mi = oi; }
-        }
-        if (md < INFINITY && lex_less(md, mi, t.d[4], t.id[4])) top5_insert(t, md, mi);
-        if (c && id == mi && d == md) c = false;
-        c = c && lex_less(d, id, t.d[4], t.id[4]);
-      }
-    }
+    if (__any_sync(FULL, is_bucket)) merge_candidates(t, is_bucket ? dist2_exact(qx, qy, qz, A.x, A.y, A.z) : INFINITY, __float_as_int(A.w), is_bucket);
     __syncwarp();   // pushes are visible before the next pop
   }
 }
 
+#if LL_GROUP == 8
+// ---- alternative mapping: ONE lane per query (32 queries per warp), used when there are enough queries to fill the machine.
+// Flat best-first loop: every iteration pops one item and issues ONE batch of independent 16-B loads whatever the item type
+// (16 for a node record, 8 for a bucket), so the warp's lanes stay aligned on memory round trips while their searches diverge.
+__device__ __forceinline__ void thread_knn5(const TreeView& tv, float qx, float qy, float qz, Top5& t) {
+#pragma unroll
+  for (int j = 0; j < LL_KNN; j++) { t.d[j] = INFINITY; t.id[j] = 0x7fffffff; }
+  if (tv.n <= 0) return;
+  unsigned stk_item[STACK_CAP]; float stk_lb[STACK_CAP]; int sp = 0;
+  stk_item[0] = (unsigned)(tv.n_levels - 1) << 26; stk_lb[0] = 0.f; sp = 1;
+  for (;;) {
+    unsigned item = 0; bool got = false;
+    while (sp > 0) { sp--; if (stk_lb[sp] <= t.d[4]) { item = stk_item[sp]; got = true; break; } }
+    if (!got) return;
+    const bool is_bucket = (item & ITEM_BUCKET) != 0;
+    const int lv = (int)((item >> 26) & 31u), idx = (int)(is_bucket ? (item & 0x7fffffffu) : (item & 0x03ffffffu));
+    const float4* addr = is_bucket ? tv.pts + (size_t)idx * BUCKET : tv.nodes[lv] + (size_t)idx * NODE_F4;
+    float4 r[16];
+#pragma unroll
+    for (int k = 0; k < 8; k++) r[k] = __ldg(addr + k);
+#pragma unroll
+    for (int k = 8; k < 16; k++) r[k] = is_bucket ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(addr + k);
+    if (is_bucket) {
+#pragma unroll
+      for (int k = 0; k < BUCKET; k++) {
+        const float d = dist2_exact(qx, qy, qz, r[k].x, r[k].y, r[k].z);
+        const int id = __float_as_int(r[k].w);
+        if (d < INFINITY && lex_less(d, id, t.d[4], t.id[4])) top5_insert(t, d, id);
+      }
+    } else {
+      float lb[8]; int best = -1; float bl = INFINITY;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        lb[c] = box_lb(r[2 * c].x, r[2 * c].y, r[2 * c].z, r[2 * c + 1].x, r[2 * c + 1].y, r[2 * c + 1].z, qx, qy, qz);
+        if (lb[c] < bl) { bl = lb[c]; best = c; }
+      }
+      const unsigned tag = lv == 0 ? ITEM_BUCKET : ((unsigned)(lv - 1) << 26);
+#pragma unroll
+      for (int c = 0; c < 8; c++) if (c != best && lb[c] < INFINITY && lb[c] <= t.d[4]) { stk_item[sp] = tag | (unsigned)(idx * FANOUT + c); stk_lb[sp] = lb[c]; sp++; }
+      if (best >= 0 && bl <= t.d[4]) { stk_item[sp] = tag | (unsigned)(idx * FANOUT + best); stk_lb[sp] = bl; sp++; }   // nearest child on top
+    }
+  }
+}
+
+#endif
 // Parity hook (ll_knn): world-frame queries in caller order.
 __global__ void __launch_bounds__(KNN_THREADS) knn_query_kernel(TreeView tv, const float4* __restrict__ q, int nq, int* __restrict__ idx5, float* __restrict__ d5) {
   __shared__ GroupStack stacks[GROUPS_PER_CTA];
@@ -296,7 +393,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query_kernel(TreeView tv, con
   const bool have = g < nq;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f); if (have) p = __ldg(&q[g]);
   const bool active = have && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
-  Top5 t; group_knn5(tv, stacks[threadIdx.x / GROUP], active, p.x, p.y, p.z, t);
+  Top5 t; group_knn5(tv, stacks[threadIdx.x / GROUP], active, p.x, p.y, p.z, t, nullptr);
   if (have && gl < LL_KNN) {
     float d = t.d[0]; int id = t.id[0];
 #pragma unroll
@@ -342,33 +439,17 @@ __global__ void query_key_kernel(KnnBlocksArgs a, unsigned* __restrict__ keys, i
   keys[i] = (is_corner ? 0u : 0x40000000u) | h; vals[i] = i;
 }
 
-// K6 + K7 fused: eight lanes per scan feature, features taken in spatially sorted order (perm).
-// Writes one residual-block slot per feature (indexed by the ORIGINAL feature order): blk_a[slot] = (a.x, a.y, a.z, type) with
-// type 0 invalid / 1 line / 2 plane, blk_v[slot*3..] = unit line direction or (un-normalised) plane normal, in fp64.
-__global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a) {
-  __shared__ GroupStack stacks[GROUPS_PER_CTA];
-  const int j = blockIdx.x * GROUPS_PER_CTA + (threadIdx.x / GROUP), gl = threadIdx.x & (GROUP - 1);
-  const int M = a.n_corner + a.n_surf;
-  const bool have = j < M;
-  const int w = have ? (a.perm ? a.perm[j] : j) : 0;      // original feature index
-  const bool is_corner = w < a.n_corner;
-  const TreeView& tv = is_corner ? a.corner : a.surf;
-  float4 f = make_float4(0.f, 0.f, 0.f, 0.f); if (have) f = __ldg(&a.feat[w]);
-  // pointAssociateToMap (non-deblur branch): p_w = q_curr * p + t_curr in fp64, stored as fp32
-  const double* qc = a.pose; const double* tc = a.pose + 4;
-  double wx, wy, wz; qrot_d(qc, (double)f.x, (double)f.y, (double)f.z, wx, wy, wz);
-  const float qx = (float)(wx + tc[0]), qy = (float)(wy + tc[1]), qz = (float)(wz + tc[2]);
-  const bool finite_in = isfinite(f.x) && isfinite(f.y) && isfinite(f.z);
-  bool owned = true;
-  if (a.world > 1) owned = cell_owner(qx, qy, qz, a.inv_cell, a.world) == (unsigned)a.rank;
-  const bool active = have && owned && finite_in;
-  Top5 t; group_knn5(tv, stacks[threadIdx.x / GROUP], active, qx, qy, qz, t);
-  if (!have || gl != 0) return;
+// Gates + functor constructors (K7) for one feature whose 5 nearest neighbours are in `t`; writes the residual-block slot `w`.
+__device__ __forceinline__ void emit_block(const KnnBlocksArgs& a, const TreeView& tv, bool is_corner, bool active, int w, const Top5& t) {
   int type = 0; double ax = 0, ay = 0, az = 0, vx = 0, vy = 0, vz = 0;
   if (active) {
-    if (a.knn_idx) {
+    if (a.seed_ids) {
 #pragma unroll
-      for (int k = 0; k < LL_KNN; k++) { a.knn_idx[w * LL_KNN + k] = (t.id[k] == 0x7fffffff) ? -1 : t.id[k]; a.knn_d[w * LL_KNN + k] = t.d[k]; }
+      for (int k = 0; k < LL_KNN; k++) a.seed_ids[(size_t)w * LL_KNN + k] = (t.id[k] == 0x7fffffff) ? -1 : t.id[k];
+    }
+    if (a.knn_d) {
+#pragma unroll
+      for (int k = 0; k < LL_KNN; k++) a.knn_d[w * LL_KNN + k] = t.d[k];
     }
     const bool found5 = t.id[4] != 0x7fffffff;
     if (is_corner) {
@@ -405,6 +486,37 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a
   a.blk_v[(size_t)w * 3 + 0] = vx; a.blk_v[(size_t)w * 3 + 1] = vy; a.blk_v[(size_t)w * 3 + 2] = vz;
 }
 
+// K6 + K7 fused, eight lanes per scan feature, features taken in spatially sorted order (perm).
+// Writes one residual-block slot per feature (indexed by the ORIGINAL feature order): blk_a[slot] = (a.x, a.y, a.z, type) with
+// type 0 invalid / 1 line / 2 plane, blk_v[slot*3..] = unit line direction or (un-normalised) plane normal, in fp64.
+template <int LANES>
+__global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a) {
+  __shared__ GroupStack stacks[LANES == GROUP ? GROUPS_PER_CTA : 1];
+  const int j = LANES == GROUP ? blockIdx.x * GROUPS_PER_CTA + (threadIdx.x / GROUP) : blockIdx.x * KNN_THREADS + threadIdx.x;
+  const int gl = LANES == GROUP ? (threadIdx.x & (GROUP - 1)) : 0;
+  const int M = a.n_corner + a.n_surf;
+  const bool have = j < M;
+  const int w = have ? (a.perm ? a.perm[j] : j) : 0;      // original feature index
+  const bool is_corner = w < a.n_corner;
+  const TreeView& tv = is_corner ? a.corner : a.surf;
+  float4 f = make_float4(0.f, 0.f, 0.f, 0.f); if (have) f = __ldg(&a.feat[w]);
+  // pointAssociateToMap (non-deblur branch): p_w = q_curr * p + t_curr in fp64, stored as fp32
+  const double* qc = a.pose; const double* tc = a.pose + 4;
+  double wx, wy, wz; qrot_d(qc, (double)f.x, (double)f.y, (double)f.z, wx, wy, wz);
+  const float qx = (float)(wx + tc[0]), qy = (float)(wy + tc[1]), qz = (float)(wz + tc[2]);
+  const bool finite_in = isfinite(f.x) && isfinite(f.y) && isfinite(f.z);
+  bool owned = true;
+  if (a.world > 1) owned = cell_owner(qx, qy, qz, a.inv_cell, a.world) == (unsigned)a.rank;
+  const bool active = have && owned && finite_in;
+  Top5 t;
+  if (LANES == GROUP) group_knn5(tv, stacks[LANES == GROUP ? threadIdx.x / GROUP : 0], active, qx, qy, qz, t, (a.seed_ids && have) ? a.seed_ids + (size_t)w * LL_KNN : nullptr);
+#if LL_GROUP == 8
+  else { if (active) thread_knn5(tv, qx, qy, qz, t); else { for (int k = 0; k < LL_KNN; k++) { t.d[k] = INFINITY; t.id[k] = 0x7fffffff; } } }
+#endif
+  if (!have || gl != 0) return;
+  emit_block(a, tv, is_corner, active, w, t);
+}
+
 int launch_knn_query(ll_ctx* ctx, const BucketTree& t, const float4* d_q, int nq, int* d_idx, float* d_d) {
   if (nq == 0) return LL_OK;
   knn_query_kernel<<<ll_div_up(nq, GROUPS_PER_CTA), KNN_THREADS, 0, ctx->stream>>>(make_view(t), d_q, nq, d_idx, d_d); ctx->launches++;
@@ -428,7 +540,12 @@ int launch_query_sort(ll_ctx* ctx, const KnnBlocksArgs& a, int* d_perm) {
 int launch_knn_blocks(ll_ctx* ctx, const KnnBlocksArgs& a) {
   int M = a.n_corner + a.n_surf;
   if (M == 0) return LL_OK;
-  knn_blocks_kernel<<<ll_div_up(M, GROUPS_PER_CTA), KNN_THREADS, 0, ctx->stream>>>(a); ctx->launches++;
+  static int mode = -1;   // LL_KNN_LANES=1|8 forces a mapping; default: one lane per query once there are enough queries to fill the SMs
+  if (mode < 0) { const char* e = getenv("LL_KNN_LANES"); mode = e ? atoi(e) : 0; }
+  const bool per_thread = LL_GROUP == 8 && (mode == 1 || (mode == 0 && M >= LL_KNN_THREAD_MIN));
+  if (per_thread) knn_blocks_kernel<1><<<ll_div_up(M, KNN_THREADS), KNN_THREADS, 0, ctx->stream>>>(a);
+  else knn_blocks_kernel<GROUP><<<ll_div_up(M, GROUPS_PER_CTA), KNN_THREADS, 0, ctx->stream>>>(a);
+  ctx->launches++;
   LL_CUDA(ctx, cudaGetLastError());
   return LL_OK;
 }
