@@ -9,7 +9,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
-int launch_inlier_select(ll_ctx* ctx, const double* d_l1, int M, double* d_sorted, double* d_unique, int* d_n_unique);
+int launch_inlier_select(ll_ctx* ctx, const double* d_l1, int M, double ratio, double* d_sorted, double* d_unique, int* d_n_unique);
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -21,14 +21,14 @@ struct RegArrays {
 static int reg_arrays(ll_ctx* ctx, int M, RegArrays* A) {
   int cap = M > ctx->cfg.max_features ? M : ctx->cfg.max_features;
   int scap = ctx->cfg.max_scan_points > cap ? ctx->cfg.max_scan_points : cap;
-  size_t bytes = align256((size_t)cap * 16) * 2 + align256((size_t)cap * 24) + align256((size_t)cap * 8) * 3 + align256((size_t)ctx->num_sms * 32 * 8) + 4096 +
+  size_t bytes = align256((size_t)cap * 16) * 2 + align256((size_t)cap * 24) + align256((size_t)cap * 8 + 64) * 3 + align256((size_t)ctx->num_sms * 32 * 8) + 4096 +
                  align256((size_t)cap * 20) * 2 + align256((size_t)cap * 4) * 2 + align256((size_t)scap * 16) * 3;
   LL_CUDA(ctx, ctx->reg_buf.reserve(bytes));
   char* p = ctx->reg_buf.as<char>();
   auto take = [&](size_t b) { char* r = p; p += align256(b); return r; };
   A->cap = cap;
   A->feat = (float4*)take((size_t)cap * 16); A->blk_a = (float4*)take((size_t)cap * 16); A->blk_v = (double*)take((size_t)cap * 24);
-  A->l1 = (double*)take((size_t)cap * 8); A->l1_sorted = (double*)take((size_t)cap * 8); A->l1_unique = (double*)take((size_t)cap * 8);
+  A->l1 = (double*)take((size_t)cap * 8); A->l1_sorted = (double*)take((size_t)cap * 8 + 64); A->l1_unique = (double*)take((size_t)cap * 8);
   A->partials = (double*)take((size_t)ctx->num_sms * 32 * 8);
   A->n_unique = (int*)take(256); A->counts = (int*)take(256); A->bounds = (float*)take(256); A->pose_tmp = (double*)take(256);
   A->knn_idx = (int*)take((size_t)cap * 20); A->knn_d = (float*)take((size_t)cap * 20); A->perm = (int*)take((size_t)cap * 4); A->tile_r2 = (float*)take((size_t)cap * 4);
@@ -307,7 +307,7 @@ static int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, i
     if (iter == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev2, s));
     LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 0, in->cere_prerun_times)));
     if (e) LL_CUDA(ctx, cudaEventRecord(e[2], s));
-    LL_TRY(launch_inlier_select(ctx, A.l1, M, A.l1_sorted, A.l1_unique, A.n_unique));
+    LL_TRY(launch_inlier_select(ctx, A.l1, M, in->inlier_ratio, A.l1_sorted, A.l1_unique, A.n_unique));
     if (e) LL_CUDA(ctx, cudaEventRecord(e[3], s));
     LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 1, in->cere_max_iterations)));
     if (e) LL_CUDA(ctx, cudaEventRecord(e[4], s));

@@ -88,7 +88,7 @@ int upload_cloud(ll_ctx* ctx, const void* src, size_t n, int fmt, int where, flo
 int launch_transform(ll_ctx* ctx, const double* d_pose7, const float4* d_in, int n, float4* d_out);
 // VoxelGrid on device: d_in [n] -> d_out [<= n], *d_n_out on device. n given by host, or by device count d_n_in (may be null).
 struct VoxelTemps { DevBuf* buf; };
-int launch_inlier_select(ll_ctx* ctx, const double* d_l1, int M, double* d_sorted, double* d_unique, int* d_n_unique);
+int launch_inlier_select(ll_ctx* ctx, const double* d_l1, int M, double ratio, double* d_sorted, double* d_unique, int* d_n_unique);
 int launch_voxel_grid(ll_ctx* ctx, const float4* d_in, int n_cap, const int* d_n_in, float leaf, float4* d_out, int* d_n_out);
 
 // ---------------------------------------------------------------------------------------------- extractor (extract.cu)

@@ -46,25 +46,43 @@ __device__ double d_angdist(const double a[4], const double b[4]) {
 __device__ void d_plus(const double x[7], const double delta[6], double bound, double out[7]) {
   double nd = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
   if (nd > 0.0) {
-    double sbd = sin(nd) / nd;
-    double dq[4] = {cos(nd), sbd * delta[0], sbd * delta[1], sbd * delta[2]}, q[4] = {x[3], x[0], x[1], x[2]}, r[4];
+    double sn, cs; sincos(nd, &sn, &cs);
+    const double sbd = sn / nd;
+    double dq[4] = {cs, sbd * delta[0], sbd * delta[1], sbd * delta[2]}, q[4] = {x[3], x[0], x[1], x[2]}, r[4];
     d_qmul(dq, q, r); out[0] = r[1]; out[1] = r[2]; out[2] = r[3]; out[3] = r[0];
   } else { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3]; }
   for (int k = 0; k < 3; k++) { double v = x[4 + k] + delta[3 + k]; out[4 + k] = fmin(fmax(v, -bound), bound); }
 }
-__device__ bool d_chol6(const double A[6][6], const double b[6], double x[6]) {
-  double L[6][6];
-  for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) L[i][j] = 0;
+__device__ __forceinline__ bool d_chol6(const double A[6][6], const double b[6], double x[6]) {
+  double L[6][6], inv[6];
+#pragma unroll
   for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < 6; j++) L[i][j] = 0;
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+#pragma unroll
     for (int j = 0; j <= i; j++) {
-      double s = A[i][j]; for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
-      if (i == j) { if (!(s > 0.0)) return false; L[i][i] = sqrt(s); } else L[i][j] = s / L[j][j];
+      double s = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+      if (i == j) { if (!(s > 0.0)) ok = false; L[i][i] = sqrt(s); inv[i] = 1.0 / L[i][i]; } else L[i][j] = s * inv[j];
     }
+  }
+  if (!ok) return false;
   double y[6];
-  for (int i = 0; i < 6; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[i][k] * y[k]; y[i] = s / L[i][i]; }
-  for (int i = 5; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k]; x[i] = s / L[i][i]; }
-  for (int i = 0; i < 6; i++) if (!isfinite(x[i])) return false;
-  return true;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { double s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s -= L[i][k] * y[k]; y[i] = s * inv[i]; }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) { double s = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k]; x[i] = s * inv[i]; }
+#pragma unroll
+  for (int i = 0; i < 6; i++) if (!isfinite(x[i])) ok = false;
+  return ok;
 }
 __device__ __forceinline__ int hidx(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }  // i <= j, upper-triangular row-major
 
@@ -193,7 +211,7 @@ __device__ void lm_accept_test(LmState& L, const double* sums, double bound) {
     double n = 0; for (int k = 0; k < 7; k++) n += L.x[k] * L.x[k]; L.x_norm = sqrt(n);
     L.x_cost = cand_cost; for (int i = 0; i < 21; i++) L.H[i] = sums[i]; for (int i = 0; i < 6; i++) L.g[i] = sums[21 + i];
     L.last_gmax = lm_gmax(L, bound); L.last_successful = 1;
-    L.radius = L.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0)); L.radius = fmin(1e16, L.radius);
+    { const double c1 = 2.0 * rel - 1.0; L.radius = L.radius / fmax(1.0 / 3.0, 1.0 - c1 * c1 * c1); } L.radius = fmin(1e16, L.radius);
     L.decrease_factor = 2.0; L.reuse_diagonal = 0;
     L.min_iter_cost = fmin(L.min_iter_cost, L.x_cost);
     if (L.x_cost < L.minimum_cost) { L.minimum_cost = L.x_cost; for (int k = 0; k < 7; k++) L.x_best[k] = L.x[k]; }
@@ -329,6 +347,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
   __shared__ double s_red[SOLVE_THREADS / 32][NSUM + 1];
   __shared__ double s_sum[32];
   __shared__ int s_flag;
+  __shared__ LmState s_lm;   // used by CTA 0 only: the solver state never leaves the chip during a solve
   RegDevState* st = a.st;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cap = tiles_per_cta * SOLVE_THREADS;
@@ -358,13 +377,22 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
     }
     S.type[li] = type;
   }
-  // ---- iteration zero trial point
+  // ---- iteration zero trial point: Plus(x, 0), the projection of the start point onto the bounds (TrustRegionMinimizer::IterationZero).
+  // Every CTA computes the same value; CTA 0 (the master) owns the solver state in its shared memory for the whole solve.
   unsigned gen = ld_acquire_u32(&st->bar_gen);
+  const bool master = blockIdx.x == 0;
   if (tid == 0) {
-    double tr[7];
-    for (int k = 0; k < 7; k++) tr[k] = st->lm.trial[k];   // written by lm_reset_kernel (stream-ordered before this kernel)
+    double x0[7], z[6] = {0, 0, 0, 0, 0, 0}, tr[7];
+    for (int k = 0; k < 7; k++) x0[k] = st->x[k];
+    d_plus(x0, z, st->bound, tr);
     setup_const(E, tr, st);
     s_flag = 0;
+    if (master) {
+      LmState& L = s_lm;
+      L.phase = 0; L.iteration = 0; L.max_iterations = a.max_iterations; L.num_invalid = 0; L.done = 0; L.termination = 0; L.last_successful = 1; L.reuse_diagonal = 0;
+      L.ls_iters = 0; L.n_valid = 0; L.total_iterations = 0; L.total_evaluations = 0;
+      for (int k = 0; k < 7; k++) L.trial[k] = tr[k];
+    }
   }
   __syncthreads();
 
@@ -406,10 +434,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
     }
     __threadfence();
     __syncthreads();
-    // ---- ticket barrier: the last CTA reduces the grid and advances the solver
-    if (tid == 0) { unsigned t = atomicAdd(&st->bar_count, 1u); s_flag = (t == gridDim.x - 1) ? 1 : 0; }
-    __syncthreads();
-    if (s_flag) {
+    // ---- grid barrier: every CTA arrives; the master waits for all of them, reduces the grid in fixed order and advances the solver
+    if (tid == 0) atomicAdd(&st->bar_count, 1u);
+    if (master) {
+      if (tid == 0) { while (ld_acquire_u32(&st->bar_count) != gridDim.x) {} st->bar_count = 0; }
+      __syncthreads();
       __threadfence();
       const int val = tid & 31, grp = tid >> 5;   // 16 groups x 32 values
       double v = 0;
@@ -437,12 +466,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
       }
       __syncthreads();
       if (tid == 0) {
-        LmState& L = st->lm;
+        LmState& L = s_lm;
         if (a.mode == 3) { for (int i = 0; i < 21; i++) L.H[i] = s_sum[i]; for (int i = 0; i < 6; i++) L.g[i] = s_sum[21 + i]; L.x_cost = s_sum[27]; L.n_valid = (int)(s_sum[28] + 0.5); L.done = 1; }
         else lm_step(L, s_sum, st->bound);
-        if (L.done && a.mode != 3) {
-          for (int k = 0; k < 7; k++) st->x[k] = L.x_best[k];
-          st->total_lm_iterations += L.iteration; st->total_evaluations += L.total_evaluations;
+        // publish the next trial point (or the result)
+        st->lm.done = L.done;
+        if (!L.done) { for (int k = 0; k < 7; k++) st->lm.trial[k] = L.trial[k]; }
+        else {
+          st->lm = L;   // whole solver state (parity hooks / host diagnostics read it)
+          if (a.mode != 3) {
+            for (int k = 0; k < 7; k++) st->x[k] = L.x_best[k];
+            st->total_lm_iterations += L.iteration; st->total_evaluations += L.total_evaluations;
+          }
           if (a.mode == 1) {   // :514-531 pose composition + ICP termination test
             double qi[4] = {L.x_best[3], L.x_best[0], L.x_best[1], L.x_best[2]}, ti[3] = {L.x_best[4], L.x_best[5], L.x_best[6]};
             const double* ql = st->pose_last; double tcur[3], qcur[4];
@@ -458,12 +493,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
             st->icp_iter++;
           }
         }
-        st->bar_count = 0;
         __threadfence();
         st_release_u32(&st->bar_gen, gen + 1);
       }
     } else {
-      if (tid == 0) { while (ld_acquire_u32(&st->bar_gen) != gen + 1) { __nanosleep(20); } }
+      if (tid == 0) { while (ld_acquire_u32(&st->bar_gen) != gen + 1) {} }
     }
     gen++;
     __syncthreads();
@@ -525,7 +559,6 @@ int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
     LL_CUDA(ctx, cudaFuncSetAttribute(lm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_MAX_SMEM));
     attr_set[ctx->device] = true;
   }
-  lm_reset_kernel<<<1, 1, 0, ctx->stream>>>(a.st, a.max_iterations); ctx->launches++;
   SolveArgs args = a; void* kargs[] = {&args, &tiles_per_cta};
   LL_CUDA(ctx, cudaLaunchCooperativeKernel((void*)lm_solve_kernel, dim3(grid), dim3(SOLVE_THREADS), kargs, smem, ctx->stream));
   ctx->launches++;
