@@ -1,0 +1,48 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/loamlivox_b200.h declares,
+its POD structs have the sizes the ctypes mirror assumes, and it refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+from loam_livox_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "loamlivox_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ll_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_every_declared_symbol_is_exported():
+    L = capi.lib()
+    names = _declared()
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(capi.EXPORTS) == names, (set(capi.EXPORTS) ^ set(names))
+
+
+def test_pod_layouts_match_the_header():
+    assert C.sizeof(capi.Config) == 7 * 4 + 2 * 4
+    assert C.sizeof(capi.RegState) == 10 * 4 + 12 * 8 + (4 + 3 + 4 + 3 + 7) * 8
+    assert C.sizeof(capi.RegResult) == 8 * 4 + (4 + 3 + 4 + 3) * 8 + 5 * 8 + 6 * 4
+    assert C.sizeof(capi.PipelineCfg) == 7 * 4
+    s = capi.default_reg_state()
+    assert (s.icp_max_iterations, s.cere_max_iterations, s.cere_prerun_times) == (15, 50, 2)        # performance_precision.yaml:25-26, :91
+    assert (s.maximum_dis_line_for_match, s.maximum_dis_plane_for_match, s.huber_a) == (2.0, 50.0, 0.1)   # point_cloud_registration.hpp:64-65,220
+    assert (s.inliner_dis, s.inlier_ratio, s.para_max_speed, s.para_max_angular_rate) == (0.02, 0.8, 0.3, 20.0)
+    c = capi.default_config()
+    assert abs(c.corner_curvature - 0.1) < 1e-7 and abs(c.surface_curvature - 0.005) < 1e-9 and c.minimum_view_angle == 5.0
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to construct a context; nothing routes through the oracle or PyTorch."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    h = C.c_void_p()
+    assert capi.lib().ll_ctx_create(None, 0, C.byref(h)) == capi.LL_ERR_CUDA and not h.value
+    src = "".join(open(os.path.join(ROOT, "loam_livox_b200", f)).read() for f in ("capi.py", "registration.py", "distributed.py", "__init__.py"))
+    assert "oracle" not in src.replace("no CPU or PyTorch fallback", "")

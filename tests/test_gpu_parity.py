@@ -219,3 +219,67 @@ def test_scan_to_pose_matches_staged_oracle(ctx, oracle):
     assert res.status == ost and res.icp_iterations == ores.icp_iterations
     assert np.linalg.norm(np.array(res.t_w_curr) - np.array(ores.t_w_curr)) < 1e-6
     assert S.quat_angle(np.array(res.q_w_curr), np.array(ores.q_w_curr)) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- committed golden vectors
+def test_gpu_matches_golden_file(ctx):
+    """The CUDA path against tests/golden/golden_small.npz (made by tests/golden/make_golden.py from the oracle)."""
+    import os
+    from loam_livox_b200.registration import Livox_laser, Map, Point_cloud_registration, voxel_grid_filter
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_small.npz"))
+    gl = Livox_laser(ctx)
+    assert gl.extract_laser_features(g["raw"], 100.0) == int(g["n_scans"])
+    info = gl.point_info()
+    for k in ("pt_type", "pt_label", "curvature", "view_angle"):
+        assert np.array_equal(info[k], g[k], equal_nan=True), k
+    assert np.array_equal(gl.split_idx(), g["split_idx"])
+    c, s, f = gl.get_features(0.0, 1.0)
+    assert np.array_equal(c, g["corners"]) and np.array_equal(s, g["surface"]) and f.shape[0] == int(g["n_full"])
+    ps, pe = gl.piece_bounds(3)
+    assert np.array_equal(ps, g["piece_start"]) and np.array_equal(pe, g["piece_end"])
+    assert np.array_equal(voxel_grid_filter(ctx, g["map_surf"], 0.4), g["voxel"])
+    m = Map(ctx, g["map_corner"], g["map_surf"])
+    ki, kd = m.nearestKSearch(1, g["knn_q"])
+    assert np.array_equal(ki, g["knn_idx"]) and np.array_equal(kd, g["knn_d2"])
+    reg = Point_cloud_registration(ctx)
+    reg.set_pose(g["guess_q"], g["guess_t"])
+    typ, a3, v3, ca, sa = reg.build_blocks(m, g["feat_corner"], g["feat_surf"])
+    assert (ca, sa, int((typ != 0).sum())) == (int(g["corner_avail"]), int(g["surf_avail"]), int(g["n_blocks"]))
+    H, gr, cost = reg.normal_equations(g["eval_x"])
+    assert abs(cost - float(g["eval_cost"])) <= 1e-10 * float(g["eval_cost"]) and np.allclose(H, g["eval_H"], rtol=1e-9, atol=1e-9 * np.abs(g["eval_H"]).max())
+    assert np.allclose(gr, g["eval_g"], rtol=1e-9, atol=1e-9 * np.abs(g["eval_g"]).max())
+    st = reg.find_out_incremental_transfrom(m, g["feat_corner"], g["feat_surf"])
+    r = reg.result
+    assert st == int(g["reg_status"]) and r.icp_iterations == int(g["reg_iters"]) and r.num_residual_blocks == int(g["reg_blocks"])
+    assert np.linalg.norm(np.array(r.t_w_curr) - g["reg_t"]) < 1e-7 and S.quat_angle(np.array(r.q_w_curr), g["reg_q"]) < 1e-7
+    assert abs(r.final_cost - float(g["reg_final_cost"])) <= 1e-7 * float(g["reg_final_cost"])
+    assert abs(r.inlier_threshold - float(g["reg_inlier_thr"])) <= 1e-7 * float(g["reg_inlier_thr"])
+
+
+def test_register_edge_cases(ctx, oracle):
+    from loam_livox_b200.registration import Map, Point_cloud_registration, LoamLivoxError
+    mc, ms, fc, fs, pose = _mk(500, 4500, 200, 1800)
+    m = Map(ctx, mc, ms)
+    # ragged inputs: no corner features at all / a NaN corner feature / pcl::PointXYZI (32-byte) layout
+    reg = Point_cloud_registration(ctx)
+    reg.set_pose(pose.q, pose.t)
+    assert reg.find_out_incremental_transfrom(m, np.zeros((0, 4), np.float32), fs) == 1 and reg.result.corner_used == 0
+    fc2 = fc.copy(); fc2[3, 0] = np.nan
+    pcl = lambda a: np.concatenate([a[:, :3], np.ones((a.shape[0], 1), np.float32), a[:, 3:4], np.zeros((a.shape[0], 3), np.float32)], axis=1)
+    reg2 = Point_cloud_registration(ctx)
+    reg2.set_pose(pose.q, pose.t)
+    assert reg2.find_out_incremental_transfrom(m, pcl(fc2), pcl(fs)) == 1
+    p = oracle.default_params(q_w_last=pose.q, t_w_last=pose.t, q_w_curr=pose.q, t_w_curr=pose.t)
+    ost, ores = oracle.register(mc, oracle.KdTree(mc), ms, oracle.KdTree(ms), fc2, fs, p)
+    assert reg2.result.corner_used == ores.corner_used and np.linalg.norm(np.array(reg2.result.t_w_curr) - np.array(ores.t_w_curr)) < 1e-7
+    # features far from the map: every gate fails -> explicit error instead of the reference's undefined behaviour
+    far = fs.copy(); far[:, :3] += 500.0
+    reg3 = Point_cloud_registration(ctx)
+    reg3.set_pose(pose.q, pose.t)
+    with pytest.raises(LoamLivoxError):
+        reg3.find_out_incremental_transfrom(m, far[:50], far)
+    # the residual-block cap would bind -> refused (the reference drops blocks at random there)
+    reg4 = Point_cloud_registration(ctx, maximum_allow_residual_block=100)
+    reg4.set_pose(pose.q, pose.t)
+    with pytest.raises(LoamLivoxError):
+        reg4.find_out_incremental_transfrom(m, fc, fs)

@@ -1,0 +1,63 @@
+"""world_size-2 gloo tests (CPU) of the host-side multi-GPU logic: the one-time IPC-handle all-gather, the cell ownership that
+splits the queries, and the fact that per-rank normal equations summed in rank order equal the single-rank ones."""
+import os
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from loam_livox_b200 import synthetic as S
+    from loam_livox_b200.distributed import all_gather_handles, cell_owner
+    from oracle import oracle as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # 1. handle exchange
+    mine = bytes([rank + 1] * 64)
+    blob = all_gather_handles(mine, world, dist)
+    ok_handles = blob == b"".join(bytes([r + 1] * 64) for r in range(world))
+    # 2. ownership partitions the queries, 3. the reduced normal equations equal the unsharded ones
+    mc, ms = S.make_map(1000, 9000)
+    pose = S.default_pose()
+    fc, fs = S.make_features(100, 900, pose)
+    guess = S.perturb_pose(pose, np.random.default_rng(0))
+    p = O.default_params(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t)
+    blocks, src, _, _ = O.build_blocks(mc, O.KdTree(mc), ms, O.KdTree(ms), fc, fs, p)
+    feats = np.concatenate([fc, fs])
+    slot = src[:, 1] + np.where(src[:, 0] == 1, fc.shape[0], 0)
+    world_pts = O.transform(feats, guess.q, guess.t)
+    own = cell_owner(world_pts, 8.0, world)
+    x = O.plus([0, 0, 0, 1, 0, 0, 0], [0.01, -0.02, 0.015, 0.05, -0.04, 0.03])
+    mine_blocks = blocks[own[slot] == rank]
+    c, g, H = O.evaluate(mine_blocks, guess.q, guess.t, x) if len(mine_blocks) else (0.0, np.zeros(6), np.zeros((6, 6)))
+    part = torch.tensor(np.concatenate([[c], g, H.ravel(), [len(mine_blocks)]]))
+    parts = [torch.zeros_like(part) for _ in range(world)]
+    dist.all_gather(parts, part)
+    total = sum(parts[r] for r in range(world)).numpy()      # fixed rank order, like the in-kernel reduction
+    cf, gf, Hf = O.evaluate(blocks, guess.q, guess.t, x)
+    ok_sum = abs(total[0] - cf) <= 1e-12 * cf and np.allclose(total[1:7], gf, rtol=1e-10, atol=1e-12) and np.allclose(total[7:43].reshape(6, 6), Hf, rtol=1e-10)
+    ok_part = int(total[43]) == blocks.shape[0] and own.min() >= 0 and own.max() < world and len(set(own.tolist())) == world
+    q.put((rank, ok_handles, ok_sum, ok_part))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_host_protocol():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] and r[2] and r[3] for r in res), res
