@@ -243,11 +243,19 @@ struct GroupStack { unsigned item[STACK_CAP]; float lb[STACK_CAP]; };
 __device__ __forceinline__ void merge_candidates(Top5& t, float d, int id, bool c) {
   c = c && d < INFINITY && lex_less(d, id, t.d[4], t.id[4]) && id != t.id[0] && id != t.id[1] && id != t.id[2] && id != t.id[3];
   while (__any_sync(FULL, c)) {
-    float md = c ? d : INFINITY; int mi = c ? id : 0x7fffffff;   // group minimum of (d, id) among the remaining candidates
+    float md; int mi;   // group minimum of (d, id) among the remaining candidates
+    if (GROUP == 32) {   // whole-warp group: two REDUX instructions (non-negative floats order like their bit patterns)
+      const unsigned key = c ? __float_as_uint(d) : 0xffffffffu;
+      const unsigned mn = __reduce_min_sync(FULL, key);
+      mi = (int)__reduce_min_sync(FULL, (c && key == mn) ? (unsigned)id : 0x7fffffffu);
+      md = mn == 0xffffffffu ? INFINITY : __uint_as_float(mn);
+    } else {
+      md = c ? d : INFINITY; mi = c ? id : 0x7fffffff;
 #pragma unroll
-    for (int o = GROUP / 2; o > 0; o >>= 1) {
-      const float od = __shfl_xor_sync(FULL, md, o, GROUP); const int oi = __shfl_xor_sync(FULL, mi, o, GROUP);
-      if (lex_less(od, oi, md, mi)) { md = od; mi = oi; }
+      for (int o = GROUP / 2; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(FULL, md, o, GROUP); const int oi = __shfl_xor_sync(FULL, mi, o, GROUP);
+        if (lex_less(od, oi, md, mi)) { md = od; mi = oi; }
+      }
     }
     if (md < INFINITY && lex_less(md, mi, t.d[4], t.id[4])) top5_insert(t, md, mi);
     if (c && id == mi && d == md) c = false;

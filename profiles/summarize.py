@@ -1,0 +1,39 @@
+"""Turns the ncu captures brought back in gpurun_out/ into the text summaries committed here.
+usage: python profiles/summarize.py <report.ncu-rep> <out.txt> [title]"""
+import csv
+import subprocess
+import sys
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    title = sys.argv[3] if len(sys.argv) > 3 else rep
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, body = rows[0], rows[1], rows[2:]
+    lines = [title, "source: ncu --set full --clock-control none --import-source on (one GPU, under gpurun); per-launch values", ""]
+    for r in body:
+        lines.append("kernel: " + r[hdr.index("Kernel Name")][:100])
+        for w in WANT:
+            if w in hdr:
+                lines.append(f"  {w:90s} {r[hdr.index(w)]:>18s} {units[hdr.index(w)]}")
+        if "dram__bytes_read.sum" in hdr:
+            def val(name):
+                v, u = float(r[hdr.index(name)].replace(",", "")), units[hdr.index(name)]
+                return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            lines.append(f"  traffic (dram read + write) = {(val('dram__bytes_read.sum') + val('dram__bytes_write.sum')) / 1e6:.3f} MB per launch")
+        lines.append("")
+    open(out, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines[:40]))
+
+
+if __name__ == "__main__":
+    main()
