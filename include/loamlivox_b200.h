@@ -185,6 +185,29 @@ typedef struct {
 int ll_scan_to_pose(ll_ctx* ctx, const ll_map* map, const void* raw, size_t n, int fmt, int where, double stamp,
                     const ll_pipeline_cfg* pc, const ll_reg_state* in, ll_reg_result* out, int* n_corner_used, int* n_surf_used);
 
+/* ---- a14: device-resident voxel-cell map (matching_mode 1) ---------------------------------------------- */
+/* Replaces Points_cloud_map<float> as the matching path uses it (cell_map_keyframe.hpp:476-1000): `resolution` is what
+ * Laser_mapping passes to set_resolution (1.0 => 0.5 m cells, :674-679), `revisit_threshold` = m_minimum_revisit_threshold
+ * (common/threshold_cell_revisit).  max_cells sizes the hash table (0 = 1 Mi cells). */
+typedef struct ll_cellmap ll_cellmap;
+int  ll_cellmap_create(ll_ctx* ctx, float resolution, int revisit_threshold, int max_cells, ll_cellmap** out);
+void ll_cellmap_release(ll_cellmap* map);
+/* Points_cloud_map::append_cloud (cell_map_keyframe.hpp:619-672; first call = set_point_cloud :578-617). xyz only. */
+int  ll_cellmap_append(ll_ctx* ctx, ll_cellmap* map, const void* pts, size_t n, int fmt, int where);
+/* update_buff_for_matching, matching_mode 1, for one of the two maps (laser_mapping.hpp:475-516): find_cells_in_radius(t, search_range)
+ * (cell_map_keyframe.hpp:761-788) + if_pt_in_fov (laser_mapping.hpp:310-324) + per-cell VoxelGrid(leaf) + optional down-sample-and-replace
+ * (m_down_sample_replace).  The concatenated cloud stays on the device (*out_dev, valid until the next call on this map) and is copied to
+ * out_host (cap points) when out_host != NULL.  Cells are visited in ascending (k, j, i) index order (the PCL octree order is unspecified). */
+int  ll_cellmap_assemble(ll_ctx* ctx, ll_cellmap* map, const double q_w_curr[4], const double t_w_curr[3], float search_range, float fov_deg, float leaf,
+                         int down_sample_replace, ll_point* out_host, size_t cap, size_t* n_out, int* cells_in_fov, const ll_point** out_dev);
+int  ll_cellmap_stats(ll_ctx* ctx, ll_cellmap* map, int* cells, int* stored_points, int* frame_idx);
+
+/* ---- device-to-device forms used when chaining stages without leaving the GPU (outputs in caller-provided device buffers) ------------- */
+int ll_voxel_downsample_dev(ll_ctx* ctx, const ll_point* in_dev, size_t n, float leaf, ll_point* out_dev, size_t* n_out);
+int ll_transform_dev(ll_ctx* ctx, const double q_wxyz[4], const double t[3], const ll_point* in_dev, size_t n, ll_point* out_dev);
+/* Device pointers to the features of the last ll_register / ll_scan_to_pose on this context (scan frame, corners then surfaces). */
+int ll_last_features_dev(ll_ctx* ctx, const ll_point** corner_dev, size_t* n_corner, const ll_point** surf_dev, size_t* n_surf);
+
 /* ---- multi-GPU ------------------------------------------------------------------------------------- */
 /* One process per GPU.  The 28-double normal equations (+4 counters) are all-reduced inside the solver kernel
  * through peer-mapped staging buffers (CUDA IPC over NVLink); the host only exchanges the IPC handles once. */

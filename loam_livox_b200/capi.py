@@ -22,7 +22,8 @@ EXPORTS = [
     "ll_config_default", "ll_ctx_create", "ll_ctx_destroy", "ll_last_error", "ll_ctx_stream", "ll_ctx_sync", "ll_extract", "ll_extract_reset", "ll_piece_bounds",
     "ll_get_features", "ll_extract_point_info", "ll_extract_split_idx", "ll_voxel_downsample", "ll_map_build", "ll_map_release", "ll_map_size",
     "ll_map_build_sharded", "ll_knn", "ll_reg_state_default", "ll_register", "ll_build_blocks", "ll_normal_equations", "ll_solve", "ll_transform",
-    "ll_scan_to_pose", "ll_comm_local_handle", "ll_comm_connect", "ll_launch_count",
+    "ll_scan_to_pose", "ll_comm_local_handle", "ll_comm_connect", "ll_launch_count", "ll_cellmap_create", "ll_cellmap_release", "ll_cellmap_append",
+    "ll_cellmap_assemble", "ll_cellmap_stats", "ll_voxel_downsample_dev", "ll_transform_dev", "ll_last_features_dev",
 ]
 
 
@@ -101,6 +102,14 @@ def lib():
     L.ll_scan_to_pose.argtypes = [vp, vp, vp, sz, ci, ci, cd, C.POINTER(PipelineCfg), C.POINTER(RegState), C.POINTER(RegResult), C.POINTER(ci), C.POINTER(ci)]
     L.ll_comm_local_handle.argtypes = [vp, vp]
     L.ll_comm_connect.argtypes = [vp, ci, ci, vp]
+    L.ll_cellmap_create.argtypes = [vp, cf, ci, ci, C.POINTER(vp)]
+    L.ll_cellmap_release.argtypes = [vp]
+    L.ll_cellmap_append.argtypes = [vp, vp, vp, sz, ci, ci]
+    L.ll_cellmap_assemble.argtypes = [vp, vp, vp, vp, cf, cf, cf, ci, vp, sz, C.POINTER(sz), C.POINTER(ci), C.POINTER(vp)]
+    L.ll_cellmap_stats.argtypes = [vp, vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
+    L.ll_voxel_downsample_dev.argtypes = [vp, vp, sz, cf, vp, C.POINTER(sz)]
+    L.ll_transform_dev.argtypes = [vp, vp, vp, vp, sz, vp]
+    L.ll_last_features_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
     L.ll_launch_count.argtypes = [vp]
     L.ll_launch_count.restype = C.c_uint64
     _LIB = L

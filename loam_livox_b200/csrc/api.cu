@@ -15,7 +15,7 @@ static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct RegArrays {
   float4* feat; float4* blk_a; double* blk_v; double* l1; double* l1_sorted; double* l1_unique; double* partials;
-  int* n_unique; int* knn_idx; float* knn_d; int* perm; float* tile_r2; float4* tmp_a; float4* tmp_b; float4* tmp_c; int* counts; float* bounds; double* pose_tmp;
+  int* n_unique; int* knn_idx; float* knn_d; int* perm; float4* tmp_a; float4* tmp_b; float4* tmp_c; int* counts; float* bounds; double* pose_tmp;
   int cap;
 };
 static int reg_arrays(ll_ctx* ctx, int M, RegArrays* A) {
@@ -31,7 +31,7 @@ static int reg_arrays(ll_ctx* ctx, int M, RegArrays* A) {
   A->l1 = (double*)take((size_t)cap * 8); A->l1_sorted = (double*)take((size_t)cap * 8 + 64); A->l1_unique = (double*)take((size_t)cap * 8);
   A->partials = (double*)take((size_t)ctx->num_sms * 32 * 8);
   A->n_unique = (int*)take(256); A->counts = (int*)take(256); A->bounds = (float*)take(256); A->pose_tmp = (double*)take(256);
-  A->knn_idx = (int*)take((size_t)cap * 20); A->knn_d = (float*)take((size_t)cap * 20); A->perm = (int*)take((size_t)cap * 4); A->tile_r2 = (float*)take((size_t)cap * 4);
+  A->knn_idx = (int*)take((size_t)cap * 20); A->knn_d = (float*)take((size_t)cap * 20); A->perm = (int*)take((size_t)cap * 4);
   A->tmp_a = (float4*)take((size_t)scap * 16); A->tmp_b = (float4*)take((size_t)scap * 16); A->tmp_c = (float4*)take((size_t)scap * 16);
   return LL_OK;
 }
@@ -207,6 +207,39 @@ int ll_transform(ll_ctx* ctx, const double q[4], const double t[3], const void* 
   return LL_OK;
 }
 
+int ll_voxel_downsample_dev(ll_ctx* ctx, const ll_point* in_dev, size_t n, float leaf, ll_point* out_dev, size_t* n_out) {
+  if (!ctx || !n_out || !(leaf > 0.f)) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  *n_out = 0; if (n == 0) return LL_OK;
+  LL_CUDA(ctx, ctx->feat_buf.reserve(512));
+  int* d_n = ctx->feat_buf.as<int>();
+  LL_TRY(launch_voxel_grid(ctx, (const float4*)in_dev, (int)n, nullptr, leaf, (float4*)out_dev, d_n));
+  int* h = (int*)ctx->pinned;
+  LL_CUDA(ctx, cudaMemcpyAsync(h, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_out = (size_t)h[0];
+  return LL_OK;
+}
+int ll_transform_dev(ll_ctx* ctx, const double q[4], const double t[3], const ll_point* in_dev, size_t n, ll_point* out_dev) {
+  if (!ctx || !q || !t) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (n == 0) return LL_OK;
+  LL_CUDA(ctx, ctx->feat_buf.reserve(512));
+  double* d_pose = (double*)((char*)ctx->feat_buf.p + 256);
+  double* h = (double*)((char*)ctx->pinned + 1024); for (int k = 0; k < 4; k++) h[k] = q[k]; for (int k = 0; k < 3; k++) h[4 + k] = t[k];
+  LL_CUDA(ctx, cudaMemcpyAsync(d_pose, h, 7 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  LL_TRY(launch_transform(ctx, d_pose, (const float4*)in_dev, (int)n, (float4*)out_dev));
+  LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return LL_OK;
+}
+int ll_last_features_dev(ll_ctx* ctx, const ll_point** corner_dev, size_t* n_corner, const ll_point** surf_dev, size_t* n_surf) {
+  if (!ctx) return LL_ERR_INVALID;
+  RegArrays A; LL_TRY(reg_arrays(ctx, 0, &A));
+  if (corner_dev) *corner_dev = (const ll_point*)A.feat; if (n_corner) *n_corner = (size_t)ctx->last_nc;
+  if (surf_dev) *surf_dev = (const ll_point*)(A.feat + ctx->last_nc); if (n_surf) *n_surf = (size_t)ctx->last_ns;
+  return LL_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- S2
 static int map_build_common(ll_ctx* ctx, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where, ll_map** out) {
   if (!ctx || !out) return LL_ERR_INVALID;
@@ -262,7 +295,7 @@ static KnnBlocksArgs knn_args(ll_ctx* ctx, const ll_map* map, const RegArrays& A
   a.pose = ctx->d_reg->pose_curr; a.max_dis_line = in->maximum_dis_line_for_match; a.max_dis_plane = in->maximum_dis_plane_for_match;
   a.icp_line = in->icp_line; a.icp_plane = in->icp_plane; a.blk_a = A.blk_a; a.blk_v = A.blk_v;
   a.corner_avail = &ctx->d_reg->corner_avail; a.surf_avail = &ctx->d_reg->surf_avail;
-  a.seed_ids = A.knn_idx; a.knn_d = debug ? A.knn_d : nullptr; a.perm = A.perm; a.tile_r2 = A.tile_r2; a.stats = &ctx->d_reg->knn_tiles;
+  a.seed_ids = A.knn_idx; a.knn_d = debug ? A.knn_d : nullptr; a.perm = A.perm;
   a.rank = map->rank; a.world = map->world; a.inv_cell = map->cell_size > 0.f ? 1.0f / map->cell_size : 1.0f;
   return a;
 }
@@ -283,6 +316,7 @@ static int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, i
   // gate (:199): CORNER_MIN_MAP_NUM 0, SURFACE_MIN_MAP_NUM 50
   if (!(map->corner.n_src > 0 && map->surf.n_src > 50 && in->current_frame_index > in->mapping_init_accumulate_frames)) return LL_OK;
   const int M = nc + ns;
+  ctx->last_nc = nc; ctx->last_ns = ns;
   if (nc > 2 * in->maximum_allow_residual_block || ns > 2 * in->maximum_allow_residual_block) { ctx->set_error("feature count exceeds 2 x maximum_allow_residual_block (reference would drop features at random)"); return LL_ERR_CAP_BINDS; }
   if (M == 0) { ctx->set_error("no features"); return LL_ERR_NO_BLOCKS; }
   RegDevState* h = (RegDevState*)ctx->pinned;
@@ -299,7 +333,6 @@ static int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, i
   for (iter = 0; iter < in->icp_max_iterations; iter++) {
     cudaEvent_t* e = iter < 16 ? &ctx->evp[5 * iter] : nullptr;
     LL_CUDA(ctx, cudaMemsetAsync(&ctx->d_reg->corner_avail, 0, 2 * sizeof(int), s));
-    LL_CUDA(ctx, cudaMemsetAsync(&ctx->d_reg->knn_tiles, 0, 4 * sizeof(int), s));
     if (iter == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     if (e) LL_CUDA(ctx, cudaEventRecord(e[0], s));
     LL_TRY(launch_knn_blocks(ctx, ka));
@@ -336,7 +369,6 @@ static int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, i
   for (int k = 0; k < 3; k++) out->t_w_incre[k] = hs->x[4 + k];
   out->final_cost = hs->final_cost; out->initial_cost = hs->initial_cost; out->angular_diff = hs->angular_diff; out->t_diff = hs->t_diff;
   out->inlier_threshold = hs->inlier_threshold * hs->final_cost / hs->initial_cost;   // :559
-  if (getenv("LL_DEBUG_KNN")) fprintf(stderr, "[knn] last iteration: tile rounds %d overflow %d candidate buckets %d second rounds %d\n", hs->knn_tiles, hs->knn_overflow_tiles, hs->knn_candidates, hs->knn_frontier_max);
   const float minimize_cost = (float)hs->final_cost;
   if (hs->angular_diff > (double)(float)in->para_max_angular_rate || minimize_cost > (float)in->max_final_cost) {   // :561-573
     out->status = 0;

@@ -215,10 +215,21 @@ __global__ void __launch_bounds__(1024) l1_select_kernel(const double* __restric
       if ((key & himask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (tid == 0) {
-      int k = s_k; unsigned b = 0;
-      for (; b < 256; b++) { if (k < (int)hist[b]) break; k -= (int)hist[b]; }
-      s_k = k; s_prefix = prefix | ((unsigned long long)b << shift);
+    if (tid < 32) {   // warp 0: bin containing the k-th element = first bin whose inclusive prefix count exceeds k
+      const int k = s_k;
+      unsigned loc[8], run = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { run += hist[tid * 8 + j]; loc[j] = run; }
+      unsigned incl = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += v; }
+      const unsigned excl = incl - run;
+      const bool mine = (unsigned)k >= excl && (unsigned)k < incl;   // exactly one lane (k < n)
+      if (mine) {
+        int j = 0; while ((unsigned)k >= excl + loc[j]) j++;
+        s_k = k - (int)(excl + (j ? loc[j - 1] : 0u));
+        s_prefix = prefix | ((unsigned long long)(tid * 8 + j) << shift);
+      }
     }
     __syncthreads();
   }

@@ -37,10 +37,10 @@ struct DevBuf {  // grow-only device allocation
 };
 
 // ------------------------------------------------------------------------------------------------ map index
-// "Bucket tree": map points sorted along a 63-bit Hilbert curve (isotropic cells), cut into leaf buckets of 8 points
-// (128 B = one line), with a 4-ary tree of axis-aligned boxes above them (a node record = its 4 children's boxes, 96 B).
-// The top levels are bulk-copied (TMA) into shared memory by the search kernels.  Search is exact: a box gives a true
-// lower bound of the fp32 distance.  lo[l] holds level l's node records; hi[0] the base of the node array.
+// "Bucket tree": map points sorted along a 63-bit Hilbert curve (isotropic cells), cut into leaf buckets of 32 points
+// (512 B = one coalesced warp load), with a 32-ary tree of axis-aligned boxes above them (a node record = its 32 children's
+// boxes, 1 KB).  Search is exact: a box gives a true lower bound of the fp32 distance.  lo[l] holds level l's node records;
+// hi[0] the base of the node array (top level first).
 #define LL_MAX_LEVELS 14
 struct BucketTree {
   int n = 0;             // valid (finite) points
@@ -89,6 +89,7 @@ struct ll_ctx {
   std::string err;
   uint64_t launches = 0;
   int hook_slots = 0;      // slot count left behind by ll_build_blocks for the parity hooks
+  int last_nc = 0, last_ns = 0;   // features of the last registration (ll_last_features_dev)
   int num_sms = 0;
   // arenas
   DevBuf scratch;      // CUB temp storage

@@ -6,8 +6,7 @@ struct TreeView {
   const float4* pts;                    // [n_pad] Hilbert-ordered points, w = original index
   const float4* src;                    // [n_src] the cloud in its original order
   const float4* nodes[LL_MAX_LEVELS];   // node records per level (6 float4 each); level 0's children are the 8-point buckets
-  const float4* node_base;              // start of the node array (top level first): its prefix is staged into shared memory
-  int n, n_levels, staged_levels, staged_f4;
+  int n, n_levels;
   float bbox[6];                        // map bounding box (min xyz, max xyz)
 };
 TreeView make_view(const BucketTree& t);
@@ -24,8 +23,6 @@ struct KnnBlocksArgs {
   int* corner_avail; int* surf_avail;
   int* seed_ids;                // [M x 5] neighbour ids of the previous ICP iteration (-1 = none): seeds of the next search
   float* knn_d;                 // optional debug output [M x 5]
-  float* tile_r2;               // [M] per-feature search radius^2 hint carried from one ICP iteration to the next (may be null)
-  int* stats;                   // [4] tiles, overflow tiles, candidate buckets, max frontier (may be null)
   const int* perm;              // spatially sorted feature order (corners then surfaces), or null = caller order
   int rank, world; float inv_cell;
 };
@@ -59,7 +56,6 @@ struct RegDevState {
   double inlier_threshold, angular_diff, t_diff, final_cost, initial_cost;
   int corner_avail, surf_avail, icp_done, icp_iter, num_residual_blocks, status, total_lm_iterations, total_evaluations;
   int n_unique; int pad0;
-  int knn_tiles, knn_overflow_tiles, knn_candidates, knn_frontier_max;   // search statistics of the last kNN launch
   unsigned int bar_count, bar_gen;
   LmState lm;
 };

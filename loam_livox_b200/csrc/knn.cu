@@ -166,7 +166,7 @@ int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t
   // level sizes: level 0 nodes have buckets as children; the top level has exactly one node
   int cnt = ll_div_up(t->n_pad / BUCKET, FANOUT); t->n_levels = 0;
   for (;;) { t->level_count[t->n_levels++] = cnt; if (cnt <= 1) break; if (t->n_levels == LL_MAX_LEVELS) { ctx->set_error("map too large for LL_MAX_LEVELS"); return LL_ERR_CAPACITY; } cnt = ll_div_up(cnt, FANOUT); }
-  // node storage is laid out TOP level first, so that the top levels form one contiguous prefix (bulk-copied to shared memory)
+  // node storage is laid out top level first
   size_t node_total = 0; for (int l = 0; l < t->n_levels; l++) node_total += (size_t)t->level_count[l];
   size_t bytes = align256((size_t)t->n_pad * 16) + align256((size_t)n_src * 16) + align256(node_total * NODE_F4 * 16);
   LL_CUDA(ctx, t->storage.reserve(bytes));
@@ -187,25 +187,23 @@ int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t
 }
 
 TreeView make_view(const BucketTree& t) {
-  TreeView v; v.pts = t.pts; v.src = t.src; v.n = t.n; v.n_levels = t.n_levels; v.node_base = t.hi[0];
+  TreeView v; v.pts = t.pts; v.src = t.src; v.n = t.n; v.n_levels = t.n_levels;
   for (int l = 0; l < LL_MAX_LEVELS; l++) v.nodes[l] = t.lo[l];
-  v.staged_levels = 0; v.staged_f4 = 0;
   for (int k = 0; k < 6; k++) v.bbox[k] = t.bbox[k];
   return v;
 }
 
 // ------------------------------------------------------------------------------------------------ search
-// Eight lanes per query, four queries per warp.  A step of a query's best-first search pops one item from the group's stack
-// (shared memory) and handles it with all 8 lanes at once: a NODE -> lane c tests child c's box (two coalesced 16-B loads per lane,
-// 256 B per group) and the qualifying children are pushed far-to-near in one shot (rank by 7 shuffles); a BUCKET -> lane c takes
-// point c (one 16-B load, 128 B per group) and the candidates are merged into the group's top-5.  The top-5 and the stack pointer are
-// replicated in the 8 lanes.  Exact: a box gives a true lower bound of the fp32 distance and (d2, index) is a total order.
+// LL_GROUP lanes per query (32: one warp per query).  A step of a query's best-first search pops one item from the group's stack
+// (shared memory) and handles it with all lanes at once: a NODE -> lane c tests child c's box (two coalesced 16-B loads per lane,
+// 1 KB per group) and the qualifying children are pushed far-to-near in one shot (ballot + popc); a BUCKET -> lane c takes
+// point c (one 16-B load, 512 B per group) and the candidates are merged into the group's top-5.  The top-5 and the stack pointer are
+// replicated in the lanes.  Exact: a box gives a true lower bound of the fp32 distance and (d2, index) is a total order.
 #define GROUP LL_GROUP
 #define KNN_THREADS 256
 #define GROUPS_PER_CTA (KNN_THREADS / GROUP)
 #define STACK_CAP (LL_GROUP == 32 ? 160 : 64)
 #define ITEM_BUCKET 0x80000000u
-#define LL_KNN_THREAD_MIN 1000000000   // measured crossover; env LL_KNN_LANES overrides
 
 __device__ __forceinline__ bool lex_less(float d, int id, float d2, int id2) { return d < d2 || (d == d2 && id < id2); }
 
@@ -349,51 +347,6 @@ __device__ __forceinline__ void group_knn5(const TreeView& tv, GroupStack& st, b
   }
 }
 
-#if LL_GROUP == 8
-// ---- alternative mapping: ONE lane per query (32 queries per warp), used when there are enough queries to fill the machine.
-// Flat best-first loop: every iteration pops one item and issues ONE batch of independent 16-B loads whatever the item type
-// (16 for a node record, 8 for a bucket), so the warp's lanes stay aligned on memory round trips while their searches diverge.
-__device__ __forceinline__ void thread_knn5(const TreeView& tv, float qx, float qy, float qz, Top5& t) {
-#pragma unroll
-  for (int j = 0; j < LL_KNN; j++) { t.d[j] = INFINITY; t.id[j] = 0x7fffffff; }
-  if (tv.n <= 0) return;
-  unsigned stk_item[STACK_CAP]; float stk_lb[STACK_CAP]; int sp = 0;
-  stk_item[0] = (unsigned)(tv.n_levels - 1) << 26; stk_lb[0] = 0.f; sp = 1;
-  for (;;) {
-    unsigned item = 0; bool got = false;
-    while (sp > 0) { sp--; if (stk_lb[sp] <= t.d[4]) { item = stk_item[sp]; got = true; break; } }
-    if (!got) return;
-    const bool is_bucket = (item & ITEM_BUCKET) != 0;
-    const int lv = (int)((item >> 26) & 31u), idx = (int)(is_bucket ? (item & 0x7fffffffu) : (item & 0x03ffffffu));
-    const float4* addr = is_bucket ? tv.pts + (size_t)idx * BUCKET : tv.nodes[lv] + (size_t)idx * NODE_F4;
-    float4 r[16];
-#pragma unroll
-    for (int k = 0; k < 8; k++) r[k] = __ldg(addr + k);
-#pragma unroll
-    for (int k = 8; k < 16; k++) r[k] = is_bucket ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(addr + k);
-    if (is_bucket) {
-#pragma unroll
-      for (int k = 0; k < BUCKET; k++) {
-        const float d = dist2_exact(qx, qy, qz, r[k].x, r[k].y, r[k].z);
-        const int id = __float_as_int(r[k].w);
-        if (d < INFINITY && lex_less(d, id, t.d[4], t.id[4])) top5_insert(t, d, id);
-      }
-    } else {
-      float lb[8]; int best = -1; float bl = INFINITY;
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        lb[c] = box_lb(r[2 * c].x, r[2 * c].y, r[2 * c].z, r[2 * c + 1].x, r[2 * c + 1].y, r[2 * c + 1].z, qx, qy, qz);
-        if (lb[c] < bl) { bl = lb[c]; best = c; }
-      }
-      const unsigned tag = lv == 0 ? ITEM_BUCKET : ((unsigned)(lv - 1) << 26);
-#pragma unroll
-      for (int c = 0; c < 8; c++) if (c != best && lb[c] < INFINITY && lb[c] <= t.d[4]) { stk_item[sp] = tag | (unsigned)(idx * FANOUT + c); stk_lb[sp] = lb[c]; sp++; }
-      if (best >= 0 && bl <= t.d[4]) { stk_item[sp] = tag | (unsigned)(idx * FANOUT + best); stk_lb[sp] = bl; sp++; }   // nearest child on top
-    }
-  }
-}
-
-#endif
 // Parity hook (ll_knn): world-frame queries in caller order.
 __global__ void __launch_bounds__(KNN_THREADS) knn_query_kernel(TreeView tv, const float4* __restrict__ q, int nq, int* __restrict__ idx5, float* __restrict__ d5) {
   __shared__ GroupStack stacks[GROUPS_PER_CTA];
@@ -494,14 +447,13 @@ __device__ __forceinline__ void emit_block(const KnnBlocksArgs& a, const TreeVie
   a.blk_v[(size_t)w * 3 + 0] = vx; a.blk_v[(size_t)w * 3 + 1] = vy; a.blk_v[(size_t)w * 3 + 2] = vz;
 }
 
-// K6 + K7 fused, eight lanes per scan feature, features taken in spatially sorted order (perm).
+// K6 + K7 fused, one query group (LL_GROUP lanes) per scan feature, features taken in spatially sorted order (perm).
 // Writes one residual-block slot per feature (indexed by the ORIGINAL feature order): blk_a[slot] = (a.x, a.y, a.z, type) with
 // type 0 invalid / 1 line / 2 plane, blk_v[slot*3..] = unit line direction or (un-normalised) plane normal, in fp64.
-template <int LANES>
 __global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a) {
-  __shared__ GroupStack stacks[LANES == GROUP ? GROUPS_PER_CTA : 1];
-  const int j = LANES == GROUP ? blockIdx.x * GROUPS_PER_CTA + (threadIdx.x / GROUP) : blockIdx.x * KNN_THREADS + threadIdx.x;
-  const int gl = LANES == GROUP ? (threadIdx.x & (GROUP - 1)) : 0;
+  __shared__ GroupStack stacks[GROUPS_PER_CTA];
+  const int j = blockIdx.x * GROUPS_PER_CTA + (threadIdx.x / GROUP);
+  const int gl = threadIdx.x & (GROUP - 1);
   const int M = a.n_corner + a.n_surf;
   const bool have = j < M;
   const int w = have ? (a.perm ? a.perm[j] : j) : 0;      // original feature index
@@ -517,10 +469,8 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a
   if (a.world > 1) owned = cell_owner(qx, qy, qz, a.inv_cell, a.world) == (unsigned)a.rank;
   const bool active = have && owned && finite_in;
   Top5 t;
-  if (LANES == GROUP) group_knn5(tv, stacks[LANES == GROUP ? threadIdx.x / GROUP : 0], active, qx, qy, qz, t, (a.seed_ids && have) ? a.seed_ids + (size_t)w * LL_KNN : nullptr);
-#if LL_GROUP == 8
-  else { if (active) thread_knn5(tv, qx, qy, qz, t); else { for (int k = 0; k < LL_KNN; k++) { t.d[k] = INFINITY; t.id[k] = 0x7fffffff; } } }
-#endif
+  group_knn5(tv, stacks[threadIdx.x / GROUP], active, qx, qy, qz, t, (a.seed_ids && have) ? a.seed_ids + (size_t)w * LL_KNN : nullptr);
+
   if (!have || gl != 0) return;
   emit_block(a, tv, is_corner, active, w, t);
 }
@@ -548,11 +498,7 @@ int launch_query_sort(ll_ctx* ctx, const KnnBlocksArgs& a, int* d_perm) {
 int launch_knn_blocks(ll_ctx* ctx, const KnnBlocksArgs& a) {
   int M = a.n_corner + a.n_surf;
   if (M == 0) return LL_OK;
-  static int mode = -1;   // LL_KNN_LANES=1|8 forces a mapping; default: one lane per query once there are enough queries to fill the SMs
-  if (mode < 0) { const char* e = getenv("LL_KNN_LANES"); mode = e ? atoi(e) : 0; }
-  const bool per_thread = LL_GROUP == 8 && (mode == 1 || (mode == 0 && M >= LL_KNN_THREAD_MIN));
-  if (per_thread) knn_blocks_kernel<1><<<ll_div_up(M, KNN_THREADS), KNN_THREADS, 0, ctx->stream>>>(a);
-  else knn_blocks_kernel<GROUP><<<ll_div_up(M, GROUPS_PER_CTA), KNN_THREADS, 0, ctx->stream>>>(a);
+  knn_blocks_kernel<<<ll_div_up(M, GROUPS_PER_CTA), KNN_THREADS, 0, ctx->stream>>>(a);
   ctx->launches++;
   LL_CUDA(ctx, cudaGetLastError());
   return LL_OK;

@@ -419,14 +419,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
         }
       }
     }
-    // ---- CTA reduce: warp shuffles, then shared memory, fixed order
+    // ---- CTA reduce: warp shuffles, then shared memory, fixed order (warps that own no valid block contribute exact zeros)
+    if (__any_sync(FULL, acc[28] != 0.0)) {
 #pragma unroll
-    for (int i = 0; i < NSUM; i++) {
-      double v = acc[i];
+      for (int i = 0; i < NSUM; i++) {
+        double v = acc[i];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-      if (lane == 0) s_red[warp][i] = v;
-    }
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == 0) s_red[warp][i] = v;
+      }
+    } else if (lane < NSUM) s_red[warp][lane] = 0.0;
     __syncthreads();
     if (tid < NSUM) {
       double v = 0; for (int wq = 0; wq < SOLVE_THREADS / 32; wq++) v += s_red[wq][tid];
@@ -550,8 +552,8 @@ int solve_max_slots(ll_ctx* ctx) { return ctx->num_sms * ((SOLVE_MAX_SMEM / SLOT
 
 int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
   static bool attr_set[64] = {false};
-  const int grid = ctx->num_sms;
   const int tiles = ll_div_up(a.M > 0 ? a.M : 1, SOLVE_THREADS);
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;   // CTAs without blocks would only lengthen the barrier
   int tiles_per_cta = ll_div_up(tiles, grid);
   const size_t smem = (size_t)tiles_per_cta * SOLVE_THREADS * SLOT_BYTES;
   if (smem > SOLVE_MAX_SMEM) { ctx->set_error("too many residual-block slots for the shared-memory-resident solver"); return LL_ERR_CAPACITY; }

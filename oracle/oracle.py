@@ -129,6 +129,14 @@ def lib():
     L.orc_inlier_threshold.argtypes = [f64p, C.c_int, C.c_double]
     L.orc_inlier_threshold.restype = C.c_double
     L.orc_plus.argtypes = [f64p, f64p, C.c_double, f64p]
+    L.orc_cellmap_create.argtypes = [C.c_float, C.c_int]
+    L.orc_cellmap_create.restype = C.c_void_p
+    L.orc_cellmap_free.argtypes = [C.c_void_p]
+    L.orc_cellmap_append.argtypes = [C.c_void_p, f32p, C.c_int]
+    L.orc_cellmap_cells.argtypes = [C.c_void_p]
+    L.orc_cellmap_points.argtypes = [C.c_void_p]
+    L.orc_cellmap_frame_idx.argtypes = [C.c_void_p]
+    L.orc_cellmap_assemble.argtypes = [C.c_void_p, f64p, f64p, C.c_float, C.c_float, C.c_float, C.c_int, f32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _LIB = L
     return L
 
@@ -290,3 +298,35 @@ def plus(x, delta, bound=0.3):
     out = np.zeros(7)
     lib().orc_plus(np.asarray(x, np.float64), np.asarray(delta, np.float64), bound, out)
     return out
+
+
+class CellMap:
+    """Points_cloud_map<float> as the matching path uses it (append_cloud, cells-in-radius + FOV + per-cell VoxelGrid)."""
+
+    def __init__(self, resolution=1.0, revisit_threshold=2000):
+        self.h = lib().orc_cellmap_create(resolution, revisit_threshold)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_cellmap_free(self.h)
+            self.h = None
+
+    def append_cloud(self, pts):
+        pts = _c32(pts)
+        lib().orc_cellmap_append(self.h, pts, pts.shape[0])
+
+    def cells(self):
+        return lib().orc_cellmap_cells(self.h)
+
+    def points(self):
+        return lib().orc_cellmap_points(self.h)
+
+    def frame_idx(self):
+        return lib().orc_cellmap_frame_idx(self.h)
+
+    def assemble(self, q, t, search_range=100.0, fov_angle=45.0, leaf=0.4, replace=True):
+        cap = max(self.points(), 1)
+        out = np.empty((cap, 4), np.float32)
+        nt, nf = C.c_int(), C.c_int()
+        n = lib().orc_cellmap_assemble(self.h, np.asarray(q, np.float64), np.asarray(t, np.float64), search_range, fov_angle, leaf, int(replace), out, cap, C.byref(nt), C.byref(nf))
+        return out[:n].copy(), nf.value

@@ -6,6 +6,7 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include "orc_cellmap.hpp"
 #include "orc_cloud.hpp"
 #include "orc_extract.hpp"
 #include "orc_registration.hpp"
@@ -167,5 +168,21 @@ void orc_solve(const double* blocks, int M, const double q_last[4], const double
 }
 double orc_inlier_threshold(const double* residuals, int M, double ratio) { std::vector<double> r(residuals, residuals + (size_t)3 * M); return Registration::inlier_residual_threshold(r, ratio); }
 void orc_plus(const double x[7], const double delta[6], double bound, double out[7]) { Problem p; p.t_bound = bound; p.plus(x, delta, out); }
+
+// ---------------------------------------------------------------- cell map (matching_mode 1)
+void* orc_cellmap_create(float resolution, int revisit_threshold) { CellMap* m = new CellMap(); m->set_resolution(resolution); m->revisit_threshold = revisit_threshold; return m; }
+void orc_cellmap_free(void* m) { delete (CellMap*)m; }
+void orc_cellmap_append(void* m, const float* pts4, int n) { ((CellMap*)m)->append_cloud(pts4, n); }
+int orc_cellmap_cells(void* m) { return (int)((CellMap*)m)->cells.size(); }
+int orc_cellmap_points(void* m) { return ((CellMap*)m)->total_points(); }
+int orc_cellmap_frame_idx(void* m) { return ((CellMap*)m)->current_frame_idx; }
+// returns the number of points written (<= cap); *n_total = the number assemble produced
+int orc_cellmap_assemble(void* m, const double q[4], const double t[3], float search_range, float fov_angle, float leaf, int replace, float* out4, int cap, int* n_total, int* cells_in_fov) {
+  std::vector<float> out; Qd qq{q[0], q[1], q[2], q[3]}; V3d tt{t[0], t[1], t[2]};
+  int n = ((CellMap*)m)->assemble(qq, tt, search_range, fov_angle, leaf, replace != 0, out, cells_in_fov);
+  if (n_total) *n_total = n;
+  int w = n < cap ? n : cap; if (w > 0) std::memcpy(out4, out.data(), (size_t)w * 16);
+  return w;
+}
 
 }  // extern "C"
