@@ -202,6 +202,27 @@ int  ll_cellmap_assemble(ll_ctx* ctx, ll_cellmap* map, const double q_w_curr[4],
                          int down_sample_replace, ll_point* out_host, size_t cap, size_t* n_out, int* cells_in_fov, const ll_point** out_dev);
 int  ll_cellmap_stats(ll_ctx* ctx, ll_cellmap* map, int* cells, int* stored_points, int* frame_idx);
 
+/* ---- streaming odometry: Laser_mapping::process_new_scan + update_buff_for_matching (matching_mode 1) ------------------------------- */
+typedef struct {
+  float line_resolution, plane_resolution;      /* feature_extraction/mapping_{line,plane}_resolution (laser_mapping.hpp:661-662)          */
+  float cell_resolution;                        /* m_pt_cell_resolution (1.0 => 0.5 m cells)                                               */
+  int   threshold_cell_revisit;                 /* common/threshold_cell_revisit                                                           */
+  float maximum_search_range_corner, maximum_search_range_surface, maximum_in_fov_angle;   /* mapping/... (:691-695)                      */
+  int   down_sample_replace;                    /* m_down_sample_replace (:277)                                                            */
+  int   max_cells;                              /* hash-table sizing of each cell map (0 = 1 Mi cells)                                     */
+  ll_pipeline_cfg pipeline;                     /* feature-extraction glue (leaves, pieces)                                                */
+  ll_reg_state reg;                             /* registration parameters; the poses in it are the initial pose                           */
+} ll_mapper_config;
+typedef struct { int n_corner, n_surf, map_corner, map_surf, cells_in_fov_corner, cells_in_fov_surf, appended_corner, appended_surf; } ll_mapper_stats;
+typedef struct ll_mapper ll_mapper;
+void ll_mapper_config_default(ll_mapper_config* cfg);
+int  ll_mapper_create(ll_ctx* ctx, const ll_mapper_config* cfg, ll_mapper** out);
+void ll_mapper_release(ll_mapper* mapper);
+/* One raw scan through process_new_scan (laser_mapping.hpp:1316-1521): features, match-map refresh from the cell maps, registration
+ * (out->status 1 accepted/skipped, 0 rejected and discarded), world-frame features appended to the cell maps, pose adopted. */
+int  ll_mapper_process_scan(ll_mapper* mapper, const void* raw, size_t n, int fmt, int where, double stamp, ll_reg_result* out, ll_mapper_stats* stats);
+int  ll_mapper_pose(const ll_mapper* mapper, double q_wxyz[4], double t[3], int* frame_index);
+
 /* ---- device-to-device forms used when chaining stages without leaving the GPU (outputs in caller-provided device buffers) ------------- */
 int ll_voxel_downsample_dev(ll_ctx* ctx, const ll_point* in_dev, size_t n, float leaf, ll_point* out_dev, size_t* n_out);
 int ll_transform_dev(ll_ctx* ctx, const double q_wxyz[4], const double t[3], const ll_point* in_dev, size_t n, ll_point* out_dev);

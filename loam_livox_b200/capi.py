@@ -23,7 +23,8 @@ EXPORTS = [
     "ll_get_features", "ll_extract_point_info", "ll_extract_split_idx", "ll_voxel_downsample", "ll_map_build", "ll_map_release", "ll_map_size",
     "ll_map_build_sharded", "ll_knn", "ll_reg_state_default", "ll_register", "ll_build_blocks", "ll_normal_equations", "ll_solve", "ll_transform",
     "ll_scan_to_pose", "ll_comm_local_handle", "ll_comm_connect", "ll_launch_count", "ll_cellmap_create", "ll_cellmap_release", "ll_cellmap_append",
-    "ll_cellmap_assemble", "ll_cellmap_stats", "ll_voxel_downsample_dev", "ll_transform_dev", "ll_last_features_dev",
+    "ll_cellmap_assemble", "ll_cellmap_stats", "ll_voxel_downsample_dev", "ll_transform_dev", "ll_last_features_dev", "ll_mapper_config_default", "ll_mapper_create", "ll_mapper_release",
+    "ll_mapper_process_scan", "ll_mapper_pose",
 ]
 
 
@@ -54,6 +55,16 @@ class RegResult(C.Structure):
 class PipelineCfg(C.Structure):
     _fields_ = [("pieces", C.c_int), ("use_piece", C.c_int), ("extractor_leaf_corner", C.c_float), ("extractor_leaf_surf", C.c_float),
                 ("mapping_leaf_corner", C.c_float), ("mapping_leaf_surf", C.c_float), ("whole_frame", C.c_int)]
+
+
+class MapperConfig(C.Structure):
+    _fields_ = [("line_resolution", C.c_float), ("plane_resolution", C.c_float), ("cell_resolution", C.c_float), ("threshold_cell_revisit", C.c_int),
+                ("maximum_search_range_corner", C.c_float), ("maximum_search_range_surface", C.c_float), ("maximum_in_fov_angle", C.c_float),
+                ("down_sample_replace", C.c_int), ("max_cells", C.c_int), ("pipeline", PipelineCfg), ("reg", RegState)]
+
+
+class MapperStats(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n_corner", "n_surf", "map_corner", "map_surf", "cells_in_fov_corner", "cells_in_fov_surf", "appended_corner", "appended_surf")]
 
 
 class LoamLivoxError(RuntimeError):
@@ -110,6 +121,11 @@ def lib():
     L.ll_voxel_downsample_dev.argtypes = [vp, vp, sz, cf, vp, C.POINTER(sz)]
     L.ll_transform_dev.argtypes = [vp, vp, vp, vp, sz, vp]
     L.ll_last_features_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
+    L.ll_mapper_config_default.argtypes = [C.POINTER(MapperConfig)]
+    L.ll_mapper_create.argtypes = [vp, C.POINTER(MapperConfig), C.POINTER(vp)]
+    L.ll_mapper_release.argtypes = [vp]
+    L.ll_mapper_process_scan.argtypes = [vp, vp, sz, ci, ci, cd, C.POINTER(RegResult), C.POINTER(MapperStats)]
+    L.ll_mapper_pose.argtypes = [vp, vp, vp, C.POINTER(ci)]
     L.ll_launch_count.argtypes = [vp]
     L.ll_launch_count.restype = C.c_uint64
     _LIB = L

@@ -13,12 +13,7 @@ int launch_inlier_select(ll_ctx* ctx, const double* d_l1, int M, double ratio, d
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct RegArrays {
-  float4* feat; float4* blk_a; double* blk_v; double* l1; double* l1_sorted; double* l1_unique; double* partials;
-  int* n_unique; int* knn_idx; float* knn_d; int* perm; float4* tmp_a; float4* tmp_b; float4* tmp_c; int* counts; float* bounds; double* pose_tmp;
-  int cap;
-};
-static int reg_arrays(ll_ctx* ctx, int M, RegArrays* A) {
+int reg_arrays(ll_ctx* ctx, int M, RegArrays* A) {
   int cap = M > ctx->cfg.max_features ? M : ctx->cfg.max_features;
   int scap = ctx->cfg.max_scan_points > cap ? ctx->cfg.max_scan_points : cap;
   size_t bytes = align256((size_t)cap * 16) * 2 + align256((size_t)cap * 24) + align256((size_t)cap * 8 + 64) * 3 + align256((size_t)ctx->num_sms * 32 * 8) + 4096 +
@@ -306,8 +301,10 @@ static SolveArgs solve_args(ll_ctx* ctx, const RegArrays& A, int M, int mode, in
   return s;
 }
 
+}  // extern "C"
+
 // Registration on features already resident in A.feat (device). Core of ll_register / ll_scan_to_pose.
-static int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, int ns, const ll_reg_state* in, ll_reg_result* out) {
+int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, int ns, const ll_reg_state* in, ll_reg_result* out) {
   cudaStream_t s = ctx->stream;
   memset(out, 0, sizeof(*out));
   out->status = 1;
@@ -377,6 +374,8 @@ static int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, i
   }
   return LL_OK;
 }
+
+extern "C" {
 
 int ll_register(ll_ctx* ctx, const ll_map* map, const void* scan_corner, size_t nc, const void* scan_surf, size_t ns, int fmt, int where, const ll_reg_state* in, ll_reg_result* out) {
   if (!ctx || !map || !in || !out) return LL_ERR_INVALID;
@@ -450,36 +449,50 @@ int ll_solve(ll_ctx* ctx, int max_iterations, double x_io[7], double* initial_co
 }
 
 // ---------------------------------------------------------------------------------------------- whole per-scan step
-int ll_scan_to_pose(ll_ctx* ctx, const ll_map* map, const void* raw, size_t n, int fmt, int where, double stamp, const ll_pipeline_cfg* pc, const ll_reg_state* in,
-                    ll_reg_result* out, int* n_corner_used, int* n_surf_used) {
-  if (!ctx || !map || !pc || !in || !out) return LL_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+}  // extern "C"
+
+// Laser_feature::laserCloudHandler for one frame, on the device: extraction, piece bounds, get_features, the extractor's VoxelGrids
+// (laser_feature_extractor.hpp:285-380) and the mapping node's input VoxelGrids (laser_mapping.hpp:1367-1373).  Leaves the features in
+// A.feat (corners then surfaces).  *dropped = 1 when the frame has <= 5 petals (:287).
+int scan_front_end(ll_ctx* ctx, const void* raw, size_t n, int fmt, int where, double stamp, const ll_pipeline_cfg* pc, const RegArrays& A, int* nc_out, int* ns_out, int* dropped) {
   cudaStream_t s = ctx->stream;
   LL_TRY(ll_extract(ctx, raw, n, fmt, where, stamp, nullptr));
-  RegArrays A; LL_TRY(reg_arrays(ctx, 0, &A));
   const int ncap = (int)n;
-  // Laser_feature::laserCloudHandler: piece bounds -> get_features -> VoxelGrid (surface: plane_res/2, corner: line_res)   (laser_feature_extractor.hpp:313-380)
   const float* d_bounds = nullptr;
   if (!pc->whole_frame) { LL_TRY(launch_piece_bounds(ctx, pc->pieces, A.bounds)); d_bounds = A.bounds + 2 * pc->use_piece; }
   LL_TRY(launch_get_features(ctx, d_bounds, 0.f, 1.f, A.tmp_a, A.tmp_b, nullptr, A.counts));
-  // corners: tmp_a --vg(extractor leaf)--> tmp_c --vg(mapping leaf)--> feat[0..)
-  int* cnt = A.counts;   // [0] corners [1] surf [2] full [3..] temporaries
+  int* cnt = A.counts;   // [0] corners [1] surf [2] full [4..7] VoxelGrid outputs
   LL_TRY(launch_voxel_grid(ctx, A.tmp_a, ncap, cnt + 0, pc->extractor_leaf_corner, A.tmp_c, cnt + 4));
-  LL_TRY(launch_voxel_grid(ctx, A.tmp_c, ncap, cnt + 4, pc->mapping_leaf_corner, A.tmp_a, cnt + 5));     // Laser_mapping::process_new_scan :1367-1373
+  LL_TRY(launch_voxel_grid(ctx, A.tmp_c, ncap, cnt + 4, pc->mapping_leaf_corner, A.tmp_a, cnt + 5));
   LL_TRY(launch_voxel_grid(ctx, A.tmp_b, ncap, cnt + 1, pc->extractor_leaf_surf, A.tmp_c, cnt + 6));
   LL_TRY(launch_voxel_grid(ctx, A.tmp_c, ncap, cnt + 6, pc->mapping_leaf_surf, A.tmp_b, cnt + 7));
   int* h = (int*)ctx->pinned + 8192;
   LL_CUDA(ctx, cudaMemcpyAsync(h, cnt, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  LL_CUDA(ctx, cudaMemcpyAsync(h + 8, ctx->ex.d_meta, 12, cudaMemcpyDeviceToHost, s));
   LL_CUDA(ctx, cudaStreamSynchronize(s));
-  int meta_scans = 0; { int* hm = (int*)ctx->pinned + 8300; LL_CUDA(ctx, cudaMemcpyAsync(hm, ctx->ex.d_meta, 12, cudaMemcpyDeviceToHost, s)); LL_CUDA(ctx, cudaStreamSynchronize(s)); meta_scans = hm[1]; }
-  const int nc = h[5], ns = h[7];
-  if (n_corner_used) *n_corner_used = nc; if (n_surf_used) *n_surf_used = ns;
-  if (meta_scans <= 5 && !pc->whole_frame) { memset(out, 0, sizeof(*out)); out->status = 1; ctx->set_error("frame dropped: <= 5 petals"); return LL_OK; }   // laser_feature_extractor.hpp:287
-  if (nc + ns > ctx->cfg.max_features) return LL_ERR_CAPACITY;
+  const int nc = h[5], ns = h[7], meta_scans = h[9];
+  *nc_out = nc; *ns_out = ns;
+  *dropped = (meta_scans <= 5 && !pc->whole_frame) ? 1 : 0;
+  if (*dropped) return LL_OK;
+  if (nc + ns > ctx->cfg.max_features) { ctx->set_error("more features than max_features"); return LL_ERR_CAPACITY; }
   LL_CUDA(ctx, cudaMemcpyAsync(A.feat, A.tmp_a, (size_t)nc * 16, cudaMemcpyDeviceToDevice, s));
   LL_CUDA(ctx, cudaMemcpyAsync(A.feat + nc, A.tmp_b, (size_t)ns * 16, cudaMemcpyDeviceToDevice, s));
+  return LL_OK;
+}
+
+extern "C" int ll_scan_to_pose(ll_ctx* ctx, const ll_map* map, const void* raw, size_t n, int fmt, int where, double stamp, const ll_pipeline_cfg* pc, const ll_reg_state* in,
+                    ll_reg_result* out, int* n_corner_used, int* n_surf_used) {
+  if (!ctx || !map || !pc || !in || !out) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  RegArrays A; LL_TRY(reg_arrays(ctx, 0, &A));
+  int nc = 0, ns = 0, dropped = 0;
+  LL_TRY(scan_front_end(ctx, raw, n, fmt, where, stamp, pc, A, &nc, &ns, &dropped));
+  if (n_corner_used) *n_corner_used = nc; if (n_surf_used) *n_surf_used = ns;
+  if (dropped) { memset(out, 0, sizeof(*out)); out->status = 1; ctx->set_error("frame dropped: <= 5 petals"); return LL_OK; }
   return register_device(ctx, map, A, nc, ns, in, out);
 }
+
+extern "C" {
 
 // ---------------------------------------------------------------------------------------------- multi-GPU
 int ll_comm_local_handle(ll_ctx* ctx, unsigned char handle[LL_IPC_HANDLE_BYTES]) {

@@ -124,6 +124,12 @@ __global__ void cm_point_flags_kernel(const int* __restrict__ pt_slot, const int
   const bool alive = s >= 0 && pt_epoch[t] == epoch[s];
   f_sel[t] = (alive && sel[s]) ? 1 : 0; f_keep[t] = (alive && !sel[s]) ? 1 : 0;
 }
+__global__ void cm_count_alive_kernel(const int* __restrict__ pt_slot, const int* __restrict__ pt_epoch, int n, const int* __restrict__ epoch, int* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool alive = t < n && pt_slot[t] >= 0 && pt_epoch[t] == epoch[pt_slot[t]];
+  const unsigned b = __ballot_sync(0xffffffffu, alive);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, __popc(b));
+}
 // sort key of a selected point: (rank of its cell, voxel z, y, x) with voxel = floor(p / leaf) relative to a per-cell origin
 __global__ void cm_voxel_keys_kernel(const float4* __restrict__ pts, const int* __restrict__ pt_slot, const int* __restrict__ idx, const int* __restrict__ d_n, const unsigned long long* __restrict__ keys,
                                      const int* __restrict__ rank_of_slot, float box, float half, float inv, unsigned long long* __restrict__ out) {
@@ -205,10 +211,13 @@ void ll_cellmap_release(ll_cellmap* m) {
 int ll_cellmap_stats(ll_ctx* ctx, ll_cellmap* m, int* cells, int* stored_points, int* frame_idx) {
   if (!ctx || !m) return LL_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  int c = 0;
-  LL_CUDA(ctx, cudaMemcpyAsync(&c, m->d_counters, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  int c[2] = {0, 0};
+  LL_CUDA(ctx, cudaMemsetAsync(m->d_counters + 1, 0, 4, ctx->stream));
+  if (m->n_pts > 0) { cm_count_alive_kernel<<<ll_div_up(m->n_pts, 256), 256, 0, ctx->stream>>>(m->pt_slot, m->pt_epoch, m->n_pts, m->epoch, m->d_counters + 1); ctx->launches++; }
+  LL_CUDA(ctx, cudaMemcpyAsync(c, m->d_counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
   LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (cells) *cells = c; if (stored_points) *stored_points = m->n_pts; if (frame_idx) *frame_idx = m->current_frame_idx;
+  // points of replaced (revisited) cells are dead and not counted
+  if (cells) *cells = c[0]; if (stored_points) *stored_points = c[1]; if (frame_idx) *frame_idx = m->current_frame_idx;
   return LL_OK;
 }
 

@@ -93,3 +93,13 @@ int launch_extract(ll_ctx* ctx, int n, double current_time);
 int launch_get_features(ll_ctx* ctx, const float* d_bounds /*min_blur,max_blur on device*/, float min_blur, float max_blur,
                         float4* d_corners, float4* d_surf, float4* d_full, int* d_counts /*3*/);
 int launch_piece_bounds(ll_ctx* ctx, int pieces, float* d_start_end /* 2*pieces */);
+
+// ---------------------------------------------------------------------------------------------- host driver pieces (api.cu)
+struct RegArrays {
+  float4* feat; float4* blk_a; double* blk_v; double* l1; double* l1_sorted; double* l1_unique; double* partials;
+  int* n_unique; int* knn_idx; float* knn_d; int* perm; float4* tmp_a; float4* tmp_b; float4* tmp_c; int* counts; float* bounds; double* pose_tmp;
+  int cap;
+};
+int reg_arrays(ll_ctx* ctx, int M, RegArrays* A);
+int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, int ns, const ll_reg_state* in, ll_reg_result* out);
+int scan_front_end(ll_ctx* ctx, const void* raw, size_t n, int fmt, int where, double stamp, const ll_pipeline_cfg* pc, const RegArrays& A, int* nc_out, int* ns_out, int* dropped);

@@ -1,0 +1,139 @@
+// Streaming odometry driver: Laser_mapping::process_new_scan + update_buff_for_matching in matching_mode 1, with everything resident on
+// the device (the cell maps, the match-map snapshot and its index, the features).
+//
+// Restates, on the reference side (ROS I/O, threads, mutexes, history buffers of mode 0 and loop closure left out):
+//   Laser_mapping::process_new_scan                /root/reference/source/laser_mapping.hpp:1316-1521
+//   Laser_mapping::update_buff_for_matching        /root/reference/source/laser_mapping.hpp:460-566 (mode 1 branch :471-516, whole-map VoxelGrid :533-537,
+//                                                                                                  KdTreeFLANN build :544-545)
+//   Laser_mapping::init_pointcloud_registration    /root/reference/source/laser_mapping.hpp:1266-1297
+// The reference refreshes the match map on a background thread after every registered scan, with the pose of that scan; here the refresh
+// runs at the start of the next scan (same pose, same map content), so the result is the reference's with maximum_parallel_thread = 1.
+#include <cstring>
+#include "common.cuh"
+#include "kernels.cuh"
+
+extern "C" {
+int ll_cellmap_create(ll_ctx*, float, int, int, ll_cellmap**);
+void ll_cellmap_release(ll_cellmap*);
+int ll_cellmap_append(ll_ctx*, ll_cellmap*, const void*, size_t, int, int);
+int ll_cellmap_assemble(ll_ctx*, ll_cellmap*, const double*, const double*, float, float, float, int, ll_point*, size_t, size_t*, int*, const ll_point**);
+}
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct ll_mapper {
+  ll_ctx* ctx = nullptr;
+  ll_mapper_config cfg;
+  ll_cellmap* cells_corner = nullptr; ll_cellmap* cells_surf = nullptr;
+  ll_map* match_map = nullptr;
+  int frame_index = 0;
+  double q_w_curr[4] = {1, 0, 0, 0}, t_w_curr[3] = {0, 0, 0};
+  DevBuf work;   // transformed / down-sampled feature clouds
+  DevBuf snap;   // match-map snapshot clouds (corner, surf) between refreshes
+  int snap_n[2] = {0, 0}, fov[2] = {0, 0};
+  bool map_dirty = false;   // m_if_mapping_updated_{corner,surface}
+};
+
+extern "C" {
+
+void ll_mapper_config_default(ll_mapper_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->line_resolution = 0.1f; c->plane_resolution = 0.4f;             // performance_precision.yaml:12-13
+  c->cell_resolution = 1.0f; c->threshold_cell_revisit = 2000;      // laser_mapping.hpp:272, performance_precision.yaml
+  c->maximum_search_range_corner = 100.f; c->maximum_search_range_surface = 100.f; c->maximum_in_fov_angle = 45.f;   // :691-695
+  c->down_sample_replace = 1;                                        // :277
+  c->pipeline.pieces = 3; c->pipeline.use_piece = 0; c->pipeline.whole_frame = 1;
+  c->pipeline.extractor_leaf_corner = 0.1f; c->pipeline.extractor_leaf_surf = 0.2f; c->pipeline.mapping_leaf_corner = 0.1f; c->pipeline.mapping_leaf_surf = 0.4f;
+  ll_reg_state_default(&c->reg);
+  c->max_cells = 0;
+}
+
+int ll_mapper_create(ll_ctx* ctx, const ll_mapper_config* cfg, ll_mapper** out) {
+  if (!ctx || !cfg || !out) return LL_ERR_INVALID;
+  ll_mapper* m = new ll_mapper(); m->ctx = ctx; m->cfg = *cfg;
+  int st = ll_cellmap_create(ctx, cfg->cell_resolution, cfg->threshold_cell_revisit, cfg->max_cells, &m->cells_corner);
+  if (st == LL_OK) st = ll_cellmap_create(ctx, cfg->cell_resolution, cfg->threshold_cell_revisit, cfg->max_cells, &m->cells_surf);
+  if (st != LL_OK) { ll_cellmap_release(m->cells_corner); delete m; return st; }
+  for (int k = 0; k < 4; k++) m->q_w_curr[k] = cfg->reg.q_w_curr[k];
+  for (int k = 0; k < 3; k++) m->t_w_curr[k] = cfg->reg.t_w_curr[k];
+  ll_extract_reset(ctx);
+  *out = m; return LL_OK;
+}
+void ll_mapper_release(ll_mapper* m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  ll_cellmap_release(m->cells_corner); ll_cellmap_release(m->cells_surf);
+  if (m->match_map) ll_map_release(m->match_map);
+  m->work.release(); m->snap.release(); delete m;
+}
+int ll_mapper_pose(const ll_mapper* m, double q_wxyz[4], double t[3], int* frame_index) {
+  if (!m) return LL_ERR_INVALID;
+  for (int k = 0; k < 4; k++) q_wxyz[k] = m->q_w_curr[k]; for (int k = 0; k < 3; k++) t[k] = m->t_w_curr[k];
+  if (frame_index) *frame_index = m->frame_index;
+  return LL_OK;
+}
+
+// One scan: features -> (refresh match map from the cell maps) -> registration -> world-frame features -> VoxelGrid -> cell maps.
+int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int where, double stamp, ll_reg_result* out, ll_mapper_stats* stats) {
+  if (!m || !out) return LL_ERR_INVALID;
+  ll_ctx* ctx = m->ctx; cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  RegArrays A; LL_TRY(reg_arrays(ctx, 0, &A));
+  int nc = 0, ns = 0, dropped = 0;
+  LL_TRY(scan_front_end(ctx, raw, n, fmt, where, stamp, &m->cfg.pipeline, A, &nc, &ns, &dropped));
+  memset(out, 0, sizeof(*out)); out->status = 1;
+  for (int k = 0; k < 4; k++) out->q_w_curr[k] = m->q_w_curr[k]; for (int k = 0; k < 3; k++) out->t_w_curr[k] = m->t_w_curr[k];
+  if (stats) { stats->n_corner = nc; stats->n_surf = ns; }
+  if (dropped) return LL_OK;                                                     // laser_feature_extractor.hpp:287
+  m->frame_index++;                                                              // m_current_frame_index++ (:1350)
+  // ---- update_buff_for_matching (mode 1): snapshot of the cells in range and in the FOV, whole-map VoxelGrid, index
+  if (m->map_dirty) {
+    size_t mc = 0, ms = 0; const ll_point* d_mc = nullptr; const ll_point* d_ms = nullptr; int fov_c = 0, fov_s = 0;
+    LL_TRY(ll_cellmap_assemble(ctx, m->cells_corner, m->q_w_curr, m->t_w_curr, m->cfg.maximum_search_range_corner, m->cfg.maximum_in_fov_angle, m->cfg.line_resolution,
+                               m->cfg.down_sample_replace, nullptr, 0, &mc, &fov_c, &d_mc));
+    LL_TRY(ll_cellmap_assemble(ctx, m->cells_surf, m->q_w_curr, m->t_w_curr, m->cfg.maximum_search_range_surface, m->cfg.maximum_in_fov_angle, m->cfg.plane_resolution,
+                               m->cfg.down_sample_replace, nullptr, 0, &ms, &fov_s, &d_ms));
+    LL_CUDA(ctx, m->snap.reserve(align256((mc + 1) * 16) + align256((ms + 1) * 16) + 256));
+    float4* s0 = m->snap.as<float4>(); float4* s1 = (float4*)((char*)s0 + align256((mc + 1) * 16)); int* d_sc = (int*)((char*)s1 + align256((ms + 1) * 16));
+    int hc[2] = {0, 0};
+    if (mc > 0) LL_TRY(launch_voxel_grid(ctx, (const float4*)d_mc, (int)mc, nullptr, m->cfg.line_resolution, s0, d_sc)); else LL_CUDA(ctx, cudaMemsetAsync(d_sc, 0, 4, s));      // :533-534
+    if (ms > 0) LL_TRY(launch_voxel_grid(ctx, (const float4*)d_ms, (int)ms, nullptr, m->cfg.plane_resolution, s1, d_sc + 1)); else LL_CUDA(ctx, cudaMemsetAsync(d_sc + 1, 0, 4, s));   // :536-537
+    LL_CUDA(ctx, cudaMemcpyAsync(hc, d_sc, 8, cudaMemcpyDeviceToHost, s));
+    LL_CUDA(ctx, cudaStreamSynchronize(s));
+    if (m->match_map) { ll_map_release(m->match_map); m->match_map = nullptr; }
+    if (hc[0] > 0 && hc[1] > 0) LL_TRY(ll_map_build(ctx, s0, (size_t)hc[0], s1, (size_t)hc[1], LL_FMT_XYZI16, LL_DEVICE, &m->match_map));                      // :544-545
+    m->snap_n[0] = hc[0]; m->snap_n[1] = hc[1]; m->fov[0] = fov_c; m->fov[1] = fov_s;
+    m->map_dirty = false;
+  }
+  if (stats) { stats->map_corner = m->snap_n[0]; stats->map_surf = m->snap_n[1]; stats->cells_in_fov_corner = m->fov[0]; stats->cells_in_fov_surf = m->fov[1]; }
+  const size_t cap = (size_t)(nc > ns ? nc : ns) + 16;
+  LL_CUDA(ctx, m->work.reserve(4 * align256(cap * 16) + 1024));
+  float4* w0 = m->work.as<float4>(); float4* w1 = (float4*)((char*)w0 + align256(cap * 16)); float4* w2 = (float4*)((char*)w1 + align256(cap * 16)); float4* w3 = (float4*)((char*)w2 + align256(cap * 16));
+  int* d_cnt = (int*)((char*)w3 + align256(cap * 16));
+  int hc[2] = {0, 0};
+  // ---- init_pointcloud_registration + find_out_incremental_transfrom (:1266-1297, :1405)
+  ll_reg_state st = m->cfg.reg;
+  st.current_frame_index = m->frame_index;
+  for (int k = 0; k < 4; k++) { st.q_w_last[k] = m->q_w_curr[k]; st.q_w_curr[k] = m->q_w_curr[k]; }
+  for (int k = 0; k < 3; k++) { st.t_w_last[k] = m->t_w_curr[k]; st.t_w_curr[k] = m->t_w_curr[k]; }
+  st.para_buffer_incremental[0] = st.para_buffer_incremental[1] = st.para_buffer_incremental[2] = 0; st.para_buffer_incremental[3] = 1;
+  st.para_buffer_incremental[4] = st.para_buffer_incremental[5] = st.para_buffer_incremental[6] = 0;
+  if (m->match_map) LL_TRY(register_device(ctx, m->match_map, A, nc, ns, &st, out));   // no map yet: the gate of :199 returns 1
+  if (out->status == 0) return LL_OK;                                           // rejected: frame discarded (:1413-1416)
+  // ---- new features to the world frame (:1422-1432), VoxelGrid (:1434-1437), cell maps (:1492-1493)
+  double* h = (double*)((char*)ctx->pinned + 40960); for (int k = 0; k < 4; k++) h[k] = out->q_w_curr[k]; for (int k = 0; k < 3; k++) h[4 + k] = out->t_w_curr[k];
+  double* d_pose = (double*)(d_cnt + 16);
+  LL_CUDA(ctx, cudaMemcpyAsync(d_pose, h, 7 * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (nc > 0) { LL_TRY(launch_transform(ctx, d_pose, A.feat, nc, w2)); LL_TRY(launch_voxel_grid(ctx, w2, nc, nullptr, m->cfg.line_resolution, w0, d_cnt)); } else LL_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 4, s));
+  if (ns > 0) { LL_TRY(launch_transform(ctx, d_pose, A.feat + nc, ns, w3)); LL_TRY(launch_voxel_grid(ctx, w3, ns, nullptr, m->cfg.plane_resolution, w1, d_cnt + 1)); } else LL_CUDA(ctx, cudaMemsetAsync(d_cnt + 1, 0, 4, s));
+  LL_CUDA(ctx, cudaMemcpyAsync(hc, d_cnt, 8, cudaMemcpyDeviceToHost, s));
+  LL_CUDA(ctx, cudaStreamSynchronize(s));
+  LL_TRY(ll_cellmap_append(ctx, m->cells_corner, w0, (size_t)hc[0], LL_FMT_XYZI16, LL_DEVICE));
+  LL_TRY(ll_cellmap_append(ctx, m->cells_surf, w1, (size_t)hc[1], LL_FMT_XYZI16, LL_DEVICE));
+  m->map_dirty = true;                                                           // m_if_mapping_updated_* (:1490-1491)
+  if (stats) { stats->appended_corner = hc[0]; stats->appended_surf = hc[1]; }
+  for (int k = 0; k < 4; k++) m->q_w_curr[k] = out->q_w_curr[k]; for (int k = 0; k < 3; k++) m->t_w_curr[k] = out->t_w_curr[k];   // :1496-1505
+  return LL_OK;
+}
+
+}  // extern "C"

@@ -230,3 +230,98 @@ def scan_to_pose(ctx: Context, match_map: Map, raw, stamp, pipeline: capi.Pipeli
     nc, ns = C.c_int(), C.c_int()
     ctx.check(ctx._lib.ll_scan_to_pose(ctx.h, match_map.h, ptr, n, fmt, where, float(stamp), C.byref(pipeline), C.byref(state), C.byref(res), C.byref(nc), C.byref(ns)))
     return res, nc.value, ns.value
+
+
+class Points_cloud_map:
+    """Device-resident voxel-cell map as the matching path uses it (Points_cloud_map<float>, /root/reference/source/cell_map_keyframe.hpp:264;
+    append_cloud :619, find_cells_in_radius :761; the consumer is update_buff_for_matching, /root/reference/source/laser_mapping.hpp:471-516)."""
+
+    def __init__(self, ctx: Context, resolution: float = 1.0, revisit_threshold: int = 2000, max_cells: int = 0):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(ctx._lib.ll_cellmap_create(ctx.h, float(resolution), int(revisit_threshold), int(max_cells), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx._lib.ll_cellmap_release(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def append_cloud(self, pts):
+        pts, fmt = _pts(pts)
+        self.ctx.check(self.ctx._lib.ll_cellmap_append(self.ctx.h, self.h, pts.ctypes.data, pts.shape[0], fmt, capi.LL_HOST))
+
+    def stats(self):
+        c, p, f = C.c_int(), C.c_int(), C.c_int()
+        self.ctx.check(self.ctx._lib.ll_cellmap_stats(self.ctx.h, self.h, C.byref(c), C.byref(p), C.byref(f)))
+        return c.value, p.value, f.value
+
+    def get_cells_size(self) -> int:
+        return self.stats()[0]
+
+    def assemble(self, q_w_curr, t_w_curr, search_range=100.0, fov_angle=45.0, leaf=0.4, replace=True):
+        """cells in radius + if_pt_in_fov + per-cell VoxelGrid (+ replace) -> (n x 4 float32 cloud, cells in the FOV)."""
+        q = np.ascontiguousarray(q_w_curr, np.float64)
+        t = np.ascontiguousarray(t_w_curr, np.float64)
+        cap = max(self.stats()[1], 1)
+        out = np.empty((cap, 4), np.float32)
+        n, nf, dev = C.c_size_t(), C.c_int(), C.c_void_p()
+        self.ctx.check(self.ctx._lib.ll_cellmap_assemble(self.ctx.h, self.h, q.ctypes.data, t.ctypes.data, float(search_range), float(fov_angle), float(leaf), int(bool(replace)),
+                                                         out.ctypes.data, cap, C.byref(n), C.byref(nf), C.byref(dev)))
+        return out[:n.value].copy(), nf.value
+
+
+class Laser_mapping:
+    """Streaming odometry: one call per raw scan (Laser_mapping::process_new_scan, /root/reference/source/laser_mapping.hpp:1316-1521, with the
+    match-map refresh of update_buff_for_matching :460-566 in matching_mode 1).  All state stays on the device."""
+
+    def __init__(self, ctx: Context, **kw):
+        self.ctx = ctx
+        cfg = capi.MapperConfig()
+        ctx._lib.ll_mapper_config_default(C.byref(cfg))
+        reg = kw.pop("reg", None)
+        pipeline = kw.pop("pipeline", None)
+        if reg is not None:
+            cfg.reg = reg
+        if pipeline is not None:
+            cfg.pipeline = pipeline
+        for k, v in kw.items():
+            if not hasattr(cfg, k):
+                raise AttributeError(k)
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        h = C.c_void_p()
+        ctx.check(ctx._lib.ll_mapper_create(ctx.h, C.byref(cfg), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx._lib.ll_mapper_release(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process_new_scan(self, raw, stamp, where=capi.LL_HOST, n=None, fmt=None):
+        if where == capi.LL_HOST:
+            pts, fmt = _pts(raw)
+            ptr, n = pts.ctypes.data, pts.shape[0]
+        else:
+            ptr = int(raw)
+        res, stats = capi.RegResult(), capi.MapperStats()
+        self.ctx.check(self.ctx._lib.ll_mapper_process_scan(self.h, ptr, n, fmt, where, float(stamp), C.byref(res), C.byref(stats)))
+        return res, stats
+
+    def pose(self):
+        q, t, f = np.empty(4), np.empty(3), C.c_int()
+        self.ctx.check(self.ctx._lib.ll_mapper_pose(self.h, q.ctypes.data, t.ctypes.data, C.byref(f)))
+        return q, t, f.value

@@ -330,3 +330,64 @@ class CellMap:
         nt, nf = C.c_int(), C.c_int()
         n = lib().orc_cellmap_assemble(self.h, np.asarray(q, np.float64), np.asarray(t, np.float64), search_range, fov_angle, leaf, int(replace), out, cap, C.byref(nt), C.byref(nf))
         return out[:n].copy(), nf.value
+
+
+class Mapper:
+    """Laser_mapping::process_new_scan + update_buff_for_matching (matching_mode 1) glued from the oracle pieces above, single-threaded
+    (/root/reference/source/laser_mapping.hpp:1316-1521, :460-566, :1266-1297).  The background refresh of the match map is run at the start
+    of the next scan with the pose the previous scan ended with, which is what the reference does with maximum_parallel_thread = 1."""
+
+    def __init__(self, params=None, line_resolution=0.1, plane_resolution=0.4, cell_resolution=1.0, revisit_threshold=2000, search_range=100.0,
+                 fov_angle=45.0, replace=True, extractor_leaf_corner=0.1, extractor_leaf_surf=0.2, threads=1):
+        self.params = params if params is not None else default_params()
+        self.line_resolution, self.plane_resolution = line_resolution, plane_resolution
+        self.search_range, self.fov_angle, self.replace = search_range, fov_angle, replace
+        self.leaf_c, self.leaf_s = extractor_leaf_corner, extractor_leaf_surf
+        self.cells_corner, self.cells_surf = CellMap(cell_resolution, revisit_threshold), CellMap(cell_resolution, revisit_threshold)
+        self.ex = Extractor()
+        self.q = np.array(list(self.params.q_w_curr), np.float64)
+        self.t = np.array(list(self.params.t_w_curr), np.float64)
+        self.frame_index = 0
+        self.dirty = False
+        self.map_c = self.map_s = None
+        self.tree_c = self.tree_s = None
+        self.threads = threads
+        self.last = {}
+
+    def process_scan(self, raw, stamp):
+        self.ex.extract(raw, stamp)
+        c, s, _ = self.ex.get_features(0.0, 1.0)
+        c = voxel_grid(voxel_grid(c, self.leaf_c), self.line_resolution)       # laser_feature_extractor.hpp:379-380 then laser_mapping.hpp:1367-1370
+        s = voxel_grid(voxel_grid(s, self.leaf_s), self.plane_resolution)      # :372-373 then :1371-1373
+        self.frame_index += 1
+        if self.dirty:
+            mc, fc = self.cells_corner.assemble(self.q, self.t, self.search_range, self.fov_angle, self.line_resolution, self.replace)
+            ms, fs = self.cells_surf.assemble(self.q, self.t, self.search_range, self.fov_angle, self.plane_resolution, self.replace)
+            self.map_c, self.map_s = voxel_grid(mc, self.line_resolution), voxel_grid(ms, self.plane_resolution)
+            self.tree_c = KdTree(self.map_c) if self.map_c.shape[0] else None
+            self.tree_s = KdTree(self.map_s) if self.map_s.shape[0] else None
+            self.dirty = False
+            self.last.update(cells_in_fov_corner=fc, cells_in_fov_surf=fs)
+        status, res = 1, None
+        if self.tree_c is not None and self.tree_s is not None:
+            p = RegParams.from_buffer_copy(self.params)
+            p.current_frame_index = self.frame_index
+            p.num_threads = self.threads
+            p.q_w_last[:] = list(self.q); p.q_w_curr[:] = list(self.q)
+            p.t_w_last[:] = list(self.t); p.t_w_curr[:] = list(self.t)
+            p.para_buffer_incremental[:] = [0, 0, 0, 1, 0, 0, 0]
+            status, res = register(self.map_c, self.tree_c, self.map_s, self.tree_s, c, s, p)
+        self.last.update(n_corner=c.shape[0], n_surf=s.shape[0], map_corner=0 if self.map_c is None else self.map_c.shape[0],
+                         map_surf=0 if self.map_s is None else self.map_s.shape[0], status=status, res=res)
+        if status == 0:
+            return status, self.q.copy(), self.t.copy()
+        q = np.array(list(res.q_w_curr)) if res is not None else self.q
+        t = np.array(list(res.t_w_curr)) if res is not None else self.t
+        wc = voxel_grid(transform(c, q, t), self.line_resolution) if c.shape[0] else c
+        ws = voxel_grid(transform(s, q, t), self.plane_resolution) if s.shape[0] else s
+        self.cells_corner.append_cloud(wc)
+        self.cells_surf.append_cloud(ws)
+        self.last.update(appended_corner=wc.shape[0], appended_surf=ws.shape[0])
+        self.dirty = True
+        self.q, self.t = q.copy(), t.copy()
+        return status, self.q.copy(), self.t.copy()

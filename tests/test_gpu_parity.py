@@ -283,3 +283,75 @@ def test_register_edge_cases(ctx, oracle):
     reg4.set_pose(pose.q, pose.t)
     with pytest.raises(LoamLivoxError):
         reg4.find_out_incremental_transfrom(m, fc, fs)
+
+
+# ---------------------------------------------------------------------------------------------- a14: device cell map, streaming mapper (C3)
+@pytest.mark.gpu
+def test_cellmap_append_assemble_parity(ctx, oracle):
+    from loam_livox_b200.registration import Points_cloud_map
+    rng = np.random.default_rng(2)
+    p = np.zeros((60000, 4), np.float32)
+    p[:, :3] = rng.normal(0, 4, (60000, 3)).astype(np.float32)
+    p[:, 3] = rng.uniform(0, 1, 60000).astype(np.float32)                  # intensity must be dropped by the cell map
+    g, o = Points_cloud_map(ctx, 1.0, 2000), oracle.CellMap(1.0, 2000)
+    for lo, hi in ((0, 25000), (25000, 25001), (25001, 60000)):
+        g.append_cloud(p[lo:hi]); o.append_cloud(p[lo:hi])
+        assert g.stats() == (o.cells(), o.points(), o.frame_idx())
+    q, t = S.quat_from_euler(0.02, -0.01, 0.4), np.array([0.5, -0.2, 0.1])
+    for replace in (False, True, True):
+        a, fa = g.assemble(q, t, 7.0, 45.0, 0.2, replace)
+        b, fb = o.assemble(q, t, 7.0, 45.0, 0.2, replace)
+        assert fa == fb and a.shape == b.shape and np.array_equal(a, b)
+        assert g.stats() == (o.cells(), o.points(), o.frame_idx())
+    # append after a replace, other pose, other leaf
+    extra = np.zeros((5000, 4), np.float32); extra[:, :3] = rng.normal(1, 3, (5000, 3)).astype(np.float32)
+    g.append_cloud(extra); o.append_cloud(extra)
+    q2, t2 = S.quat_from_euler(0.0, 0.1, -2.0), np.array([-1.0, 0.3, 0.0])
+    a, fa = g.assemble(q2, t2, 100.0, 45.0, 0.4, True)
+    b, fb = o.assemble(q2, t2, 100.0, 45.0, 0.4, True)
+    assert fa == fb and np.array_equal(a, b) and g.stats() == (o.cells(), o.points(), o.frame_idx())
+    # nothing in range
+    a, fa = g.assemble(q2, np.array([500.0, 0, 0]), 5.0, 45.0, 0.4, True)
+    assert a.shape[0] == 0 and fa == 0
+
+
+@pytest.mark.gpu
+def test_cellmap_revisit_parity(ctx, oracle):
+    from loam_livox_b200.registration import Points_cloud_map
+    rng = np.random.default_rng(3)
+    g, o = Points_cloud_map(ctx, 1.0, 3), oracle.CellMap(1.0, 3)
+    near = np.zeros((2000, 4), np.float32); near[:, :3] = rng.uniform(0, 3, (2000, 3)).astype(np.float32)
+    far = np.zeros((2000, 4), np.float32); far[:, :3] = rng.uniform(10, 13, (2000, 3)).astype(np.float32)
+    seq = [near[:1000], far[:700], far[700:1400], far[1400:], near[1000:1500], near[1500:], far[:10]]
+    for c in seq:
+        g.append_cloud(c); o.append_cloud(c)
+        assert g.stats() == (o.cells(), o.points(), o.frame_idx())
+    q, t = np.array([1.0, 0, 0, 0]), np.array([-5.0, 1.5, 1.5])
+    a, fa = g.assemble(q, t, 100.0, 45.0, 0.1, False)
+    b, fb = o.assemble(q, t, 100.0, 45.0, 0.1, False)
+    assert fa == fb and np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_streaming_mapper_parity(ctx, oracle):
+    """Config C3 in small: the device mapper against the oracle's process_new_scan loop, scan by scan (pose within 1e-4 m / 1e-4 rad)."""
+    from loam_livox_b200 import capi
+    from loam_livox_b200.registration import Laser_mapping
+    poses = S.trajectory(n_scans=9, n_static=3, speed=1.0)
+    reg = capi.default_reg_state(mapping_init_accumulate_frames=3)
+    gm = Laser_mapping(ctx, reg=reg)
+    om = oracle.Mapper(oracle.default_params(mapping_init_accumulate_frames=3, num_threads=4), threads=4)
+    for k, pose in enumerate(poses):
+        raw = S.make_scan(24000, pose, seed=S.SEED + k)
+        res, stats = gm.process_new_scan(raw, 100.0 + 0.1 * k)
+        ost, oq, ot = om.process_scan(raw, 100.0 + 0.1 * k)
+        assert res.status == ost
+        assert (stats.n_corner, stats.n_surf) == (om.last["n_corner"], om.last["n_surf"])
+        assert (stats.map_corner, stats.map_surf) == (om.last["map_corner"], om.last["map_surf"]), k
+        assert (stats.appended_corner, stats.appended_surf) == (om.last["appended_corner"], om.last["appended_surf"]), k
+        q, t, f = gm.pose()
+        assert f == om.frame_index
+        assert np.linalg.norm(t - ot) < 1e-4 and S.quat_angle(q, oq) < 1e-4, (k, t, ot)
+        if om.last["res"] is not None and om.last["res"].registered:
+            assert res.registered == 1 and res.icp_iterations == om.last["res"].icp_iterations
+    assert gm.pose()[2] == 9
