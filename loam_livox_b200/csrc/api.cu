@@ -291,12 +291,13 @@ static KnnBlocksArgs knn_args(ll_ctx* ctx, const ll_map* map, const RegArrays& A
   a.icp_line = in->icp_line; a.icp_plane = in->icp_plane; a.blk_a = A.blk_a; a.blk_v = A.blk_v;
   a.corner_avail = &ctx->d_reg->corner_avail; a.surf_avail = &ctx->d_reg->surf_avail;
   a.seed_ids = A.knn_idx; a.knn_d = debug ? A.knn_d : nullptr; a.perm = A.perm;
+  ctx->solve_world = (map->world > 1 && ctx->world > 1) ? ctx->world : 1;   // replicas of the whole map never exchange anything
   a.rank = map->rank; a.world = map->world; a.inv_cell = map->cell_size > 0.f ? 1.0f / map->cell_size : 1.0f;
   return a;
 }
 static SolveArgs solve_args(ll_ctx* ctx, const RegArrays& A, int M, int mode, int max_iter) {
   SolveArgs s; s.st = ctx->d_reg; s.feat = A.feat; s.blk_a = A.blk_a; s.blk_v = A.blk_v; s.l1 = A.l1; s.l1_sorted_unique = A.l1_unique; s.d_n_unique = A.n_unique;
-  s.partials = A.partials; s.M = M; s.max_iterations = max_iter; s.mode = mode; s.rank = ctx->rank; s.world = ctx->world; s.comm_local = (double*)ctx->comm_local;
+  s.partials = A.partials; s.M = M; s.max_iterations = max_iter; s.mode = mode; s.rank = ctx->rank; s.world = ctx->solve_world; s.comm_local = (double*)ctx->comm_local;
   for (int i = 0; i < 8; i++) s.comm_peer[i] = (double*)ctx->comm_peers[i];
   return s;
 }
@@ -327,9 +328,14 @@ int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, 
   LL_TRY(launch_query_sort(ctx, ka, A.perm));   // spatial tiles of features (Hilbert order at the initial pose)
   LL_CUDA(ctx, cudaEventRecord(ctx->evp[81], s));
   int iter = 0; RegDevState* hs = (RegDevState*)((char*)ctx->pinned + align256(sizeof(RegDevState)));
+  const bool sharded = ctx->world > 1 && map->world > 1;
+  if (sharded && (map->world != ctx->world || map->rank != ctx->rank)) { ctx->set_error("map shard and context disagree on rank/world"); return LL_ERR_INVALID; }
+  if (sharded && M > ctx->cfg.max_features) { ctx->set_error("more features than max_features (exchange buffer)"); return LL_ERR_CAPACITY; }
+  double* x_l1 = sharded ? (double*)((char*)ctx->comm_local + LL_COMM_X_OFF) : nullptr;
   for (iter = 0; iter < in->icp_max_iterations; iter++) {
     cudaEvent_t* e = iter < 16 ? &ctx->evp[5 * iter] : nullptr;
     LL_CUDA(ctx, cudaMemsetAsync(&ctx->d_reg->corner_avail, 0, 2 * sizeof(int), s));
+    if (sharded) LL_CUDA(ctx, cudaMemsetAsync(x_l1, 0xff, (size_t)M * sizeof(double), s));   // NaN = nobody owns a block here (peers fill it after solve #1)
     if (iter == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     if (e) LL_CUDA(ctx, cudaEventRecord(e[0], s));
     LL_TRY(launch_knn_blocks(ctx, ka));
@@ -337,7 +343,8 @@ int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, 
     if (iter == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev2, s));
     LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 0, in->cere_prerun_times)));
     if (e) LL_CUDA(ctx, cudaEventRecord(e[2], s));
-    LL_TRY(launch_inlier_select(ctx, A.l1, M, in->inlier_ratio, A.l1_sorted, A.l1_unique, A.n_unique));
+    if (sharded) LL_TRY(launch_l1_exchange(ctx, A.l1, M));
+    LL_TRY(launch_inlier_select(ctx, sharded ? x_l1 : A.l1, M, in->inlier_ratio, A.l1_sorted, A.l1_unique, A.n_unique));
     if (e) LL_CUDA(ctx, cudaEventRecord(e[3], s));
     LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 1, in->cere_max_iterations)));
     if (e) LL_CUDA(ctx, cudaEventRecord(e[4], s));
@@ -498,7 +505,8 @@ extern "C" {
 int ll_comm_local_handle(ll_ctx* ctx, unsigned char handle[LL_IPC_HANDLE_BYTES]) {
   if (!ctx) return LL_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  if (!ctx->comm_local) { LL_CUDA(ctx, cudaMalloc(&ctx->comm_local, 2 * 8 * 64 * sizeof(double))); LL_CUDA(ctx, cudaMemset(ctx->comm_local, 0, 2 * 8 * 64 * sizeof(double))); }
+  const size_t comm_bytes = LL_COMM_X_OFF + (size_t)ctx->cfg.max_features * sizeof(double);
+  if (!ctx->comm_local) { LL_CUDA(ctx, cudaMalloc(&ctx->comm_local, comm_bytes)); LL_CUDA(ctx, cudaMemset(ctx->comm_local, 0, comm_bytes)); }
   cudaIpcMemHandle_t h; LL_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->comm_local));
   static_assert(sizeof(cudaIpcMemHandle_t) <= LL_IPC_HANDLE_BYTES, "ipc handle size");
   memset(handle, 0, LL_IPC_HANDLE_BYTES); memcpy(handle, &h, sizeof(h));

@@ -76,7 +76,17 @@ struct SolveArgs {
   // multi-GPU
   int rank, world; double* comm_local; double* comm_peer[8];
 };
+// Layout of the IPC-exported staging buffer of a rank (ll_comm_local_handle):
+//   [0, 8192)            2 parities x 8 ranks x 64 doubles: the 29 sums of one evaluation + a generation flag at double index 32
+//   [8192, 8192+256)     control words: [0] comm_gen (local, monotonic over the life of the context: never reset, so a stale flag can never
+//                        match), [1] exchange generation (local), [2] block counter (local), [16..24) exchange flags written by the peers
+//   [16384, ...)         L1 exchange buffer X: one double per residual-block slot (max_features)
+#define LL_COMM_CTRL_OFF 8192
+#define LL_COMM_X_OFF 16384
 int launch_solve(ll_ctx* ctx, const SolveArgs& a);
+// Sharded mode, K10: every rank pushes the loss-corrected L1 norms of the slots it owns into every peer's X buffer (NVLink stores), then a
+// flag barrier; afterwards X is identical on all ranks (NaN where nobody produced a block).
+int launch_l1_exchange(ll_ctx* ctx, const double* d_l1, int M);
 int solve_max_slots(ll_ctx* ctx);
 
 // ---------------------------------------------------------------------------------------------- clouds (cloud.cu)

@@ -452,7 +452,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
       if (a.world > 1 && warp == 0) {
         // fused all-reduce over NVLink peer memory: every rank writes its 29 sums into slot [rank] of every peer's staging
         // buffer (double-buffered by generation parity), then sums the slots in rank order -> bit-identical on all ranks.
-        const unsigned g1 = gen + 1; const int par = g1 & 1;
+        unsigned* cgen = (unsigned*)((char*)a.comm_local + LL_COMM_CTRL_OFF);   // monotonic over the life of the context
+        const unsigned g1 = *cgen + 1; const int par = g1 & 1;
         for (int p = 0; p < a.world; p++) {
           double* dst = a.comm_peer[p] + ((size_t)par * 8 + a.rank) * 64;
           if (lane < NSUM) dst[lane] = s_sum[lane];
@@ -465,6 +466,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
         double t = 0;
         if (lane < NSUM) for (int p = 0; p < a.world; p++) t += *((volatile double*)(a.comm_local + ((size_t)par * 8 + p) * 64 + lane));
         if (lane < NSUM) s_sum[lane] = t;
+        if (lane == 0) *cgen = g1;
       }
       __syncthreads();
       if (tid == 0) {
@@ -564,5 +566,35 @@ int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
   SolveArgs args = a; void* kargs[] = {&args, &tiles_per_cta};
   LL_CUDA(ctx, cudaLaunchCooperativeKernel((void*)lm_solve_kernel, dim3(grid), dim3(SOLVE_THREADS), kargs, smem, ctx->stream));
   ctx->launches++;
+  return LL_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------- sharded mode: K10 exchange over peer memory
+struct L1ExchangeArgs { const double* l1; int M; int rank, world; char* comm_local; char* comm_peer[8]; };
+__global__ void __launch_bounds__(256) l1_exchange_kernel(L1ExchangeArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.M) {
+    const double v = a.l1[i];
+    if (v < INFINITY) for (int p = 0; p < a.world; p++) ((double*)(a.comm_peer[p] + LL_COMM_X_OFF))[i] = v;   // one owner per slot: no write conflicts
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  unsigned* ctrl = (unsigned*)(a.comm_local + LL_COMM_CTRL_OFF);
+  if (atomicAdd(&ctrl[2], 1u) != gridDim.x - 1) return;
+  // last CTA of this rank: all of this rank's pushes are issued and fenced; tell every peer, then wait for every peer
+  ctrl[2] = 0u;
+  const unsigned g = ctrl[1] + 1u; ctrl[1] = g;
+  __threadfence_system();
+  for (int p = 0; p < a.world; p++) st_release_sys_u32((unsigned*)(a.comm_peer[p] + LL_COMM_CTRL_OFF) + 16 + a.rank, g);
+  for (int p = 0; p < a.world; p++) { const unsigned* f = ctrl + 16 + p; while (ld_acquire_sys_u32(f) != g) {} }
+}
+int launch_l1_exchange(ll_ctx* ctx, const double* d_l1, int M) {
+  if (ctx->world <= 1 || M == 0) return LL_OK;
+  L1ExchangeArgs a; a.l1 = d_l1; a.M = M; a.rank = ctx->rank; a.world = ctx->world; a.comm_local = (char*)ctx->comm_local;
+  for (int i = 0; i < 8; i++) a.comm_peer[i] = (char*)ctx->comm_peers[i];
+  l1_exchange_kernel<<<ll_div_up(M, 256), 256, 0, ctx->stream>>>(a); ctx->launches++;
+  LL_CUDA(ctx, cudaGetLastError());
   return LL_OK;
 }

@@ -355,3 +355,20 @@ def test_streaming_mapper_parity(ctx, oracle):
         if om.last["res"] is not None and om.last["res"].registered:
             assert res.registered == 1 and res.icp_iterations == om.last["res"].icp_iterations
     assert gm.pose()[2] == 9
+
+
+# ---------------------------------------------------------------------------------------------- 8(e): sharded registration on >= 2 GPUs
+@pytest.mark.gpu
+def test_sharded_registration_two_gpus():
+    """Spawns tests/multi_gpu/sharded_check.py under torchrun when the box has >= 2 GPUs (skipped on the 1-GPU round-end box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(root, "tests", "multi_gpu", "sharded_check.py")]
+    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=280)
+    assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
