@@ -95,6 +95,8 @@ int ll_voxel_downsample(ll_ctx* ctx, const void* in, size_t n, int fmt, int wher
  * (laser_mapping.hpp:544-545) and in the 4-argument registration overload (point_cloud_registration.hpp:596-597).
  * The two world-frame clouds are copied to HBM and indexed; the handle is immutable and may be shared. */
 int  ll_map_build(ll_ctx* ctx, const void* corner, size_t n_corner, const void* surf, size_t n_surf, int fmt, int where, ll_map** out);
+/* Re-index an existing snapshot in place, reusing its device buffers (the per-scan refresh, laser_mapping.hpp:533-545). Not concurrent with searches of `map`. */
+int  ll_map_rebuild(ll_ctx* ctx, ll_map* map, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where);
 void ll_map_release(ll_map* map);
 size_t ll_map_size(const ll_map* map, int which /*0 corner, 1 surface*/);
 /* Multi-GPU: keep only the points whose cell (cell_size metres) is owned by `rank` of `world`, plus a halo of
@@ -213,7 +215,8 @@ typedef struct {
   ll_pipeline_cfg pipeline;                     /* feature-extraction glue (leaves, pieces)                                                */
   ll_reg_state reg;                             /* registration parameters; the poses in it are the initial pose                           */
 } ll_mapper_config;
-typedef struct { int n_corner, n_surf, map_corner, map_surf, cells_in_fov_corner, cells_in_fov_surf, appended_corner, appended_surf; } ll_mapper_stats;
+typedef struct { int n_corner, n_surf, map_corner, map_surf, cells_in_fov_corner, cells_in_fov_surf, appended_corner, appended_surf;
+                 float ms_front_end, ms_refresh, ms_register, ms_append; /* host wall clock per phase, syncs included */ } ll_mapper_stats;
 typedef struct ll_mapper ll_mapper;
 void ll_mapper_config_default(ll_mapper_config* cfg);
 int  ll_mapper_create(ll_ctx* ctx, const ll_mapper_config* cfg, ll_mapper** out);

@@ -236,10 +236,7 @@ int ll_last_features_dev(ll_ctx* ctx, const ll_point** corner_dev, size_t* n_cor
 }
 
 // ---------------------------------------------------------------------------------------------- S2
-static int map_build_common(ll_ctx* ctx, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where, ll_map** out) {
-  if (!ctx || !out) return LL_ERR_INVALID;
-  cudaSetDevice(ctx->device);
-  ll_map* m = new ll_map(); m->device = ctx->device;
+static int map_index(ll_ctx* ctx, ll_map* m, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where) {
   size_t nmax = nc > ns ? nc : ns;
   LL_CUDA(ctx, ctx->feat_buf.reserve(align256(nmax * 16) + 256));
   float4* d_in = ctx->feat_buf.as<float4>();
@@ -248,8 +245,22 @@ static int map_build_common(ll_ctx* ctx, const void* corner, size_t nc, const vo
   if (st == LL_OK) st = upload_cloud(ctx, surf, ns, fmt, where, d_in);
   if (st == LL_OK) st = build_bucket_tree(ctx, d_in, (int)ns, &m->surf);
   if (st == LL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = LL_ERR_CUDA;
+  return st;
+}
+static int map_build_common(ll_ctx* ctx, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where, ll_map** out) {
+  if (!ctx || !out) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  ll_map* m = new ll_map(); m->device = ctx->device;
+  int st = map_index(ctx, m, corner, nc, surf, ns, fmt, where);
   if (st != LL_OK) { m->corner.storage.release(); m->surf.storage.release(); delete m; return st; }
   *out = m; return LL_OK;
+}
+// Re-index an existing snapshot in place (device buffers are reused when large enough): the per-scan refresh of
+// update_buff_for_matching (laser_mapping.hpp:544-545) without an allocation per scan.  The caller must not be searching `map` concurrently.
+int ll_map_rebuild(ll_ctx* ctx, ll_map* map, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where) {
+  if (!ctx || !map) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  return map_index(ctx, map, corner, nc, surf, ns, fmt, where);
 }
 int ll_map_build(ll_ctx* ctx, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where, ll_map** out) {
   return map_build_common(ctx, corner, nc, surf, ns, fmt, where, out);

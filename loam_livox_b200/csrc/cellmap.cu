@@ -33,7 +33,7 @@ struct ll_cellmap {
   unsigned long long* keys = nullptr; int* last_update = nullptr; int* create_frame = nullptr; int* epoch = nullptr; int* bump = nullptr;
   int* d_counters = nullptr;        // [0] number of cells, [1] scratch
   float4* pts = nullptr; int* pt_slot = nullptr; int* pt_epoch = nullptr;
-  DevBuf table_buf, store_buf, out_buf, tmp_buf;
+  DevBuf table_buf, store_buf, store_alt, out_buf, tmp_buf;
 };
 
 __device__ __forceinline__ unsigned long long cm_pack(int k, int j, int i) {
@@ -206,7 +206,7 @@ int ll_cellmap_create(ll_ctx* ctx, float resolution, int revisit_threshold, int 
 void ll_cellmap_release(ll_cellmap* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  m->table_buf.release(); m->store_buf.release(); m->out_buf.release(); m->tmp_buf.release(); delete m;
+  m->table_buf.release(); m->store_buf.release(); m->store_alt.release(); m->out_buf.release(); m->tmp_buf.release(); delete m;
 }
 int ll_cellmap_stats(ll_ctx* ctx, ll_cellmap* m, int* cells, int* stored_points, int* frame_idx) {
   if (!ctx || !m) return LL_ERR_INVALID;
@@ -314,11 +314,12 @@ int ll_cellmap_assemble(ll_ctx* ctx, ll_cellmap* m, const double q_wxyz[4], cons
   if (down_sample_replace) {
     const int n_new = n_keep + n_cen;
     int cap_new = m->cap_pts; while (cap_new < n_new) cap_new *= 2;
-    DevBuf nb; LL_CUDA(ctx, nb.reserve(align256((size_t)cap_new * 16) + 2 * align256((size_t)cap_new * 4)));
+    DevBuf& nb = m->store_alt;   // ping-pong: the two stores persist, so a refresh allocates nothing in steady state
+    LL_CUDA(ctx, nb.reserve(align256((size_t)cap_new * 16) + 2 * align256((size_t)cap_new * 4)));
     float4* np = nb.as<float4>(); int* ns = (int*)((char*)np + align256((size_t)cap_new * 16)); int* ne = (int*)((char*)ns + align256((size_t)cap_new * 4));
     cm_rebuild_kernel<<<ll_div_up(n_new > 0 ? n_new : 1, 256), 256, 0, s>>>(m->pts, m->pt_slot, m->pt_epoch, ikeep, cnt + 2, d_out, cslot, cnt + 3, m->epoch, np, ns, ne, cap_new);
-    LL_CUDA(ctx, cudaStreamSynchronize(s));
-    m->store_buf.release(); m->store_buf = nb; m->pts = np; m->pt_slot = ns; m->pt_epoch = ne; m->cap_pts = cap_new; m->n_pts = n_new;
+    { DevBuf t = m->store_buf; m->store_buf = m->store_alt; m->store_alt = t; }   // stream-ordered: later work on this stream sees the new store
+    m->pts = np; m->pt_slot = ns; m->pt_epoch = ne; m->cap_pts = cap_new; m->n_pts = n_new;
     ctx->launches++;
   }
   *n_out = (size_t)n_cen;

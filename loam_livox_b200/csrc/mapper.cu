@@ -8,6 +8,7 @@
 //   Laser_mapping::init_pointcloud_registration    /root/reference/source/laser_mapping.hpp:1266-1297
 // The reference refreshes the match map on a background thread after every registered scan, with the pose of that scan; here the refresh
 // runs at the start of the next scan (same pose, same map content), so the result is the reference's with maximum_parallel_thread = 1.
+#include <chrono>
 #include <cstring>
 #include "common.cuh"
 #include "kernels.cuh"
@@ -19,6 +20,7 @@ int ll_cellmap_append(ll_ctx*, ll_cellmap*, const void*, size_t, int, int);
 int ll_cellmap_assemble(ll_ctx*, ll_cellmap*, const double*, const double*, float, float, float, int, ll_point*, size_t, size_t*, int*, const ll_point**);
 }
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct ll_mapper {
   ll_ctx* ctx = nullptr;
@@ -30,6 +32,7 @@ struct ll_mapper {
   DevBuf work;   // transformed / down-sampled feature clouds
   DevBuf snap;   // match-map snapshot clouds (corner, surf) between refreshes
   int snap_n[2] = {0, 0}, fov[2] = {0, 0};
+  bool have_map = false;
   bool map_dirty = false;   // m_if_mapping_updated_{corner,surface}
 };
 
@@ -78,12 +81,14 @@ int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int
   ll_ctx* ctx = m->ctx; cudaSetDevice(ctx->device);
   cudaStream_t s = ctx->stream;
   if (stats) memset(stats, 0, sizeof(*stats));
+  double tp = now_ms();
   RegArrays A; LL_TRY(reg_arrays(ctx, 0, &A));
   int nc = 0, ns = 0, dropped = 0;
   LL_TRY(scan_front_end(ctx, raw, n, fmt, where, stamp, &m->cfg.pipeline, A, &nc, &ns, &dropped));
   memset(out, 0, sizeof(*out)); out->status = 1;
   for (int k = 0; k < 4; k++) out->q_w_curr[k] = m->q_w_curr[k]; for (int k = 0; k < 3; k++) out->t_w_curr[k] = m->t_w_curr[k];
-  if (stats) { stats->n_corner = nc; stats->n_surf = ns; }
+  if (stats) { stats->n_corner = nc; stats->n_surf = ns; stats->ms_front_end = (float)(now_ms() - tp); }
+  tp = now_ms();
   if (dropped) return LL_OK;                                                     // laser_feature_extractor.hpp:287
   m->frame_index++;                                                              // m_current_frame_index++ (:1350)
   // ---- update_buff_for_matching (mode 1): snapshot of the cells in range and in the FOV, whole-map VoxelGrid, index
@@ -100,12 +105,16 @@ int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int
     if (ms > 0) LL_TRY(launch_voxel_grid(ctx, (const float4*)d_ms, (int)ms, nullptr, m->cfg.plane_resolution, s1, d_sc + 1)); else LL_CUDA(ctx, cudaMemsetAsync(d_sc + 1, 0, 4, s));   // :536-537
     LL_CUDA(ctx, cudaMemcpyAsync(hc, d_sc, 8, cudaMemcpyDeviceToHost, s));
     LL_CUDA(ctx, cudaStreamSynchronize(s));
-    if (m->match_map) { ll_map_release(m->match_map); m->match_map = nullptr; }
-    if (hc[0] > 0 && hc[1] > 0) LL_TRY(ll_map_build(ctx, s0, (size_t)hc[0], s1, (size_t)hc[1], LL_FMT_XYZI16, LL_DEVICE, &m->match_map));                      // :544-545
+    m->have_map = false;
+    if (hc[0] > 0 && hc[1] > 0) {
+      if (!m->match_map) LL_TRY(ll_map_build(ctx, s0, (size_t)hc[0], s1, (size_t)hc[1], LL_FMT_XYZI16, LL_DEVICE, &m->match_map));
+      else LL_TRY(ll_map_rebuild(ctx, m->match_map, s0, (size_t)hc[0], s1, (size_t)hc[1], LL_FMT_XYZI16, LL_DEVICE));   // buffers reused: no allocation per scan
+      m->have_map = true;
+    }                      // :544-545
     m->snap_n[0] = hc[0]; m->snap_n[1] = hc[1]; m->fov[0] = fov_c; m->fov[1] = fov_s;
     m->map_dirty = false;
   }
-  if (stats) { stats->map_corner = m->snap_n[0]; stats->map_surf = m->snap_n[1]; stats->cells_in_fov_corner = m->fov[0]; stats->cells_in_fov_surf = m->fov[1]; }
+  if (stats) { stats->ms_refresh = (float)(now_ms() - tp); stats->map_corner = m->snap_n[0]; stats->map_surf = m->snap_n[1]; stats->cells_in_fov_corner = m->fov[0]; stats->cells_in_fov_surf = m->fov[1]; }
   const size_t cap = (size_t)(nc > ns ? nc : ns) + 16;
   LL_CUDA(ctx, m->work.reserve(4 * align256(cap * 16) + 1024));
   float4* w0 = m->work.as<float4>(); float4* w1 = (float4*)((char*)w0 + align256(cap * 16)); float4* w2 = (float4*)((char*)w1 + align256(cap * 16)); float4* w3 = (float4*)((char*)w2 + align256(cap * 16));
@@ -118,7 +127,10 @@ int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int
   for (int k = 0; k < 3; k++) { st.t_w_last[k] = m->t_w_curr[k]; st.t_w_curr[k] = m->t_w_curr[k]; }
   st.para_buffer_incremental[0] = st.para_buffer_incremental[1] = st.para_buffer_incremental[2] = 0; st.para_buffer_incremental[3] = 1;
   st.para_buffer_incremental[4] = st.para_buffer_incremental[5] = st.para_buffer_incremental[6] = 0;
-  if (m->match_map) LL_TRY(register_device(ctx, m->match_map, A, nc, ns, &st, out));   // no map yet: the gate of :199 returns 1
+  tp = now_ms();
+  if (m->have_map) LL_TRY(register_device(ctx, m->match_map, A, nc, ns, &st, out));
+  if (stats) stats->ms_register = (float)(now_ms() - tp);
+  tp = now_ms();   // no map yet: the gate of :199 returns 1
   if (out->status == 0) return LL_OK;                                           // rejected: frame discarded (:1413-1416)
   // ---- new features to the world frame (:1422-1432), VoxelGrid (:1434-1437), cell maps (:1492-1493)
   double* h = (double*)((char*)ctx->pinned + 40960); for (int k = 0; k < 4; k++) h[k] = out->q_w_curr[k]; for (int k = 0; k < 3; k++) h[4 + k] = out->t_w_curr[k];
@@ -131,7 +143,7 @@ int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int
   LL_TRY(ll_cellmap_append(ctx, m->cells_corner, w0, (size_t)hc[0], LL_FMT_XYZI16, LL_DEVICE));
   LL_TRY(ll_cellmap_append(ctx, m->cells_surf, w1, (size_t)hc[1], LL_FMT_XYZI16, LL_DEVICE));
   m->map_dirty = true;                                                           // m_if_mapping_updated_* (:1490-1491)
-  if (stats) { stats->appended_corner = hc[0]; stats->appended_surf = hc[1]; }
+  if (stats) { stats->appended_corner = hc[0]; stats->appended_surf = hc[1]; stats->ms_append = (float)(now_ms() - tp); }
   for (int k = 0; k < 4; k++) m->q_w_curr[k] = out->q_w_curr[k]; for (int k = 0; k < 3; k++) m->t_w_curr[k] = out->t_w_curr[k];   // :1496-1505
   return LL_OK;
 }

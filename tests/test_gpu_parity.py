@@ -357,6 +357,29 @@ def test_streaming_mapper_parity(ctx, oracle):
     assert gm.pose()[2] == 9
 
 
+@pytest.mark.gpu
+def test_streaming_mapper_long_sequence(ctx, oracle):
+    """60 scans with yaw motion: the cell maps grow, get down-sampled-and-replaced on every refresh, and the two implementations must stay
+    together (pose 1e-4, identical feature / map / append counts) all the way."""
+    from loam_livox_b200 import capi
+    from loam_livox_b200.registration import Laser_mapping
+    poses = S.trajectory(n_scans=60, n_static=3, speed=2.0, yaw_rate_deg=20.0)
+    gm = Laser_mapping(ctx, reg=capi.default_reg_state(mapping_init_accumulate_frames=3))
+    om = oracle.Mapper(oracle.default_params(mapping_init_accumulate_frames=3, num_threads=4), threads=4)
+    worst = 0.0
+    for k, pose in enumerate(poses):
+        raw = S.make_scan(16000, pose, seed=S.SEED + 100 + k)
+        res, stats = gm.process_new_scan(raw, 100.0 + 0.1 * k)
+        ost, oq, ot = om.process_scan(raw, 100.0 + 0.1 * k)
+        assert res.status == ost, k
+        q, t, _ = gm.pose()
+        worst = max(worst, float(np.linalg.norm(t - ot)), float(S.quat_angle(q, oq)))
+        assert worst < 1e-4, (k, worst)
+        assert (stats.map_corner, stats.map_surf, stats.appended_corner, stats.appended_surf) == \
+            (om.last["map_corner"], om.last["map_surf"], om.last["appended_corner"], om.last["appended_surf"]), k
+    assert gm.cfg.down_sample_replace == 1
+
+
 # ---------------------------------------------------------------------------------------------- 8(e): sharded registration on >= 2 GPUs
 @pytest.mark.gpu
 def test_sharded_registration_two_gpus():
