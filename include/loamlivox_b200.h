@@ -113,7 +113,7 @@ int ll_knn(ll_ctx* ctx, const ll_map* map, int which, const ll_point* queries, s
 /* Inputs of Point_cloud_registration: exactly what Laser_mapping::init_pointcloud_registration copies
  * (laser_mapping.hpp:1266-1297) plus the members Scene_alignment pokes (scene_alignment.hpp:233-243,292-306). */
 typedef struct {
-  int    if_motion_deblur;                /* m_if_motion_deblur                                        */
+  int    if_motion_deblur;                /* m_if_motion_deblur: *_mb functors + interpolated matching */
   int    current_frame_index;             /* m_current_frame_index                                     */
   int    mapping_init_accumulate_frames;  /* m_mapping_init_accumulate_frames                          */
   int    icp_max_iterations;              /* m_para_icp_max_iterations                                 */

@@ -8,3 +8,11 @@ __device__ __forceinline__ void qrot_d(const double q[4] /*w,x,y,z*/, double vx,
   double dx = uy * cz - uz * cy, dy = uz * cx - ux * cz, dz = ux * cy - uy * cx;
   ox = (vx + cx * w) + dx; oy = (vy + cy * w) + dy; oz = (vz + cz * w) + dz;
 }
+
+// Point_cloud_registration::refine_blur (point_cloud_registration.hpp:128-141) with m_if_motion_deblur = 1: float arithmetic (the time stamps
+// are converted to float at the call), not clamped below 0, 1.0 when not finite or > 1.
+__device__ __forceinline__ float refine_blur_f(float in_blur, float min_blur, float max_blur) {
+  const float res = (in_blur - min_blur) / (max_blur - min_blur);
+  if (!isfinite(res) || (double)res > 1.0) return 1.0f;
+  return res;
+}

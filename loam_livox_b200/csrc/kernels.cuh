@@ -12,6 +12,7 @@ struct TreeView {
 TreeView make_view(const BucketTree& t);
 int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t);
 
+struct RegDevState;
 struct KnnBlocksArgs {
   TreeView corner, surf;
   const float4* feat;     // [n_corner + n_surf] scan-frame features (x,y,z,timestamp)
@@ -25,6 +26,8 @@ struct KnnBlocksArgs {
   float* knn_d;                 // optional debug output [M x 5]
   const int* perm;              // spatially sorted feature order (corners then surfaces), or null = caller order
   int rank, world; float inv_cell;
+  const RegDevState* st;        // motion deblur reads q_last/t_last, t_incre and the Rodrigues terms from here
+  int deblur;
 };
 int launch_knn_query(ll_ctx* ctx, const BucketTree& t, const float4* d_q, int nq, int* d_idx, float* d_d);
 int launch_knn_blocks(ll_ctx* ctx, const KnnBlocksArgs& a);
@@ -55,7 +58,9 @@ struct RegDevState {
   double bound, huber_a, inliner_dis, inlier_ratio, min_icp_R, min_icp_T;
   double inlier_threshold, angular_diff, t_diff, final_cost, initial_cost;
   int corner_avail, surf_avail, icp_done, icp_iter, num_residual_blocks, status, total_lm_iterations, total_evaluations;
-  int n_unique; int pad0;
+  int n_unique; int if_motion_deblur;
+  // motion deblur (N1): time-stamp range of refine_blur, and compute_interpolatation_rodrigue's outputs (:607-620) after every solve #2
+  double min_ts, max_ts, interp_theta, interp_hat[9], interp_hat_sq[9];
   unsigned int bar_count, bar_gen;
   LmState lm;
 };
@@ -75,6 +80,7 @@ struct SolveArgs {
                              // 2: plain solve (parity hook) ; 3: evaluate once at st->x (parity hook, writes sums to st->lm.H/g/x_cost)
   // multi-GPU
   int rank, world; double* comm_local; double* comm_peer[8];
+  int deblur;                // 1: *_mb functors (ceres_icp.hpp:81-233), s per block from the feature's time stamp
 };
 // Layout of the IPC-exported staging buffer of a rank (ll_comm_local_handle):
 //   [0, 8192)            2 parities x 8 ranks x 64 doubles: the 29 sums of one evaluation + a generation flag at double index 32

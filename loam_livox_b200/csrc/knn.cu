@@ -463,7 +463,23 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a
   // pointAssociateToMap (non-deblur branch): p_w = q_curr * p + t_curr in fp64, stored as fp32
   const double* qc = a.pose; const double* tc = a.pose + 4;
   double wx, wy, wz; qrot_d(qc, (double)f.x, (double)f.y, (double)f.z, wx, wy, wz);
-  const float qx = (float)(wx + tc[0]), qy = (float)(wy + tc[1]), qz = (float)(wz + tc[2]);
+  float qx = (float)(wx + tc[0]), qy = (float)(wy + tc[1]), qz = (float)(wz + tc[2]);
+  if (a.deblur) {
+    // pointAssociateToMap, deblur branch (:627-654, if_undistore_in_matching = 1): Rodrigues-interpolated increment applied before q_last
+    const RegDevState* st = a.st;
+    const double is = (double)refine_blur_f(f.w, (float)st->min_ts, (float)st->max_ts);
+    if (is != 1.0) {
+      const double th = st->interp_theta * is; double sn, cs; sincos(th, &sn, &cs); const double oc = 1.0 - cs;
+      const double* H = st->interp_hat; const double* H2 = st->interp_hat_sq;
+      const double px = (double)f.x, py = (double)f.y, pz = (double)f.z;
+      double rx = ((1.0 + sn * H[0] + oc * H2[0]) * px + (sn * H[1] + oc * H2[1]) * py) + (sn * H[2] + oc * H2[2]) * pz;
+      double ry = ((sn * H[3] + oc * H2[3]) * px + (1.0 + sn * H[4] + oc * H2[4]) * py) + (sn * H[5] + oc * H2[5]) * pz;
+      double rz = ((sn * H[6] + oc * H2[6]) * px + (sn * H[7] + oc * H2[7]) * py) + (1.0 + sn * H[8] + oc * H2[8]) * pz;
+      rx += st->x[4] * (is * 1.0); ry += st->x[5] * (is * 1.0); rz += st->x[6] * (is * 1.0);
+      double ox, oy, oz; qrot_d(st->pose_last, rx, ry, rz, ox, oy, oz);
+      qx = (float)(ox + st->pose_last[4]); qy = (float)(oy + st->pose_last[5]); qz = (float)(oz + st->pose_last[6]);
+    }
+  }
   const bool finite_in = isfinite(f.x) && isfinite(f.y) && isfinite(f.z);
   bool owned = true;
   if (a.world > 1) owned = cell_owner(qx, qy, qz, a.inv_cell, a.world) == (unsigned)a.rank;

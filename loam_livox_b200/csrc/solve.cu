@@ -15,6 +15,7 @@
 #include <cfloat>
 #include "common.cuh"
 #include "kernels.cuh"
+#include "exact_math.cuh"
 
 #define FULL 0xffffffffu
 #define NSUM 29          // 21 JtJ (upper, row-major) + 6 Jtr + cost + valid-block count
@@ -265,7 +266,7 @@ __device__ __noinline__ void lm_step(LmState& L, const double* sums, double boun
 }
 
 // ------------------------------------------------------------------------------------------------ per-block evaluation
-struct Slot { double px, py, pz, ax, ay, az, vx, vy, vz; int type; };
+struct Slot { double px, py, pz, ax, ay, az, vx, vy, vz; double s; int type; };   // s: m_motion_blur_s (deblur only)
 
 struct EvalConst {   // uniform per evaluation, in shared memory
   double x[7];       // trial point: q (x,y,z,w), t
@@ -273,17 +274,37 @@ struct EvalConst {   // uniform per evaluation, in shared memory
   double Rl[3][3];   // rotation by q_last (columns = q_last * e_k)
   double tl[3];
   double huber_a, huber_b;
+  // Eigen slerp(Identity -> q_incre) pieces that do not depend on the block (deblur only): theta = acos|w|, d(theta)/dw
+  double sl_theta, sl_sin, sl_cos, sl_dth_dw; int sl_lerp;
 };
 
 __device__ __forceinline__ void cross3(double ax, double ay, double az, double bx, double by, double bz, double& ox, double& oy, double& oz) {
   ox = ay * bz - az * by; oy = az * bx - ax * bz; oz = ax * by - ay * bx;
 }
 // residual (3), optional Jacobian (3 x 6, tangent space), returns rho' (Huber weight) and adds 0.5*rho to *cost
+// MB = the *_mb functors (ceres_icp.hpp:106-134, :187-218): q_incre -> Identity.slerp(s, q_incre) (Eigen: scale0 * I + scale1 * q_incre, scales
+// from theta = acos|w|, plain lerp when |w| >= 1 - eps; the result is NOT re-normalised and goes through _transformVector as is) and
+// t_incre -> s * t_incre.  The derivative below is the derivative of exactly that expression, which is what the reference's Jets compute.
+template <bool MB>
 __device__ __forceinline__ void eval_block(const Slot& s, const EvalConst& E, double r[3], double J[6][3], bool want_j) {
-  const double ux = E.x[0], uy = E.x[1], uz = E.x[2], w = E.x[3];
+  double ux = E.x[0], uy = E.x[1], uz = E.x[2], w = E.x[3];
+  double sc1 = 1.0, dsc0 = 0.0, dsc1 = 0.0, ts = 1.0;   // scale1, d(scale0)/dw, d(scale1)/dw, translation scale
+  if (MB) {
+    const double sb = s.s; double sc0;
+    if (E.sl_lerp) { sc0 = 1.0 - sb; sc1 = sb; }
+    else {
+      double s0, c0, s1, c1; sincos((1.0 - sb) * E.sl_theta, &s0, &c0); sincos(sb * E.sl_theta, &s1, &c1);
+      const double inv = 1.0 / E.sl_sin;
+      sc0 = s0 * inv; sc1 = s1 * inv;
+      dsc0 = ((1.0 - sb) * c0 * E.sl_sin - s0 * E.sl_cos) * inv * inv * E.sl_dth_dw;
+      dsc1 = (sb * c1 * E.sl_sin - s1 * E.sl_cos) * inv * inv * E.sl_dth_dw;
+    }
+    if (E.x[3] < 0.0) { sc1 = -sc1; dsc1 = -dsc1; }
+    ux *= sc1; uy *= sc1; uz *= sc1; w = sc0 + sc1 * E.x[3]; ts = sb;
+  }
   double cx, cy, cz; cross3(ux, uy, uz, s.px, s.py, s.pz, cx, cy, cz); cx += cx; cy += cy; cz += cz;   // 2 (u x p)
   double ex, ey, ez; cross3(ux, uy, uz, cx, cy, cz, ex, ey, ez);
-  const double yx = s.px + w * cx + ex + E.x[4], yy = s.py + w * cy + ey + E.x[5], yz = s.pz + w * cz + ez + E.x[6];
+  const double yx = s.px + w * cx + ex + ts * E.x[4], yy = s.py + w * cy + ey + ts * E.x[5], yz = s.pz + w * cz + ez + ts * E.x[6];
   const double dx = E.Rl[0][0] * yx + E.Rl[0][1] * yy + E.Rl[0][2] * yz + E.tl[0] - s.ax;
   const double dy = E.Rl[1][0] * yx + E.Rl[1][1] * yy + E.Rl[1][2] * yz + E.tl[1] - s.ay;
   const double dz = E.Rl[2][0] * yx + E.Rl[2][1] * yy + E.Rl[2][2] * yz + E.tl[2] - s.az;
@@ -296,12 +317,17 @@ __device__ __forceinline__ void eval_block(const Slot& s, const EvalConst& E, do
   for (int c = 0; c < 6; c++) {
     double gx, gy, gz;   // derivative of y = q_incre * p + t_incre along tangent direction c
     if (c < 3) {
-      const double dux = E.PJ[0][c], duy = E.PJ[1][c], duz = E.PJ[2][c], dw = E.PJ[3][c];
+      double dux = E.PJ[0][c], duy = E.PJ[1][c], duz = E.PJ[2][c], dw = E.PJ[3][c];
+      if (MB) {   // direction of (scale1 u, scale0 + scale1 w) along the ambient direction (du, dw)
+        const double k1 = dsc1 * dw;
+        dux = k1 * E.x[0] + sc1 * dux; duy = k1 * E.x[1] + sc1 * duy; duz = k1 * E.x[2] + sc1 * duz;
+        dw = dsc0 * dw + k1 * E.x[3] + sc1 * dw;
+      }
       double ax, ay, az; cross3(dux, duy, duz, s.px, s.py, s.pz, ax, ay, az); ax += ax; ay += ay; az += az;  // 2 (du x p)
       double bx, by, bz; cross3(dux, duy, duz, cx, cy, cz, bx, by, bz);                                       // du x 2(u x p)
       double fx, fy, fz; cross3(ux, uy, uz, ax, ay, az, fx, fy, fz);                                          // u x 2(du x p)
       gx = dw * cx + w * ax + bx + fx; gy = dw * cy + w * ay + by + fy; gz = dw * cz + w * az + bz + fz;
-    } else { gx = c == 3 ? 1.0 : 0.0; gy = c == 4 ? 1.0 : 0.0; gz = c == 5 ? 1.0 : 0.0; }
+    } else { gx = c == 3 ? ts : 0.0; gy = c == 4 ? ts : 0.0; gz = c == 5 ? ts : 0.0; }
     const double e0 = E.Rl[0][0] * gx + E.Rl[0][1] * gy + E.Rl[0][2] * gz;
     const double e1 = E.Rl[1][0] * gx + E.Rl[1][1] * gy + E.Rl[1][2] * gz;
     const double e2 = E.Rl[2][0] * gx + E.Rl[2][1] * gy + E.Rl[2][2] * gz;
@@ -325,22 +351,28 @@ __device__ void setup_const(EvalConst& E, const double* x, const RegDevState* st
   for (int k = 0; k < 3; k++) { double e[3] = {k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0}, o[3]; d_qrot(ql, e, o); E.Rl[0][k] = o[0]; E.Rl[1][k] = o[1]; E.Rl[2][k] = o[2]; }
   E.tl[0] = st->pose_last[4]; E.tl[1] = st->pose_last[5]; E.tl[2] = st->pose_last[6];
   E.huber_a = st->huber_a; E.huber_b = st->huber_a * st->huber_a;
+  { const double d = x[3], ad = fabs(d);
+    if (ad >= 1.0 - 2.220446049250313e-16) { E.sl_lerp = 1; E.sl_theta = 0; E.sl_sin = 1; E.sl_cos = 1; E.sl_dth_dw = 0; }
+    else { E.sl_lerp = 0; E.sl_theta = acos(ad); E.sl_sin = sin(E.sl_theta); E.sl_cos = cos(E.sl_theta); E.sl_dth_dw = -(d < 0.0 ? -1.0 : 1.0) / sqrt(1.0 - ad * ad); } }
 }
 
 // ------------------------------------------------------------------------------------------------ the persistent kernel
 // Residual blocks are staged ONCE into shared memory (SoA: 52 B per block) and stay there for the whole solve.
 // CTA b owns the 512-slot tiles b, b + grid, b + 2 grid, ...  (coalesced staging, balanced over the SMs).
-struct SmemSlots { float* p[3]; float* a[3]; double* v[3]; int* type; };
+struct SmemSlots { float* p[3]; float* a[3]; double* v[3]; int* type; float* s; };
 __device__ __forceinline__ SmemSlots carve(unsigned char* base, int cap) {
   SmemSlots s; double* d = (double*)base;
   s.v[0] = d; s.v[1] = d + cap; s.v[2] = d + 2 * cap;
   float* f = (float*)(d + 3 * (size_t)cap);
   s.p[0] = f; s.p[1] = f + cap; s.p[2] = f + 2 * cap; s.a[0] = f + 3 * cap; s.a[1] = f + 4 * cap; s.a[2] = f + 5 * cap;
   s.type = (int*)(f + 6 * (size_t)cap);
+  s.s = f + 7 * (size_t)cap;   // only carved for the deblur kernel (SLOT_BYTES_MB)
   return s;
 }
 #define SLOT_BYTES 52
+#define SLOT_BYTES_MB 56
 
+template <bool MB>
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a, int tiles_per_cta) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ EvalConst E;
@@ -373,6 +405,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
         const float4 f = a.feat[i];
         S.p[0][li] = f.x; S.p[1][li] = f.y; S.p[2][li] = f.z; S.a[0][li] = ba.x; S.a[1][li] = ba.y; S.a[2][li] = ba.z;
         S.v[0][li] = a.blk_v[(size_t)i * 3]; S.v[1][li] = a.blk_v[(size_t)i * 3 + 1]; S.v[2][li] = a.blk_v[(size_t)i * 3 + 2];
+        if (MB) S.s[li] = refine_blur_f(f.w, (float)st->min_ts, (float)st->max_ts);   // refine_blur(pointOri.intensity, ...) * 1.0 (:309, :407)
       }
     }
     S.type[li] = type;
@@ -407,7 +440,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
       if (s.type != 0) {
         s.px = S.p[0][li]; s.py = S.p[1][li]; s.pz = S.p[2][li]; s.ax = S.a[0][li]; s.ay = S.a[1][li]; s.az = S.a[2][li];
         s.vx = S.v[0][li]; s.vy = S.v[1][li]; s.vz = S.v[2][li];
-        double r[3], J[6][3]; eval_block(s, E, r, J, true);
+        if (MB) s.s = (double)S.s[li];
+        double r[3], J[6][3]; eval_block<MB>(s, E, r, J, true);
         double rho0; const double wgt = huber_weight(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], E.huber_a, E.huber_b, rho0);
         acc[27] += 0.5 * rho0; acc[28] += 1.0;
         int h = 0;
@@ -490,6 +524,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
             for (int k = 0; k < 4; k++) st->pose_curr[k] = qcur[k]; for (int k = 0; k < 3; k++) st->pose_curr[4 + k] = tcur[k];
             st->angular_diff = (double)((float)d_angdist(qcur, ql)) * 57.3;
             double td = 0; for (int k = 0; k < 3; k++) td += (tcur[k] - st->pose_last[4 + k]) * (tcur[k] - st->pose_last[4 + k]); st->t_diff = sqrt(td);
+            if (MB) {   // compute_interpolatation_rodrigue (:607-620): Eigen::AngleAxisd(q_incre), used by the next iteration's pointAssociateToMap
+              double n = sqrt(qi[1] * qi[1] + qi[2] * qi[2] + qi[3] * qi[3]), ax[3], ang;
+              if (n != 0.0) { ang = 2.0 * atan2(n, fabs(qi[0])); if (qi[0] < 0) n = -n; ax[0] = qi[1] / n; ax[1] = qi[2] / n; ax[2] = qi[3] / n; }
+              else { ang = 0; ax[0] = 1; ax[1] = 0; ax[2] = 0; }
+              const double an = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]); for (int k = 0; k < 3; k++) ax[k] /= an;
+              double* H = st->interp_hat; for (int k = 0; k < 9; k++) H[k] = 0;
+              H[1] = -ax[2]; H[3] = ax[2]; H[2] = ax[1]; H[6] = -ax[1]; H[5] = -ax[0]; H[7] = ax[0];
+              for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double t = 0; for (int k = 0; k < 3; k++) t += H[i * 3 + k] * H[k * 3 + j]; st->interp_hat_sq[i * 3 + j] = t; }
+              st->interp_theta = ang;
+            }
             st->final_cost = L.final_cost; st->initial_cost = L.initial_cost; st->num_residual_blocks = L.n_valid;
             double dt = 0; for (int k = 0; k < 3; k++) dt += (st->t_last_opt[k] - ti[k]) * (st->t_last_opt[k] - ti[k]);
             if (d_angdist(st->q_last_opt, qi) < 57.3 * st->min_icp_R && sqrt(dt) < st->min_icp_T) st->icp_done = 1;
@@ -527,7 +571,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
         if (s.type != 0) {
           s.px = S.p[0][li]; s.py = S.p[1][li]; s.pz = S.p[2][li]; s.ax = S.a[0][li]; s.ay = S.a[1][li]; s.az = S.a[2][li];
           s.vx = S.v[0][li]; s.vy = S.v[1][li]; s.vz = S.v[2][li];
-          double r[3], J[6][3]; eval_block(s, E, r, J, false);
+          if (MB) s.s = (double)S.s[li];
+          double r[3], J[6][3]; eval_block<MB>(s, E, r, J, false);
           double rho0; const double wgt = huber_weight(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], E.huber_a, E.huber_b, rho0);
           const double sc = sqrt(wgt);
           l1 = fabs(sc * r[0]) + fabs(sc * r[1]) + fabs(sc * r[2]);
@@ -538,33 +583,24 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
   }
 }
 
-__global__ void lm_reset_kernel(RegDevState* st, int max_iterations) {
-  LmState& L = st->lm;
-  L.phase = 0; L.iteration = 0; L.max_iterations = max_iterations; L.num_invalid = 0; L.done = 0; L.termination = 0; L.last_successful = 1; L.reuse_diagonal = 0;
-  L.ls_iters = 0; L.n_valid = 0; L.total_iterations = 0; L.total_evaluations = 0;
-  // iteration zero evaluates Plus(x, 0): the projection of the start point onto the bounds (TrustRegionMinimizer::IterationZero)
-  double x0[7], z[6] = {0, 0, 0, 0, 0, 0};
-  for (int k = 0; k < 7; k++) x0[k] = st->x[k];
-  d_plus(x0, z, st->bound, L.trial);
-  st->bar_count = 0;
-}
-
 #define SOLVE_MAX_SMEM (200 * 1024)
-int solve_max_slots(ll_ctx* ctx) { return ctx->num_sms * ((SOLVE_MAX_SMEM / SLOT_BYTES) / SOLVE_THREADS) * SOLVE_THREADS; }
+int solve_max_slots(ll_ctx* ctx) { return ctx->num_sms * ((SOLVE_MAX_SMEM / SLOT_BYTES_MB) / SOLVE_THREADS) * SOLVE_THREADS; }
 
 int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
-  static bool attr_set[64] = {false};
+  static bool attr_set[64][2] = {{false, false}};
   const int tiles = ll_div_up(a.M > 0 ? a.M : 1, SOLVE_THREADS);
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;   // CTAs without blocks would only lengthen the barrier
   int tiles_per_cta = ll_div_up(tiles, grid);
-  const size_t smem = (size_t)tiles_per_cta * SOLVE_THREADS * SLOT_BYTES;
+  const int mb = a.deblur ? 1 : 0;
+  const size_t smem = (size_t)tiles_per_cta * SOLVE_THREADS * (mb ? SLOT_BYTES_MB : SLOT_BYTES);
   if (smem > SOLVE_MAX_SMEM) { ctx->set_error("too many residual-block slots for the shared-memory-resident solver"); return LL_ERR_CAPACITY; }
-  if (ctx->device < 64 && !attr_set[ctx->device]) {
-    LL_CUDA(ctx, cudaFuncSetAttribute(lm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_MAX_SMEM));
-    attr_set[ctx->device] = true;
+  void* fn = mb ? (void*)lm_solve_kernel<true> : (void*)lm_solve_kernel<false>;
+  if (ctx->device < 64 && !attr_set[ctx->device][mb]) {
+    LL_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_MAX_SMEM));
+    attr_set[ctx->device][mb] = true;
   }
   SolveArgs args = a; void* kargs[] = {&args, &tiles_per_cta};
-  LL_CUDA(ctx, cudaLaunchCooperativeKernel((void*)lm_solve_kernel, dim3(grid), dim3(SOLVE_THREADS), kargs, smem, ctx->stream));
+  LL_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SOLVE_THREADS), kargs, smem, ctx->stream));
   ctx->launches++;
   return LL_OK;
 }

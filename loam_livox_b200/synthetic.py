@@ -248,6 +248,27 @@ def make_features(n_corner, n_surf, pose=None, seed=SEED, sigma=0.004, max_range
     return collect(corner_sampler, n_corner), collect(surf_sampler, n_surf)
 
 
+def make_distorted_features(pose_last, pose_curr, nc, ns, seed=0):
+    """Features of a scan taken WHILE the sensor moves from pose_last to pose_curr: the point with time fraction s is seen from
+    pose_last * (slerp(I, s, q_inc), s t_inc) -- the motion model the *_mb functors assume.  intensity = time stamp in [0, 0.1]."""
+    from scipy.spatial.transform import Rotation as Rsc, Slerp
+    fc, fs = make_features(nc, ns, pose_curr, seed=SEED + seed)
+    Rl, Rc = pose_last.R(), pose_curr.R()
+    R_inc = Rl.T @ Rc
+    t_inc = Rl.T @ (pose_curr.t - pose_last.t)
+    sl = Slerp([0.0, 1.0], Rsc.from_matrix(np.stack([np.eye(3), R_inc])))
+    out = []
+    for f in (fc, fs):
+        s = f[:, 3].astype(np.float64) / 0.1
+        pw = f[:, :3].astype(np.float64) @ Rc.T + pose_curr.t                 # world points (sampled from the scene at pose_curr)
+        Ri = sl(s).as_matrix()                                                # interpolated increment per point
+        y = (pw - pose_last.t) @ Rl - s[:, None] * t_inc                      # q_last^-1 (pw - t_last) - s t_inc
+        ps = np.einsum("nji,nj->ni", Ri, y)                                   # R_i^T y
+        g = f.copy(); g[:, :3] = ps.astype(np.float32)
+        out.append(g)
+    return out[0], out[1]
+
+
 def trajectory(n_scans=1000, n_static=50, dt=0.1, speed=1.0, yaw_rate_deg=5.0):
     """C3 trajectory: n_static stationary scans, then forward motion with sinusoidal yaw."""
     poses = []

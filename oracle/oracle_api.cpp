@@ -141,14 +141,14 @@ int orc_build_blocks(const float* map_c, int nmc, void* tree_c, const float* map
   reg.build_blocks(map_c, *(KdTree*)tree_c, map_s, *(KdTree*)tree_s, scan_c, nc, scan_s, ns, blocks, corner_avail, surf_avail);
   for (size_t i = 0; i < blocks.size() && (int)i < cap; i++) {
     double* o = blocks_out + i * 11; const ResidualBlock& b = blocks[i];
-    o[0] = b.type; for (int k = 0; k < 3; k++) { o[1 + k] = b.p[k]; o[4 + k] = b.a[k]; o[7 + k] = b.v[k]; } o[10] = b.motion_blur ? b.s : -1.0;
+    o[0] = b.type; for (int k = 0; k < 3; k++) { o[1 + k] = b.p[k]; o[4 + k] = b.a[k]; o[7 + k] = b.v[k]; } o[10] = b.motion_blur ? b.s : std::nan("");   // NaN = not a *_mb block (s itself may be negative: refine_blur does not clamp below 0)
     src_out[2 * i] = b.src; src_out[2 * i + 1] = b.src_index;
   }
   return (int)blocks.size();
 }
 static void fill_problem(Problem& prob, const double* blocks, int M, const double q_last[4], const double t_last[3], double huber_a, double bound) {
   prob.blocks.resize(M);
-  for (int i = 0; i < M; i++) { const double* o = blocks + (size_t)i * 11; ResidualBlock& b = prob.blocks[i]; b.type = (int)o[0]; for (int k = 0; k < 3; k++) { b.p[k] = o[1 + k]; b.a[k] = o[4 + k]; b.v[k] = o[7 + k]; } b.motion_blur = o[10] >= 0; b.s = o[10] >= 0 ? o[10] : 1.0; b.src = 0; b.src_index = i; }
+  for (int i = 0; i < M; i++) { const double* o = blocks + (size_t)i * 11; ResidualBlock& b = prob.blocks[i]; b.type = (int)o[0]; for (int k = 0; k < 3; k++) { b.p[k] = o[1 + k]; b.a[k] = o[4 + k]; b.v[k] = o[7 + k]; } b.motion_blur = !std::isnan(o[10]); b.s = b.motion_blur ? o[10] : 1.0; b.src = 0; b.src_index = i; }
   prob.q_last = {q_last[0], q_last[1], q_last[2], q_last[3]}; prob.t_last = {t_last[0], t_last[1], t_last[2]}; prob.huber_a = huber_a; prob.t_bound = bound;
 }
 // Evaluate at x: cost, gradient(6), JtJ (36, row-major, loss-corrected, unscaled), residuals (3M, optional), jac (18M, optional)

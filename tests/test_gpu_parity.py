@@ -395,3 +395,60 @@ def test_sharded_registration_two_gpus():
            os.path.join(root, "tests", "multi_gpu", "sharded_check.py")]
     out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=280)
     assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+# ---------------------------------------------------------------------------------------------- N1: motion deblur (*_mb functors)
+@pytest.mark.gpu
+def test_deblur_blocks_normal_equations_and_solve(ctx, oracle):
+    from loam_livox_b200.registration import Map, Point_cloud_registration
+    mc, ms, fc, fs, pose = _mk(5000, 45000, 1000, 9000)
+    fc[:7, 3] = 0.15; fs[:9, 3] = -0.02                      # refine_blur: > 1 -> 1.0, negative stays negative
+    guess = S.perturb_pose(pose, np.random.default_rng(1))
+    m = Map(ctx, mc, ms)
+    reg = Point_cloud_registration(ctx, if_motion_deblur=1)
+    reg.set_pose(guess.q, guess.t)
+    typ, a3, v3, ca, sa = reg.build_blocks(m, fc, fs)
+    p = oracle.default_params(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t, if_motion_deblur=1)
+    blocks, src, oca, osa = oracle.build_blocks(mc, oracle.KdTree(mc), ms, oracle.KdTree(ms), fc, fs, p)
+    assert (ca, sa) == (oca, osa)
+    slot = src[:, 1] + np.where(src[:, 0] == 1, fc.shape[0], 0)
+    assert np.array_equal(np.nonzero(typ)[0], slot) and np.array_equal(a3[slot], blocks[:, 4:7])
+    for d in ([0.01, -0.02, 0.015, 0.05, -0.04, 0.03], [0, 0, 0, 0.02, 0.01, -0.03], [-0.2, 0.1, 0.05, 0.0, 0.1, 0.0]):   # slerp branch, lerp branch (w = 1), larger angle
+        x = oracle.plus([0, 0, 0, 1, 0, 0, 0], d)
+        H, g, cost = reg.normal_equations(x)
+        oc, og, oH = oracle.evaluate(blocks, guess.q, guess.t, x)
+        assert abs(cost - oc) <= 1e-10 * abs(oc)
+        assert np.allclose(g, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
+        assert np.allclose(H, oH, rtol=1e-9, atol=1e-9 * np.abs(oH).max())
+    for iters in (2, 50):
+        xg, ic, fcst, it = reg.solve([0, 0, 0, 1, 0, 0, 0], iters)
+        xo, so = oracle.solve(blocks, guess.q, guess.t, [0, 0, 0, 1, 0, 0, 0], iters)
+        assert it == int(so["iterations"])
+        assert abs(ic - so["initial_cost"]) <= 1e-10 * so["initial_cost"] and abs(fcst - so["final_cost"]) <= 1e-9 * so["final_cost"]
+        assert np.allclose(xg, xo, rtol=0, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_deblur_register_parity_on_distorted_scan(ctx, oracle):
+    """if_motion_deblur = 1 end to end: Rodrigues-interpolated matching transform + *_mb residuals, on a scan distorted by sensor motion."""
+    from loam_livox_b200.registration import Map, Point_cloud_registration
+    mc, ms = S.make_map(5000, 45000)
+    m = Map(ctx, mc, ms)
+    tc, ts = oracle.KdTree(mc), oracle.KdTree(ms)
+    last = S.default_pose()
+    for k, (eul, dt) in enumerate((((0.01, -0.02, 0.06), (0.20, -0.05, 0.02)), ((-0.03, 0.01, -0.10), (-0.10, 0.15, 0.0)))):
+        curr = S.Pose(S.quat_mul(last.q, S.quat_from_euler(*eul)), last.t + np.array(dt))
+        fc, fs = S.make_distorted_features(last, curr, 1000, 9000, seed=k)
+        reg = Point_cloud_registration(ctx, if_motion_deblur=1)
+        reg.set_pose(last.q, last.t)
+        st = reg.find_out_incremental_transfrom(m, fc, fs)
+        p = oracle.default_params(q_w_last=last.q, t_w_last=last.t, q_w_curr=last.q, t_w_curr=last.t, if_motion_deblur=1)
+        ost, ores = oracle.register(mc, tc, ms, ts, fc, fs, p)
+        r = reg.result
+        assert st == ost == 1 and r.icp_iterations == ores.icp_iterations
+        assert (r.corner_used, r.surf_used, r.num_residual_blocks) == (ores.corner_used, ores.surf_used, ores.num_residual_blocks)
+        dtn = np.linalg.norm(np.array(r.t_w_curr) - np.array(ores.t_w_curr)); da = S.quat_angle(np.array(r.q_w_curr), np.array(ores.q_w_curr))
+        assert dtn < 1e-4 and da < 1e-4, (dtn, da)        # north_star tolerance
+        assert dtn < 1e-6 and da < 1e-6, (dtn, da)
+        assert abs(r.final_cost - ores.final_cost) <= 1e-6 * ores.final_cost
+        assert np.linalg.norm(np.array(r.t_w_curr) - curr.t) < 0.01 and S.quat_angle(np.array(r.q_w_curr), curr.q) < 2e-3

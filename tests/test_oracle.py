@@ -222,3 +222,49 @@ def test_oracle_reproduces_golden_file(oracle):
     st, res = oracle.register(g["map_corner"], oracle.KdTree(g["map_corner"]), g["map_surf"], oracle.KdTree(g["map_surf"]), g["feat_corner"], g["feat_surf"], p)
     assert st == int(g["reg_status"]) and res.icp_iterations == int(g["reg_iters"])
     assert np.allclose(res.t_w_curr, g["reg_t"], atol=1e-12) and np.allclose(res.q_w_curr, g["reg_q"], atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------- N1: motion deblur (*_mb functors)
+def test_mb_jet_jacobian_matches_central_differences(oracle):
+    mc, ms = S.make_map(2000, 18000)
+    pose = S.default_pose()
+    fc, fs = S.make_features(150, 1350, pose)
+    fc[:5, 3] = 0.15; fs[:5, 3] = -0.02                                       # s > 1 -> 1.0 ; s < 0 stays negative (refine_blur, :128-141)
+    guess = S.perturb_pose(pose, np.random.default_rng(0))
+    p = oracle.default_params(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t, if_motion_deblur=1)
+    b, src, ca, sa = oracle.build_blocks(mc, oracle.KdTree(mc), ms, oracle.KdTree(ms), fc, fs, p)
+    s = b[:, 10]
+    assert s.min() < 0 and s.max() == 1.0 and np.all(s >= -0.3)
+    for x in (oracle.plus([0, 0, 0, 1, 0, 0, 0], [0.01, -0.02, 0.015, 0.05, -0.04, 0.03]), np.array([0, 0, 0, 1.0, 0.01, 0.0, -0.02])):   # sin branch, lerp branch
+        cost, g, H, r, J = oracle.evaluate(b, guess.q, guess.t, x, want_full=True)
+        eps = 1e-6
+        quad = np.repeat((r.reshape(-1, 3) ** 2).sum(1) < 0.009, 3)
+        for c in range(3, 6):                                                 # translation columns: the slerp branch does not matter
+            d = np.zeros(6); d[c] = eps
+            rp = oracle.evaluate(b, guess.q, guess.t, oracle.plus(x, d, bound=10.0), want_full=True)[3]
+            rm = oracle.evaluate(b, guess.q, guess.t, oracle.plus(x, -d, bound=10.0), want_full=True)[3]
+            assert np.allclose(((rp - rm) / (2 * eps))[quad], J[quad, c], atol=2e-6)
+        if x[3] < 1.0:                                                        # rotation columns away from the lerp/slerp branch switch
+            for c in range(3):
+                d = np.zeros(6); d[c] = eps
+                rp = oracle.evaluate(b, guess.q, guess.t, oracle.plus(x, d, bound=10.0), want_full=True)[3]
+                rm = oracle.evaluate(b, guess.q, guess.t, oracle.plus(x, -d, bound=10.0), want_full=True)[3]
+                assert np.allclose(((rp - rm) / (2 * eps))[quad], J[quad, c], atol=5e-6)
+        assert np.allclose(H, J.T @ J, rtol=1e-12) and np.allclose(g, J.T @ r, rtol=1e-12)
+
+
+def test_deblur_registration_recovers_motion_of_distorted_scan(oracle):
+    """A scan distorted by the sensor's own motion: with if_motion_deblur = 1 the pose is recovered clearly better than without."""
+    mc, ms = S.make_map(5000, 45000)
+    tc, ts = oracle.KdTree(mc), oracle.KdTree(ms)
+    last = S.default_pose()
+    curr = S.Pose(S.quat_mul(last.q, S.quat_from_euler(0.01, -0.02, 0.06)), last.t + np.array([0.20, -0.05, 0.02]))
+    fc, fs = S.make_distorted_features(last, curr, 500, 4500)
+    errs = {}
+    for mode in (0, 1):
+        p = oracle.default_params(q_w_last=last.q, t_w_last=last.t, q_w_curr=last.q, t_w_curr=last.t, if_motion_deblur=mode)
+        st, res = oracle.register(mc, tc, ms, ts, fc, fs, p)
+        assert st == 1 and res.registered == 1
+        errs[mode] = (np.linalg.norm(np.array(res.t_w_curr) - curr.t), S.quat_angle(np.array(res.q_w_curr), curr.q))
+    assert errs[1][0] < 0.01 and errs[1][1] < 2e-3, errs
+    assert errs[1][0] < 0.5 * errs[0][0], errs
