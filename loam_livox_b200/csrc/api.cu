@@ -469,6 +469,15 @@ int ll_solve(ll_ctx* ctx, int max_iterations, double x_io[7], double* initial_co
   return LL_OK;
 }
 
+// Diagnostics: the master CTA's cycle counters of the last registration (kernels.cuh: RegDevState::prof).
+int ll_debug_solver_cycles(ll_ctx* ctx, long long out8[8]) {
+  if (!ctx || !out8) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  LL_CUDA(ctx, cudaMemcpyAsync(out8, ctx->d_reg->prof, 8 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return LL_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- whole per-scan step
 }  // extern "C"
 

@@ -62,6 +62,7 @@ struct RegDevState {
   // motion deblur (N1): time-stamp range of refine_blur, and compute_interpolatation_rodrigue's outputs (:607-620) after every solve #2
   double min_ts, max_ts, interp_theta, interp_hat[9], interp_hat_sq[9];
   unsigned int bar_count, bar_gen;
+  long long prof[8];   // master-CTA cycle counters of the solver: eval, wait, grid reduce, lm_step, publish, #evaluations, staging, epilogue
   LmState lm;
 };
 

@@ -359,21 +359,75 @@ __device__ void setup_const(EvalConst& E, const double* x, const RegDevState* st
 // ------------------------------------------------------------------------------------------------ the persistent kernel
 // Residual blocks are staged ONCE into shared memory (SoA: 52 B per block) and stay there for the whole solve.
 // CTA b owns the 512-slot tiles b, b + grid, b + 2 grid, ...  (coalesced staging, balanced over the SMs).
-struct SmemSlots { float* p[3]; float* a[3]; double* v[3]; int* type; float* s; };
-__device__ __forceinline__ SmemSlots carve(unsigned char* base, int cap) {
+// ---- fast path (no motion deblur): the same r, J^T J, J^T r in closed form.
+// With y = q_incre p, d' = y + t_incre - a' (a' = R_last^T (a - t_last)), w' = R_last^T v, alpha = d'.w':
+//   line : r = R_last (d' - alpha w'),  J = R_last (I - w' w'^T) G        plane: r = R_last alpha w',  J = R_last w' w'^T G
+//   G = d(y + t)/d(tangent, t) = [ -2 [y]x | I ]   (EigenQuaternionParameterization::Plus is q <- exp(delta) q: dy = 2 delta x y)
+// so J^T J and J^T r need only beta = G^T w', G^T G (closed form in y) and G^T r': ~150 fp64 flops per block instead of ~1200.
+struct FastSlot { double px, py, pz, ax, ay, az, wx, wy, wz; int type; };
+__device__ __forceinline__ void fast_residual(const FastSlot& s, const EvalConst& E, double y[3], double r[3], double& alpha) {
+  const double ux = E.x[0], uy = E.x[1], uz = E.x[2], w = E.x[3];
+  double cx, cy, cz; cross3(ux, uy, uz, s.px, s.py, s.pz, cx, cy, cz); cx += cx; cy += cy; cz += cz;
+  double ex, ey, ez; cross3(ux, uy, uz, cx, cy, cz, ex, ey, ez);
+  y[0] = s.px + w * cx + ex; y[1] = s.py + w * cy + ey; y[2] = s.pz + w * cz + ez;
+  const double dx = y[0] + E.x[4] - s.ax, dy = y[1] + E.x[5] - s.ay, dz = y[2] + E.x[6] - s.az;
+  alpha = dx * s.wx + dy * s.wy + dz * s.wz;
+  if (s.type == 1) { r[0] = dx - alpha * s.wx; r[1] = dy - alpha * s.wy; r[2] = dz - alpha * s.wz; }
+  else { r[0] = alpha * s.wx; r[1] = alpha * s.wy; r[2] = alpha * s.wz; }
+}
+__device__ __forceinline__ void fast_accumulate(const FastSlot& s, const EvalConst& E, double acc[NSUM]) {
+  double y[3], r[3], alpha; fast_residual(s, E, y, r, alpha);
+  double rho0; const double wgt = huber_weight(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], E.huber_a, E.huber_b, rho0);
+  acc[27] += 0.5 * rho0; acc[28] += 1.0;
+  const bool line = s.type == 1;
+  const double wn2 = s.wx * s.wx + s.wy * s.wy + s.wz * s.wz;
+  // beta = G^T w' = (2 y x w', w')
+  double b[6]; cross3(y[0], y[1], y[2], s.wx, s.wy, s.wz, b[0], b[1], b[2]); b[0] += b[0]; b[1] += b[1]; b[2] += b[2]; b[3] = s.wx; b[4] = s.wy; b[5] = s.wz;
+  // gradient: line J^T r = G^T (r - w'(w'.r)); plane J^T r = |w'|^2 G^T r
+  double rr[3], cg;
+  if (line) { const double wr = s.wx * r[0] + s.wy * r[1] + s.wz * r[2]; rr[0] = r[0] - wr * s.wx; rr[1] = r[1] - wr * s.wy; rr[2] = r[2] - wr * s.wz; cg = wgt; }
+  else { rr[0] = r[0]; rr[1] = r[1]; rr[2] = r[2]; cg = wgt * wn2; }
+  double g0, g1, g2; cross3(y[0], y[1], y[2], rr[0], rr[1], rr[2], g0, g1, g2);
+  acc[21] += cg * (g0 + g0); acc[22] += cg * (g1 + g1); acc[23] += cg * (g2 + g2); acc[24] += cg * rr[0]; acc[25] += cg * rr[1]; acc[26] += cg * rr[2];
+  // Hessian: line G^T G - (2 - |w'|^2) beta beta^T ; plane |w'|^2 beta beta^T
+  const double cb = line ? -wgt * (2.0 - wn2) : wgt * wn2;
+  int h = 0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+#pragma unroll
+    for (int j = i; j < 6; j++) { acc[h] += cb * b[i] * b[j]; h++; }
+  }
+  if (line) {
+    const double yy = y[0] * y[0] + y[1] * y[1] + y[2] * y[2], w4 = 4.0 * wgt, w2 = 2.0 * wgt;
+    // rows 0..2 of G^T G: [4 (|y|^2 I - y y^T) | 2 [e_i x y]_k], rows 3..5: [ . | I ]
+    acc[0] += w4 * (yy - y[0] * y[0]); acc[1] -= w4 * y[0] * y[1]; acc[2] -= w4 * y[0] * y[2];
+    acc[4] -= w2 * y[2]; acc[5] += w2 * y[1];                                  // (0,3) = 0, (0,4) = -2 y_z, (0,5) = 2 y_y
+    acc[6] += w4 * (yy - y[1] * y[1]); acc[7] -= w4 * y[1] * y[2];
+    acc[8] += w2 * y[2]; acc[10] -= w2 * y[0];                                 // (1,3) = 2 y_z, (1,4) = 0, (1,5) = -2 y_x
+    acc[11] += w4 * (yy - y[2] * y[2]);
+    acc[12] -= w2 * y[1]; acc[13] += w2 * y[0];                                // (2,3) = -2 y_y, (2,4) = 2 y_x, (2,5) = 0
+    acc[15] += wgt; acc[18] += wgt; acc[20] += wgt;                            // (3,3), (4,4), (5,5)
+  }
+}
+
+struct SmemSlots { float* p[3]; float* a[3]; double* v[3]; double* ap[3]; int* type; float* s; };
+// MB (general path): v = line direction / plane normal (world), a = anchor (world, fp32-exact), s = blur factor      -> 56 B / slot
+// !MB (fast path):   v = R_last^T v, ap = R_last^T (a - t_last): the evaluation never touches the last pose again   -> 64 B / slot
+__device__ __forceinline__ SmemSlots carve(unsigned char* base, int cap, bool mb) {
   SmemSlots s; double* d = (double*)base;
-  s.v[0] = d; s.v[1] = d + cap; s.v[2] = d + 2 * cap;
-  float* f = (float*)(d + 3 * (size_t)cap);
-  s.p[0] = f; s.p[1] = f + cap; s.p[2] = f + 2 * cap; s.a[0] = f + 3 * cap; s.a[1] = f + 4 * cap; s.a[2] = f + 5 * cap;
-  s.type = (int*)(f + 6 * (size_t)cap);
-  s.s = f + 7 * (size_t)cap;   // only carved for the deblur kernel (SLOT_BYTES_MB)
+  s.v[0] = d; s.v[1] = d + cap; s.v[2] = d + 2 * cap; d += 3 * (size_t)cap;
+  if (!mb) { s.ap[0] = d; s.ap[1] = d + cap; s.ap[2] = d + 2 * cap; d += 3 * (size_t)cap; } else { s.ap[0] = s.ap[1] = s.ap[2] = nullptr; }
+  float* f = (float*)d;
+  s.p[0] = f; s.p[1] = f + cap; s.p[2] = f + 2 * cap; f += 3 * (size_t)cap;
+  if (mb) { s.a[0] = f; s.a[1] = f + cap; s.a[2] = f + 2 * cap; f += 3 * (size_t)cap; s.s = f; f += cap; } else { s.a[0] = s.a[1] = s.a[2] = nullptr; s.s = nullptr; }
+  s.type = (int*)f;
   return s;
 }
-#define SLOT_BYTES 52
+#define SLOT_BYTES 64
 #define SLOT_BYTES_MB 56
 
 template <bool MB>
-__global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a, int tiles_per_cta) {
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a, int tiles_per_cta, int tile) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ EvalConst E;
   __shared__ double s_red[SOLVE_THREADS / 32][NSUM + 1];
@@ -383,8 +437,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
   RegDevState* st = a.st;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cap = tiles_per_cta * SOLVE_THREADS;
-  const SmemSlots S = carve(s_dyn, cap);
+  const SmemSlots S = carve(s_dyn, cap, MB);
 
+  const long long t_k0 = clock64();
   // ---- stage this CTA's residual blocks
   double thr = 0;
   if (a.mode == 1) {   // K10 tail: threshold = max(inliner_dis, element floor(ratio * n_unique) of the sorted unique L1 norms)
@@ -396,16 +451,24 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
     if (blockIdx.x == 0 && tid == 0) st->inlier_threshold = thr;
   }
   for (int k = 0; k < tiles_per_cta; k++) {
-    const int i = (blockIdx.x + gridDim.x * k) * SOLVE_THREADS + tid, li = k * SOLVE_THREADS + tid;
+    const int i = (blockIdx.x + gridDim.x * k) * tile + tid, li = k * SOLVE_THREADS + tid;   // tile <= SOLVE_THREADS slots per CTA and pass: threads >= tile idle
     int type = 0;
-    if (i < a.M) {
+    if (i < a.M && tid < tile) {
       const float4 ba = a.blk_a[i]; type = __float_as_int(ba.w);
       if (type != 0 && a.mode == 1 && (a.l1[i] > thr)) type = 0;
       if (type != 0) {
         const float4 f = a.feat[i];
-        S.p[0][li] = f.x; S.p[1][li] = f.y; S.p[2][li] = f.z; S.a[0][li] = ba.x; S.a[1][li] = ba.y; S.a[2][li] = ba.z;
-        S.v[0][li] = a.blk_v[(size_t)i * 3]; S.v[1][li] = a.blk_v[(size_t)i * 3 + 1]; S.v[2][li] = a.blk_v[(size_t)i * 3 + 2];
-        if (MB) S.s[li] = refine_blur_f(f.w, (float)st->min_ts, (float)st->max_ts);   // refine_blur(pointOri.intensity, ...) * 1.0 (:309, :407)
+        S.p[0][li] = f.x; S.p[1][li] = f.y; S.p[2][li] = f.z;
+        const double v0 = a.blk_v[(size_t)i * 3], v1 = a.blk_v[(size_t)i * 3 + 1], v2 = a.blk_v[(size_t)i * 3 + 2];
+        if (MB) {
+          S.a[0][li] = ba.x; S.a[1][li] = ba.y; S.a[2][li] = ba.z; S.v[0][li] = v0; S.v[1][li] = v1; S.v[2][li] = v2;
+          S.s[li] = refine_blur_f(f.w, (float)st->min_ts, (float)st->max_ts);   // refine_blur(pointOri.intensity, ...) * 1.0 (:309, :407)
+        } else {   // into the frame of the last pose: w' = R_last^T v, a' = R_last^T (a - t_last)
+          const double qc[4] = {st->pose_last[0], -st->pose_last[1], -st->pose_last[2], -st->pose_last[3]};
+          double vin[3] = {v0, v1, v2}, o[3]; d_qrot(qc, vin, o); S.v[0][li] = o[0]; S.v[1][li] = o[1]; S.v[2][li] = o[2];
+          double ain[3] = {(double)ba.x - st->pose_last[4], (double)ba.y - st->pose_last[5], (double)ba.z - st->pose_last[6]}; d_qrot(qc, ain, o);
+          S.ap[0][li] = o[0]; S.ap[1][li] = o[1]; S.ap[2][li] = o[2];
+        }
       }
     }
     S.type[li] = type;
@@ -429,19 +492,30 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
   }
   __syncthreads();
 
+  if (master && tid == 0) st->prof[6] += clock64() - t_k0;
   for (;;) {
+    const long long t_e0 = clock64();
     // ---- evaluate: r, J, Huber, 29 partial sums per thread
     double acc[NSUM];
 #pragma unroll
     for (int i = 0; i < NSUM; i++) acc[i] = 0.0;
     for (int k = 0; k < tiles_per_cta; k++) {
       const int li = k * SOLVE_THREADS + tid;
-      Slot s; s.type = S.type[li];
+      const int type = S.type[li];
+      if (!MB) {
+        if (type != 0) {
+          FastSlot fs; fs.type = type; fs.px = S.p[0][li]; fs.py = S.p[1][li]; fs.pz = S.p[2][li]; fs.ax = S.ap[0][li]; fs.ay = S.ap[1][li]; fs.az = S.ap[2][li];
+          fs.wx = S.v[0][li]; fs.wy = S.v[1][li]; fs.wz = S.v[2][li];
+          fast_accumulate(fs, E, acc);
+        }
+        continue;
+      }
+      Slot s; s.type = type;
       if (s.type != 0) {
         s.px = S.p[0][li]; s.py = S.p[1][li]; s.pz = S.p[2][li]; s.ax = S.a[0][li]; s.ay = S.a[1][li]; s.az = S.a[2][li];
         s.vx = S.v[0][li]; s.vy = S.v[1][li]; s.vz = S.v[2][li];
-        if (MB) s.s = (double)S.s[li];
-        double r[3], J[6][3]; eval_block<MB>(s, E, r, J, true);
+        s.s = (double)S.s[li];
+        double r[3], J[6][3]; eval_block<true>(s, E, r, J, true);
         double rho0; const double wgt = huber_weight(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], E.huber_a, E.huber_b, rho0);
         acc[27] += 0.5 * rho0; acc[28] += 1.0;
         int h = 0;
@@ -471,9 +545,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
     __threadfence();
     __syncthreads();
     // ---- grid barrier: every CTA arrives; the master waits for all of them, reduces the grid in fixed order and advances the solver
+    const long long t_e1 = clock64();
+    long long t_e2 = 0, t_e3 = 0;
     if (tid == 0) atomicAdd(&st->bar_count, 1u);
     if (master) {
-      if (tid == 0) { while (ld_acquire_u32(&st->bar_count) != gridDim.x) {} st->bar_count = 0; }
+      if (tid == 0) { while (ld_acquire_u32(&st->bar_count) != gridDim.x) {} st->bar_count = 0; t_e2 = clock64(); }
       __syncthreads();
       __threadfence();
       const int val = tid & 31, grp = tid >> 5;   // 16 groups x 32 values
@@ -504,9 +580,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
       }
       __syncthreads();
       if (tid == 0) {
+        t_e3 = clock64();
         LmState& L = s_lm;
         if (a.mode == 3) { for (int i = 0; i < 21; i++) L.H[i] = s_sum[i]; for (int i = 0; i < 6; i++) L.g[i] = s_sum[21 + i]; L.x_cost = s_sum[27]; L.n_valid = (int)(s_sum[28] + 0.5); L.done = 1; }
         else lm_step(L, s_sum, st->bound);
+        const long long t_e4 = clock64();
         // publish the next trial point (or the result)
         st->lm.done = L.done;
         if (!L.done) { for (int k = 0; k < 7; k++) st->lm.trial[k] = L.trial[k]; }
@@ -541,6 +619,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
             st->icp_iter++;
           }
         }
+        { const long long t_e5 = clock64(); st->prof[0] += t_e1 - t_e0; st->prof[1] += t_e2 - t_e1; st->prof[2] += t_e3 - t_e2; st->prof[3] += t_e4 - t_e3; st->prof[4] += t_e5 - t_e4; st->prof[5] += 1; }
         __threadfence();
         st_release_u32(&st->bar_gen, gen + 1);
       }
@@ -562,17 +641,28 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
     if (s_flag) break;
   }
   // ---- epilogue of solve #1: loss-corrected L1 norm of every block at the solution (problem.Evaluate, :476-481)
+  const long long t_p0 = clock64();
   if (a.mode == 0) {
     for (int k = 0; k < tiles_per_cta; k++) {
-      const int i = (blockIdx.x + gridDim.x * k) * SOLVE_THREADS + tid, li = k * SOLVE_THREADS + tid;
-      if (i < a.M) {
+      const int i = (blockIdx.x + gridDim.x * k) * tile + tid, li = k * SOLVE_THREADS + tid;
+      if (i < a.M && tid < tile) {
         double l1 = INFINITY;
         Slot s; s.type = S.type[li];
         if (s.type != 0) {
-          s.px = S.p[0][li]; s.py = S.p[1][li]; s.pz = S.p[2][li]; s.ax = S.a[0][li]; s.ay = S.a[1][li]; s.az = S.a[2][li];
-          s.vx = S.v[0][li]; s.vy = S.v[1][li]; s.vz = S.v[2][li];
-          if (MB) s.s = (double)S.s[li];
-          double r[3], J[6][3]; eval_block<MB>(s, E, r, J, false);
+          double r[3];
+          if (MB) {
+            s.px = S.p[0][li]; s.py = S.p[1][li]; s.pz = S.p[2][li]; s.ax = S.a[0][li]; s.ay = S.a[1][li]; s.az = S.a[2][li];
+            s.vx = S.v[0][li]; s.vy = S.v[1][li]; s.vz = S.v[2][li];
+            s.s = (double)S.s[li];
+            double J[6][3]; eval_block<true>(s, E, r, J, false);
+          } else {   // the L1 norm is taken in the world frame: r = R_last r'
+            FastSlot fs; fs.type = s.type; fs.px = S.p[0][li]; fs.py = S.p[1][li]; fs.pz = S.p[2][li]; fs.ax = S.ap[0][li]; fs.ay = S.ap[1][li]; fs.az = S.ap[2][li];
+            fs.wx = S.v[0][li]; fs.wy = S.v[1][li]; fs.wz = S.v[2][li];
+            double y[3], rp[3], alpha; fast_residual(fs, E, y, rp, alpha);
+            r[0] = E.Rl[0][0] * rp[0] + E.Rl[0][1] * rp[1] + E.Rl[0][2] * rp[2];
+            r[1] = E.Rl[1][0] * rp[0] + E.Rl[1][1] * rp[1] + E.Rl[1][2] * rp[2];
+            r[2] = E.Rl[2][0] * rp[0] + E.Rl[2][1] * rp[1] + E.Rl[2][2] * rp[2];
+          }
           double rho0; const double wgt = huber_weight(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], E.huber_a, E.huber_b, rho0);
           const double sc = sqrt(wgt);
           l1 = fabs(sc * r[0]) + fabs(sc * r[1]) + fabs(sc * r[2]);
@@ -581,15 +671,20 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
       }
     }
   }
+  if (master && tid == 0) st->prof[7] += clock64() - t_p0;
 }
 
 #define SOLVE_MAX_SMEM (200 * 1024)
-int solve_max_slots(ll_ctx* ctx) { return ctx->num_sms * ((SOLVE_MAX_SMEM / SLOT_BYTES_MB) / SOLVE_THREADS) * SOLVE_THREADS; }
+int solve_max_slots(ll_ctx* ctx) { return ctx->num_sms * ((SOLVE_MAX_SMEM / SLOT_BYTES) / SOLVE_THREADS) * SOLVE_THREADS; }
 
 int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
   static bool attr_set[64][2] = {{false, false}};
-  const int tiles = ll_div_up(a.M > 0 ? a.M : 1, SOLVE_THREADS);
-  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;   // CTAs without blocks would only lengthen the barrier
+  // The evaluation is fp64-throughput bound (64 DFMA/clk/SM): spread the slots over ALL SMs, even when that leaves CTAs partly empty.
+  // tile = slots per CTA and pass (a multiple of 32, <= SOLVE_THREADS); measured: 61 full CTAs 8.3 us/evaluation, 148 CTAs x 224 slots 3.5 us.
+  const int M1 = a.M > 0 ? a.M : 1;
+  int tile = ((ll_div_up(M1, ctx->num_sms) + 31) / 32) * 32; if (tile > SOLVE_THREADS) tile = SOLVE_THREADS;
+  const int tiles = ll_div_up(M1, tile);
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   int tiles_per_cta = ll_div_up(tiles, grid);
   const int mb = a.deblur ? 1 : 0;
   const size_t smem = (size_t)tiles_per_cta * SOLVE_THREADS * (mb ? SLOT_BYTES_MB : SLOT_BYTES);
@@ -599,7 +694,7 @@ int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
     LL_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_MAX_SMEM));
     attr_set[ctx->device][mb] = true;
   }
-  SolveArgs args = a; void* kargs[] = {&args, &tiles_per_cta};
+  SolveArgs args = a; void* kargs[] = {&args, &tiles_per_cta, &tile};
   LL_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SOLVE_THREADS), kargs, smem, ctx->stream));
   ctx->launches++;
   return LL_OK;
