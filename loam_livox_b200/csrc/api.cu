@@ -17,7 +17,7 @@ int reg_arrays(ll_ctx* ctx, int M, RegArrays* A) {
   int cap = M > ctx->cfg.max_features ? M : ctx->cfg.max_features;
   int scap = ctx->cfg.max_scan_points > cap ? ctx->cfg.max_scan_points : cap;
   size_t bytes = align256((size_t)cap * 16) * 2 + align256((size_t)cap * 24) + align256((size_t)cap * 8 + 64) * 3 + align256((size_t)ctx->num_sms * 32 * 8) + 4096 +
-                 align256((size_t)cap * 20) * 2 + align256((size_t)cap * 4) * 2 + align256((size_t)scap * 16) * 3;
+                 align256((size_t)cap * 20) * 2 + align256((size_t)cap * 4) * 2 + align256((size_t)scap * 16) * 4;
   LL_CUDA(ctx, ctx->reg_buf.reserve(bytes));
   char* p = ctx->reg_buf.as<char>();
   auto take = [&](size_t b) { char* r = p; p += align256(b); return r; };
@@ -27,7 +27,7 @@ int reg_arrays(ll_ctx* ctx, int M, RegArrays* A) {
   A->partials = (double*)take((size_t)ctx->num_sms * 32 * 8);
   A->n_unique = (int*)take(256); A->counts = (int*)take(256); A->bounds = (float*)take(256); A->pose_tmp = (double*)take(256);
   A->knn_idx = (int*)take((size_t)cap * 20); A->knn_d = (float*)take((size_t)cap * 20); A->perm = (int*)take((size_t)cap * 4);
-  A->tmp_a = (float4*)take((size_t)scap * 16); A->tmp_b = (float4*)take((size_t)scap * 16); A->tmp_c = (float4*)take((size_t)scap * 16);
+  A->tmp_a = (float4*)take((size_t)scap * 16); A->tmp_b = (float4*)take((size_t)scap * 16); A->tmp_c = (float4*)take((size_t)scap * 16); A->tmp_d = (float4*)take((size_t)scap * 16);
   return LL_OK;
 }
 
@@ -58,6 +58,8 @@ int ll_ctx_create(const ll_config* cfg, int device, ll_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return LL_ERR_CUDA; }
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device); ctx->num_sms = prop.multiProcessorCount;
   cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2); cudaEventCreate(&ctx->ev3);
   for (int i = 0; i < 5 * 16 + 2; i++) cudaEventCreate(&ctx->evp[i]);
   ctx->pinned_cap = 1 << 16; cudaHostAlloc(&ctx->pinned, ctx->pinned_cap, cudaHostAllocDefault);
@@ -69,7 +71,8 @@ int ll_ctx_create(const ll_config* cfg, int device, ll_ctx** out) {
 void ll_ctx_destroy(ll_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2);
+  ctx->scratch2.release(); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
   ctx->scratch.release(); ctx->stage_in.release(); ctx->extract_buf.release(); ctx->feat_buf.release(); ctx->reg_buf.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->d_reg) cudaFree(ctx->d_reg);
@@ -492,10 +495,15 @@ int scan_front_end(ll_ctx* ctx, const void* raw, size_t n, int fmt, int where, d
   if (!pc->whole_frame) { LL_TRY(launch_piece_bounds(ctx, pc->pieces, A.bounds)); d_bounds = A.bounds + 2 * pc->use_piece; }
   LL_TRY(launch_get_features(ctx, d_bounds, 0.f, 1.f, A.tmp_a, A.tmp_b, nullptr, A.counts));
   int* cnt = A.counts;   // [0] corners [1] surf [2] full [4..7] VoxelGrid outputs
-  LL_TRY(launch_voxel_grid(ctx, A.tmp_a, ncap, cnt + 0, pc->extractor_leaf_corner, A.tmp_c, cnt + 4));
-  LL_TRY(launch_voxel_grid(ctx, A.tmp_c, ncap, cnt + 4, pc->mapping_leaf_corner, A.tmp_a, cnt + 5));
+  // corner chain on the side stream, surface chain on the main stream (laser_feature_extractor.hpp:372-380 then laser_mapping.hpp:1367-1373)
+  LL_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
+  LL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+  LL_TRY(launch_voxel_grid_on(ctx, ctx->stream2, ctx->scratch2, A.tmp_a, ncap, cnt + 0, pc->extractor_leaf_corner, A.tmp_d, cnt + 4));
+  LL_TRY(launch_voxel_grid_on(ctx, ctx->stream2, ctx->scratch2, A.tmp_d, ncap, cnt + 4, pc->mapping_leaf_corner, A.tmp_a, cnt + 5));
+  LL_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
   LL_TRY(launch_voxel_grid(ctx, A.tmp_b, ncap, cnt + 1, pc->extractor_leaf_surf, A.tmp_c, cnt + 6));
   LL_TRY(launch_voxel_grid(ctx, A.tmp_c, ncap, cnt + 6, pc->mapping_leaf_surf, A.tmp_b, cnt + 7));
+  LL_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
   int* h = (int*)ctx->pinned + 8192;
   LL_CUDA(ctx, cudaMemcpyAsync(h, cnt, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
   LL_CUDA(ctx, cudaMemcpyAsync(h + 8, ctx->ex.d_meta, 12, cudaMemcpyDeviceToHost, s));

@@ -149,7 +149,11 @@ __global__ void vg_centroid_kernel(const float4* __restrict__ in, const VgMeta* 
 }
 
 int launch_voxel_grid(ll_ctx* ctx, const float4* d_in, int n_cap, const int* d_n_in, float leaf, float4* d_out, int* d_n_out) {
-  cudaStream_t s = ctx->stream;
+  return launch_voxel_grid_on(ctx, ctx->stream, ctx->scratch, d_in, n_cap, d_n_in, leaf, d_out, d_n_out);
+}
+// Same, on an explicit stream with its own scratch arena (two VoxelGrid chains of one scan run side by side: every kernel here is far too
+// small to fill the GPU, so the chains overlap almost perfectly).
+int launch_voxel_grid_on(ll_ctx* ctx, cudaStream_t s, DevBuf& scratch, const float4* d_in, int n_cap, const int* d_n_in, float leaf, float4* d_out, int* d_n_out) {
   if (n_cap <= 0) { LL_CUDA(ctx, cudaMemsetAsync(d_n_out, 0, sizeof(int), s)); return LL_OK; }
   size_t sort_bytes = 0, sel_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, n_cap, 0, 32, s);
@@ -157,8 +161,8 @@ int launch_voxel_grid(ll_ctx* ctx, const float4* d_in, int n_cap, const int* d_n
   size_t tmp_bytes = sort_bytes > sel_bytes ? sort_bytes : sel_bytes;
   size_t o_meta = 0, o_k0 = align256(sizeof(VgMeta) + 16), o_k1 = o_k0 + align256((size_t)n_cap * 4), o_v0 = o_k1 + align256((size_t)n_cap * 4), o_v1 = o_v0 + align256((size_t)n_cap * 4),
          o_fl = o_v1 + align256((size_t)n_cap * 4), o_seg = o_fl + align256((size_t)n_cap), o_tmp = o_seg + align256((size_t)n_cap * 4);
-  LL_CUDA(ctx, ctx->scratch.reserve(o_tmp + tmp_bytes + 256));
-  char* base = ctx->scratch.as<char>();
+  LL_CUDA(ctx, scratch.reserve(o_tmp + tmp_bytes + 256));
+  char* base = scratch.as<char>();
   VgMeta* meta = (VgMeta*)(base + o_meta); int* d_num_seg = (int*)(base + o_meta + sizeof(VgMeta));
   unsigned* k0 = (unsigned*)(base + o_k0); unsigned* k1 = (unsigned*)(base + o_k1); int* v0 = (int*)(base + o_v0); int* v1 = (int*)(base + o_v1);
   unsigned char* flags = (unsigned char*)(base + o_fl); int* seg = (int*)(base + o_seg);
@@ -199,41 +203,62 @@ __global__ void l1_unique_kernel(const double* __restrict__ l1, int M, unsigned 
 // One CTA: k = floor(ratio * n) smallest of uniq[0..n) (distinct non-negative doubles: bit patterns order like the values).
 // Writes uniq_out[0] = that value and *n_out = 1 (the solver kernel then picks element floor(ratio * 1) = 0).
 __global__ void __launch_bounds__(1024) l1_select_kernel(const double* __restrict__ uniq, const int* __restrict__ n_unique, double ratio, double* __restrict__ out, int* __restrict__ n_out) {
-  __shared__ unsigned hist[256];
-  __shared__ unsigned long long s_prefix; __shared__ int s_k;
-  const int n = *n_unique, tid = threadIdx.x;
+  // 11-bit digits from the top; as soon as the bin holding the k-th element has <= 1024 members they are gathered and ranked directly
+  // (the values are distinct), which for a scan's L1 norms happens after two passes.
+  __shared__ unsigned hist[2048];
+  __shared__ unsigned s_warp[32];
+  __shared__ unsigned long long s_prefix, s_mask; __shared__ int s_k, s_m, s_cnt;
+  __shared__ unsigned long long s_list[1024];
+  const int n = *n_unique, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (n <= 0) { if (tid == 0) *n_out = 0; return; }
-  if (tid == 0) { int k = (int)(ratio * (double)n); if (k > n - 1) k = n - 1; s_k = k; s_prefix = 0ull; }
+  if (tid == 0) { int k = (int)(ratio * (double)n); if (k > n - 1) k = n - 1; s_k = k; s_prefix = 0ull; s_mask = 0ull; s_m = n; s_cnt = 0; }
   __syncthreads();
-  for (int pass = 7; pass >= 0; pass--) {
-    if (tid < 256) hist[tid] = 0u;
+  const int shifts[6] = {53, 42, 31, 20, 9, 0};
+  for (int pass = 0; pass < 6 && s_m > 1024; pass++) {
+    const int shift = shifts[pass]; const unsigned dmask = pass == 5 ? 511u : 2047u;
+    hist[tid] = 0u; hist[tid + 1024] = 0u;
     __syncthreads();
-    const unsigned long long prefix = s_prefix; const int shift = pass * 8;
-    const unsigned long long himask = pass == 7 ? 0ull : (~0ull << (shift + 8));
-    for (int i = tid; i < n; i += blockDim.x) {
+    const unsigned long long prefix = s_prefix, himask = s_mask;
+    for (int i = tid; i < n; i += 1024) {
       const unsigned long long key = (unsigned long long)__double_as_longlong(uniq[i]);
-      if ((key & himask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+      if ((key & himask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & dmask], 1u);
     }
     __syncthreads();
-    if (tid < 32) {   // warp 0: bin containing the k-th element = first bin whose inclusive prefix count exceeds k
-      const int k = s_k;
-      unsigned loc[8], run = 0;
+    // bin containing the k-th element: thread t owns bins 2t, 2t+1
+    const unsigned h0 = hist[2 * tid], h1 = hist[2 * tid + 1], run = h0 + h1;
+    unsigned incl = run;
 #pragma unroll
-      for (int j = 0; j < 8; j++) { run += hist[tid * 8 + j]; loc[j] = run; }
-      unsigned incl = run;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) { unsigned w = s_warp[lane], wi = w;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += v; }
-      const unsigned excl = incl - run;
-      const bool mine = (unsigned)k >= excl && (unsigned)k < incl;   // exactly one lane (k < n)
-      if (mine) {
-        int j = 0; while ((unsigned)k >= excl + loc[j]) j++;
-        s_k = k - (int)(excl + (j ? loc[j - 1] : 0u));
-        s_prefix = prefix | ((unsigned long long)(tid * 8 + j) << shift);
-      }
+      for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += v; }
+      s_warp[lane] = wi - w; }
+    __syncthreads();
+    const unsigned excl = s_warp[warp] + incl - run; const unsigned k = (unsigned)s_k;
+    __syncthreads();
+    if (k >= excl && k < excl + run) {   // exactly one thread
+      const int j = (k >= excl + h0) ? 1 : 0;
+      s_k = (int)(k - excl - (j ? h0 : 0u)); s_m = (int)(j ? h1 : h0);
+      s_prefix = prefix | ((unsigned long long)(2 * tid + j) << shift);
+      s_mask = himask | ((unsigned long long)dmask << shift);
     }
     __syncthreads();
   }
-  if (tid == 0) { out[0] = __longlong_as_double((long long)s_prefix); *n_out = 1; }
+  // gather the (<= 1024) members of the selected bin and pick the one with exactly s_k smaller members
+  const unsigned long long prefix = s_prefix, himask = s_mask;
+  for (int i = tid; i < n; i += 1024) {
+    const unsigned long long key = (unsigned long long)__double_as_longlong(uniq[i]);
+    if ((key & himask) == prefix) { const int slot = atomicAdd(&s_cnt, 1); if (slot < 1024) s_list[slot] = key; }
+  }
+  __syncthreads();
+  const int m = min(s_cnt, 1024);
+  if (tid < m) {
+    const unsigned long long mine = s_list[tid]; int rank = 0;
+    for (int q = 0; q < m; q++) rank += (s_list[q] < mine) ? 1 : 0;
+    if (rank == s_k) { out[0] = __longlong_as_double((long long)mine); *n_out = 1; }
+  }
 }
 
 int launch_inlier_select(ll_ctx* ctx, const double* d_l1, int M, double ratio, double* d_sorted, double* d_unique, int* d_n_unique) {

@@ -105,6 +105,7 @@ struct ll_ctx {
   RegDevState* d_reg = nullptr;   // device
   // multi-GPU
   int rank = 0, world = 1;
+  cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; DevBuf scratch2;   // side stream of the per-scan front end
   int reg_deblur = 0;                      // if_motion_deblur of the registration whose blocks are on the device
   int solve_world = 1;                     // world size the solver kernels all-reduce over (1 unless the map in use is sharded)
   void* comm_local = nullptr;              // this rank's staging slot (device memory, IPC-exported)

@@ -125,16 +125,29 @@ __global__ void ex_petal_kernel(const float4* __restrict__ raw, int n, const flo
                                 int* __restrict__ scan_first, int* __restrict__ scan_last, int* __restrict__ meta) {
   const int lane = threadIdx.x;
   __shared__ int s_nsplit, s_ngroup;
-  if (lane == 0) {
-    int ns = 0, n_edge = 0, n_zero = 0; const int nc = *d_num_cand;
-    for (int c = 0; c < nc; c++) {
-      const int idx = cand_idx[c]; const int t = cand[idx];
-      if (t == 1) { if (n_edge == 0 || (idx - split[ns - 1]) > 50) { split[ns++] = idx; n_edge++; } }
-      else if (t == 2) { if (n_zero == 0 || (idx - split[ns - 1]) > 50) { split[ns++] = idx; n_zero++; } }
+  __shared__ int s_c[256];
+  {
+    // lane 0 walks the candidates in order (the hysteresis is sequential), the warp stages them through shared memory 256 at a time
+    // so that the walk does not pay two dependent global loads per candidate.
+    int ns = 0, n_edge = 0, n_zero = 0, last_split = 0; const int nc = *d_num_cand;
+    for (int base = 0; base < nc; base += 256) {
+      for (int k = lane; k < 256 && base + k < nc; k += 32) { const int idx = cand_idx[base + k]; s_c[k] = (idx << 2) | (int)cand[idx]; }
+      __syncwarp();
+      if (lane == 0) {
+        const int m = min(256, nc - base);
+        for (int k = 0; k < m; k++) {
+          const int idx = s_c[k] >> 2, t = s_c[k] & 3;
+          if (t == 1) { if (n_edge == 0 || (idx - last_split) > 50) { split[ns++] = idx; last_split = idx; n_edge++; } }
+          else if (t == 2) { if (n_zero == 0 || (idx - last_split) > 50) { split[ns++] = idx; last_split = idx; n_zero++; } }
+        }
+      }
+      __syncwarp();
     }
-    split[ns++] = n - 1;
-    s_nsplit = ns; meta[0] = ns;
-    if (ns < 6) { meta[1] = 0; meta[2] = 0; } else meta[2] = ns - 1;
+    if (lane == 0) {
+      split[ns++] = n - 1;
+      s_nsplit = ns; meta[0] = ns;
+      if (ns < 6) { meta[1] = 0; meta[2] = 0; } else meta[2] = ns - 1;
+    }
   }
   __syncwarp();
   const int ns = s_nsplit;

@@ -103,6 +103,7 @@ int launch_transform(ll_ctx* ctx, const double* d_pose7, const float4* d_in, int
 struct VoxelTemps { DevBuf* buf; };
 int launch_inlier_select(ll_ctx* ctx, const double* d_l1, int M, double ratio, double* d_sorted, double* d_unique, int* d_n_unique);
 int launch_voxel_grid(ll_ctx* ctx, const float4* d_in, int n_cap, const int* d_n_in, float leaf, float4* d_out, int* d_n_out);
+int launch_voxel_grid_on(ll_ctx* ctx, cudaStream_t s, DevBuf& scratch, const float4* d_in, int n_cap, const int* d_n_in, float leaf, float4* d_out, int* d_n_out);
 
 // ---------------------------------------------------------------------------------------------- extractor (extract.cu)
 int extract_reserve(ll_ctx* ctx, int n);
@@ -114,7 +115,7 @@ int launch_piece_bounds(ll_ctx* ctx, int pieces, float* d_start_end /* 2*pieces 
 // ---------------------------------------------------------------------------------------------- host driver pieces (api.cu)
 struct RegArrays {
   float4* feat; float4* blk_a; double* blk_v; double* l1; double* l1_sorted; double* l1_unique; double* partials;
-  int* n_unique; int* knn_idx; float* knn_d; int* perm; float4* tmp_a; float4* tmp_b; float4* tmp_c; int* counts; float* bounds; double* pose_tmp;
+  int* n_unique; int* knn_idx; float* knn_d; int* perm; float4* tmp_a; float4* tmp_b; float4* tmp_c; float4* tmp_d; int* counts; float* bounds; double* pose_tmp;
   int cap;
 };
 int reg_arrays(ll_ctx* ctx, int M, RegArrays* A);
