@@ -76,6 +76,7 @@ struct ExtractState {
   int* cand_idx = nullptr; int* d_num_cand = nullptr;
   int* split_idx = nullptr;        // [<= n]
   int* scan_first = nullptr; int* scan_last = nullptr;
+  double* d_time = nullptr;        // m_current_time of this scan (device scalar read by ex_point_kernel)
   int* d_meta = nullptr;           // [0]=n_split [1]=n_scans [2]=clutter_size
   double first_receive_time = -1, current_time = 0, last_maximum_time_stamp = 0;
 };
@@ -106,6 +107,9 @@ struct ll_ctx {
   // multi-GPU
   int rank = 0, world = 1;
   cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; DevBuf scratch2;   // side stream of the per-scan front end
+  // The per-scan front end (extract + get_features + 4 VoxelGrids + count read-back) replayed as ONE CUDA graph: ~60 launches whose
+  // enqueue cost on the host (CUB dispatch included) was longer than their execution.  Re-captured when the shape or any buffer changes.
+  struct FrontGraph { cudaGraphExec_t exec = nullptr; size_t n = 0; ll_pipeline_cfg pc; void* bufs[5] = {nullptr}; bool warm = false; uint64_t launches = 0; } fg;
   int reg_deblur = 0;                      // if_motion_deblur of the registration whose blocks are on the device
   int solve_world = 1;                     // world size the solver kernels all-reduce over (1 unless the map in use is sharded)
   void* comm_local = nullptr;              // this rank's staging slot (device memory, IPC-exported)

@@ -22,7 +22,7 @@ static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 #define PUBLIC_MASK 0x3f
 
 struct ExtractParams {
-  int n; float dt; double current_time;
+  int n; float dt; const double* d_current_time;   // device scalar: the value changes per scan, the captured launch does not
   float min_dis_sq, min_sigma, max_edge_polar, thr_corner, thr_surface, min_view_angle;
 };
 
@@ -43,7 +43,7 @@ __global__ void ex_point_kernel(const float4* __restrict__ raw, ExtractParams P,
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P.n) return;
   const float4 p = raw[idx];
-  time_stamp[idx] = (float)(P.current_time + (double)(((float)idx) * P.dt));
+  time_stamp[idx] = (float)(*P.d_current_time + (double)(((float)idx) * P.dt));
   unsigned self = 0; float polar = 0.f, depth = 0.f;
   if (pt_is_nan(p)) self = LL_PT_NAN;
   else if (p.x == 0.f && idx > 0) { self = LL_PT_000; float u, v; projection_of(raw, idx - 1, u, v, polar); }
@@ -248,13 +248,13 @@ int extract_reserve(ll_ctx* ctx, int n) {
   e.polar_dir = (int8_t*)take((size_t)n); e.self_mask = (uint8_t*)take((size_t)n); e.cand = (uint8_t*)take((size_t)n);
   e.cand_idx = (int*)take((size_t)n * 4); e.split_idx = (int*)take((size_t)(n + 1) * 4);
   e.scan_first = (int*)take((size_t)(n + 1) * 4); e.scan_last = (int*)take((size_t)(n + 1) * 4);
-  e.d_num_cand = (int*)take(256); e.d_meta = (int*)take(256);
+  e.d_num_cand = (int*)take(256); e.d_meta = (int*)take(256); e.d_time = (double*)take(256);
   return LL_OK;
 }
 
-int launch_extract(ll_ctx* ctx, int n, double current_time) {
+int launch_extract(ll_ctx* ctx, int n) {
   ExtractState& e = ctx->ex; cudaStream_t s = ctx->stream;
-  ExtractParams P; P.n = n; P.dt = ctx->cfg.time_interval_pts; P.current_time = current_time;
+  ExtractParams P; P.n = n; P.dt = ctx->cfg.time_interval_pts; P.d_current_time = e.d_time;
   P.min_dis_sq = ctx->cfg.livox_min_dis * ctx->cfg.livox_min_dis; P.min_sigma = ctx->cfg.livox_min_sigma;
   P.max_edge_polar = (float)std::pow(std::tan(ctx->cfg.max_fov_deg / 57.3) * 1, 2);
   P.thr_corner = ctx->cfg.corner_curvature; P.thr_surface = ctx->cfg.surface_curvature; P.min_view_angle = ctx->cfg.minimum_view_angle;

@@ -107,7 +107,7 @@ int launch_voxel_grid_on(ll_ctx* ctx, cudaStream_t s, DevBuf& scratch, const flo
 
 // ---------------------------------------------------------------------------------------------- extractor (extract.cu)
 int extract_reserve(ll_ctx* ctx, int n);
-int launch_extract(ll_ctx* ctx, int n, double current_time);
+int launch_extract(ll_ctx* ctx, int n);   // current_time is read from ctx->ex.d_time
 int launch_get_features(ll_ctx* ctx, const float* d_bounds /*min_blur,max_blur on device*/, float min_blur, float max_blur,
                         float4* d_corners, float4* d_surf, float4* d_full, int* d_counts /*3*/);
 int launch_piece_bounds(ll_ctx* ctx, int pieces, float* d_start_end /* 2*pieces */);
