@@ -60,6 +60,7 @@ int ll_ctx_create(const ll_config* cfg, int device, ll_ctx** out) {
   cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_it[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_it[1], cudaEventDisableTiming);
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2); cudaEventCreate(&ctx->ev3);
   for (int i = 0; i < 5 * 16 + 2; i++) cudaEventCreate(&ctx->evp[i]);
   ctx->pinned_cap = 1 << 16; cudaHostAlloc(&ctx->pinned, ctx->pinned_cap, cudaHostAllocDefault);
@@ -328,7 +329,7 @@ static SolveArgs solve_args(ll_ctx* ctx, const RegArrays& A, int M, int mode, in
   SolveArgs s; s.st = ctx->d_reg; s.feat = A.feat; s.blk_a = A.blk_a; s.blk_v = A.blk_v; s.l1 = A.l1; s.l1_sorted_unique = A.l1_unique; s.d_n_unique = A.n_unique;
   s.partials = A.partials; s.M = M; s.max_iterations = max_iter; s.mode = mode; s.rank = ctx->rank; s.world = ctx->solve_world; s.comm_local = (double*)ctx->comm_local;
   for (int i = 0; i < 8; i++) s.comm_peer[i] = (double*)ctx->comm_peers[i];
-  s.deblur = ctx->reg_deblur;
+  s.deblur = ctx->reg_deblur; s.prerun_iterations = 0; s.table = nullptr; s.table_mask = 0; s.uniq = nullptr; s.n_uniq = nullptr;
   return s;
 }
 
@@ -362,29 +363,53 @@ int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, 
   if (sharded && (map->world != ctx->world || map->rank != ctx->rank)) { ctx->set_error("map shard and context disagree on rank/world"); return LL_ERR_INVALID; }
   if (sharded && M > ctx->cfg.max_features) { ctx->set_error("more features than max_features (exchange buffer)"); return LL_ERR_CAPACITY; }
   double* x_l1 = sharded ? (double*)((char*)ctx->comm_local + LL_COMM_X_OFF) : nullptr;
-  for (iter = 0; iter < in->icp_max_iterations; iter++) {
-    cudaEvent_t* e = iter < 16 ? &ctx->evp[5 * iter] : nullptr;
+  unsigned set_cap = 1024; while (set_cap < (unsigned)(2 * M)) set_cap <<= 1;   // hash set of the L1 norms (K10)
+  LL_CUDA(ctx, ctx->scratch.reserve((size_t)set_cap * 8 + 256));
+  // One ICP iteration's device work + a snapshot of the 1.7 KB state into pinned slot `it & 1`.
+  RegDevState* slots[2] = {hs, (RegDevState*)((char*)hs + align256(sizeof(RegDevState)))};
+  auto enqueue_iteration = [&](int it) -> int {
+    cudaEvent_t* e = it < 16 ? &ctx->evp[5 * it] : nullptr;
     LL_CUDA(ctx, cudaMemsetAsync(&ctx->d_reg->corner_avail, 0, 2 * sizeof(int), s));
     if (sharded) LL_CUDA(ctx, cudaMemsetAsync(x_l1, 0xff, (size_t)M * sizeof(double), s));   // NaN = nobody owns a block here (peers fill it after solve #1)
-    if (iter == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    if (it == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     if (e) LL_CUDA(ctx, cudaEventRecord(e[0], s));
     LL_TRY(launch_knn_blocks(ctx, ka));
     if (e) LL_CUDA(ctx, cudaEventRecord(e[1], s));
-    if (iter == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev2, s));
-    LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 0, in->cere_prerun_times)));
-    if (e) LL_CUDA(ctx, cudaEventRecord(e[2], s));
-    if (sharded) LL_TRY(launch_l1_exchange(ctx, A.l1, M));
-    LL_TRY(launch_inlier_select(ctx, sharded ? x_l1 : A.l1, M, in->inlier_ratio, A.l1_sorted, A.l1_unique, A.n_unique));
-    if (e) LL_CUDA(ctx, cudaEventRecord(e[3], s));
-    LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 1, in->cere_max_iterations)));
+    if (it == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev2, s));
+    if (!sharded) {
+      // one launch: solve #1 -> L1 norms -> de-duplication + order statistic -> outlier drop -> solve #2 -> pose (lm_solve_kernel, mode 4)
+      SolveArgs sa = solve_args(ctx, A, M, 4, in->cere_max_iterations);
+      sa.prerun_iterations = in->cere_prerun_times; sa.table = (unsigned long long*)ctx->scratch.p; sa.table_mask = set_cap - 1;
+      sa.n_uniq = (int*)A.l1_sorted; sa.uniq = A.l1_sorted + 2;
+      if (e) { LL_CUDA(ctx, cudaEventRecord(e[2], s)); LL_CUDA(ctx, cudaEventRecord(e[3], s)); }
+      LL_TRY(launch_solve(ctx, sa));
+    } else {
+      LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 0, in->cere_prerun_times)));
+      if (e) LL_CUDA(ctx, cudaEventRecord(e[2], s));
+      LL_TRY(launch_l1_exchange(ctx, A.l1, M));
+      LL_TRY(launch_inlier_select(ctx, x_l1, M, in->inlier_ratio, A.l1_sorted, A.l1_unique, A.n_unique));
+      if (e) LL_CUDA(ctx, cudaEventRecord(e[3], s));
+      LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 1, in->cere_max_iterations)));
+    }
     if (e) LL_CUDA(ctx, cudaEventRecord(e[4], s));
-    LL_CUDA(ctx, cudaMemcpyAsync(hs, ctx->d_reg, sizeof(RegDevState), cudaMemcpyDeviceToHost, s));
-    LL_CUDA(ctx, cudaStreamSynchronize(s));
+    LL_CUDA(ctx, cudaMemcpyAsync(slots[it & 1], ctx->d_reg, sizeof(RegDevState), cudaMemcpyDeviceToHost, s));
+    LL_CUDA(ctx, cudaEventRecord(ctx->ev_it[it & 1], s));
+    return LL_OK;
+  };
+  // The host stays one iteration ahead: iteration k+1 is enqueued before iteration k's state is read back, so the GPU never waits for the
+  // PCIe round trip of the termination test.  The kernels of an iteration enqueued after the loop has ended return at once (st->icp_done).
+  const bool speculate = !sharded;
+  LL_TRY(enqueue_iteration(0));
+  for (iter = 0; iter < in->icp_max_iterations; iter++) {
+    if (speculate && iter + 1 < in->icp_max_iterations) LL_TRY(enqueue_iteration(iter + 1));
+    LL_CUDA(ctx, cudaEventSynchronize(ctx->ev_it[iter & 1]));
+    hs = slots[iter & 1];
     if (hs->lm.termination == -1) { ctx->set_error("no residual block survived the gates / inlier selection"); return LL_ERR_NO_BLOCKS; }
     if (iter == 0 && (hs->corner_avail + (in->icp_plane ? hs->surf_avail : 0)) > in->maximum_allow_residual_block) {
       ctx->set_error("residual blocks exceed maximum_allow_residual_block (reference would drop blocks at random)"); return LL_ERR_CAP_BINDS;
     }
     if (hs->icp_done) break;
+    if (!speculate && iter + 1 < in->icp_max_iterations) LL_TRY(enqueue_iteration(iter + 1));
   }
   LL_CUDA(ctx, cudaEventRecord(ctx->ev3, s));
   LL_CUDA(ctx, cudaEventSynchronize(ctx->ev3));
@@ -486,10 +511,10 @@ int ll_solve(ll_ctx* ctx, int max_iterations, double x_io[7], double* initial_co
 }
 
 // Diagnostics: the master CTA's cycle counters of the last registration (kernels.cuh: RegDevState::prof).
-int ll_debug_solver_cycles(ll_ctx* ctx, long long out8[8]) {
+int ll_debug_solver_cycles(ll_ctx* ctx, long long out8[16]) {
   if (!ctx || !out8) return LL_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  LL_CUDA(ctx, cudaMemcpyAsync(out8, ctx->d_reg->prof, 8 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  LL_CUDA(ctx, cudaMemcpyAsync(out8, ctx->d_reg->prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return LL_OK;
 }

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "exact_math.cuh"
+#include "select.cuh"
 
 #define FULL 0xffffffffu
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -185,80 +186,18 @@ int launch_voxel_grid_on(ll_ctx* ctx, cudaStream_t s, DevBuf& scratch, const flo
 // De-duplication = one pass through a global-memory hash set (atomicCAS on the 64-bit patterns; duplicates are rare but must
 // not be counted), which also compacts the distinct values; the order statistic = an 8-pass byte-wise radix select by one CTA.
 // Exact, and ~6x cheaper than sort + unique for the few 10^4 blocks of a scan.
-#define L1_EMPTY 0xffffffffffffffffull
 __global__ void l1_unique_kernel(const double* __restrict__ l1, int M, unsigned long long* __restrict__ table, unsigned table_mask, double* __restrict__ uniq, int* __restrict__ n_unique) {
+  __shared__ int s_scratch[34];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M) return;
-  const double v = l1[i];
-  if (!(v < INFINITY)) return;   // invalid slot (+inf) or NaN
-  const unsigned long long key = (unsigned long long)__double_as_longlong(v == 0.0 ? 0.0 : v);   // -0.0 == 0.0 in a std::set
-  unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) & table_mask;
-  for (;;) {
-    const unsigned long long prev = atomicCAS(&table[h], L1_EMPTY, key);
-    if (prev == L1_EMPTY) { uniq[atomicAdd(n_unique, 1)] = v; return; }
-    if (prev == key) return;
-    h = (h + 1) & table_mask;
-  }
+  l1_set_insert(table, table_mask, uniq, n_unique, i < M ? l1[i] : INFINITY, i < M, s_scratch);
 }
-// One CTA: k = floor(ratio * n) smallest of uniq[0..n) (distinct non-negative doubles: bit patterns order like the values).
-// Writes uniq_out[0] = that value and *n_out = 1 (the solver kernel then picks element floor(ratio * 1) = 0).
+// One CTA: writes out[0] = the order statistic and *n_out = 1 (the solver kernel then picks element floor(ratio * 1) = 0).
 __global__ void __launch_bounds__(1024) l1_select_kernel(const double* __restrict__ uniq, const int* __restrict__ n_unique, double ratio, double* __restrict__ out, int* __restrict__ n_out) {
-  // 11-bit digits from the top; as soon as the bin holding the k-th element has <= 1024 members they are gathered and ranked directly
-  // (the values are distinct), which for a scan's L1 norms happens after two passes.
-  __shared__ unsigned hist[2048];
-  __shared__ unsigned s_warp[32];
-  __shared__ unsigned long long s_prefix, s_mask; __shared__ int s_k, s_m, s_cnt;
-  __shared__ unsigned long long s_list[1024];
-  const int n = *n_unique, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (n <= 0) { if (tid == 0) *n_out = 0; return; }
-  if (tid == 0) { int k = (int)(ratio * (double)n); if (k > n - 1) k = n - 1; s_k = k; s_prefix = 0ull; s_mask = 0ull; s_m = n; s_cnt = 0; }
-  __syncthreads();
-  const int shifts[6] = {53, 42, 31, 20, 9, 0};
-  for (int pass = 0; pass < 6 && s_m > 1024; pass++) {
-    const int shift = shifts[pass]; const unsigned dmask = pass == 5 ? 511u : 2047u;
-    hist[tid] = 0u; hist[tid + 1024] = 0u;
-    __syncthreads();
-    const unsigned long long prefix = s_prefix, himask = s_mask;
-    for (int i = tid; i < n; i += 1024) {
-      const unsigned long long key = (unsigned long long)__double_as_longlong(uniq[i]);
-      if ((key & himask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & dmask], 1u);
-    }
-    __syncthreads();
-    // bin containing the k-th element: thread t owns bins 2t, 2t+1
-    const unsigned h0 = hist[2 * tid], h1 = hist[2 * tid + 1], run = h0 + h1;
-    unsigned incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) { unsigned w = s_warp[lane], wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += v; }
-      s_warp[lane] = wi - w; }
-    __syncthreads();
-    const unsigned excl = s_warp[warp] + incl - run; const unsigned k = (unsigned)s_k;
-    __syncthreads();
-    if (k >= excl && k < excl + run) {   // exactly one thread
-      const int j = (k >= excl + h0) ? 1 : 0;
-      s_k = (int)(k - excl - (j ? h0 : 0u)); s_m = (int)(j ? h1 : h0);
-      s_prefix = prefix | ((unsigned long long)(2 * tid + j) << shift);
-      s_mask = himask | ((unsigned long long)dmask << shift);
-    }
-    __syncthreads();
-  }
-  // gather the (<= 1024) members of the selected bin and pick the one with exactly s_k smaller members
-  const unsigned long long prefix = s_prefix, himask = s_mask;
-  for (int i = tid; i < n; i += 1024) {
-    const unsigned long long key = (unsigned long long)__double_as_longlong(uniq[i]);
-    if ((key & himask) == prefix) { const int slot = atomicAdd(&s_cnt, 1); if (slot < 1024) s_list[slot] = key; }
-  }
-  __syncthreads();
-  const int m = min(s_cnt, 1024);
-  if (tid < m) {
-    const unsigned long long mine = s_list[tid]; int rank = 0;
-    for (int q = 0; q < m; q++) rank += (s_list[q] < mine) ? 1 : 0;
-    if (rank == s_k) { out[0] = __longlong_as_double((long long)mine); *n_out = 1; }
-  }
+  __shared__ SelectSmem S;
+  const int n = *n_unique;
+  if (n <= 0) { if (threadIdx.x == 0) *n_out = 0; return; }
+  const double v = block_select<1024>(uniq, n, ratio, S);
+  if (threadIdx.x == 0) { out[0] = v; *n_out = 1; }
 }
 
 int launch_inlier_select(ll_ctx* ctx, const double* d_l1, int M, double ratio, double* d_sorted, double* d_unique, int* d_n_unique) {

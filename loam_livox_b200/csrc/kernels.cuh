@@ -62,7 +62,7 @@ struct RegDevState {
   // motion deblur (N1): time-stamp range of refine_blur, and compute_interpolatation_rodrigue's outputs (:607-620) after every solve #2
   double min_ts, max_ts, interp_theta, interp_hat[9], interp_hat_sq[9];
   unsigned int bar_count, bar_gen;
-  long long prof[8];   // master-CTA cycle counters of the solver: eval, wait, grid reduce, lm_step, publish, #evaluations, staging, epilogue
+  long long prof[16];  // [8..12]: fused K10 section: L1 + insert, barrier, select, barrier, drop   // master-CTA cycle counters of the solver: eval, wait, grid reduce, lm_step, publish, #evaluations, staging, epilogue
   LmState lm;
 };
 
@@ -77,10 +77,12 @@ struct SolveArgs {
   double* partials;          // [grid x 32]
   int M;
   int max_iterations;
-  int mode;                  // 0: solve #1 (write l1 at the end) ; 1: solve #2 (apply threshold first, compose pose at the end) ;
+  int mode;                  // 4: fused (see below) ; 0: solve #1 (write l1 at the end) ; 1: solve #2 (apply threshold first, compose pose at the end) ;
                              // 2: plain solve (parity hook) ; 3: evaluate once at st->x (parity hook, writes sums to st->lm.H/g/x_cost)
   // multi-GPU
   int rank, world; double* comm_local; double* comm_peer[8];
+  // mode 4 (one launch per ICP iteration: solve #1 -> K10 -> solve #2)
+  int prerun_iterations; unsigned long long* table; unsigned table_mask; double* uniq; int* n_uniq;
   int deblur;                // 1: *_mb functors (ceres_icp.hpp:81-233), s per block from the feature's time stamp
 };
 // Layout of the IPC-exported staging buffer of a rank (ll_comm_local_handle):

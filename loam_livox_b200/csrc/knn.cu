@@ -451,6 +451,7 @@ __device__ __forceinline__ void emit_block(const KnnBlocksArgs& a, const TreeVie
 // Writes one residual-block slot per feature (indexed by the ORIGINAL feature order): blk_a[slot] = (a.x, a.y, a.z, type) with
 // type 0 invalid / 1 line / 2 plane, blk_v[slot*3..] = unit line direction or (un-normalised) plane normal, in fp64.
 __global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a) {
+  if (a.st->icp_done) return;   // launched ahead of the termination test by the host: the ICP loop has already ended
   __shared__ GroupStack stacks[GROUPS_PER_CTA];
   const int j = blockIdx.x * GROUPS_PER_CTA + (threadIdx.x / GROUP);
   const int gl = threadIdx.x & (GROUP - 1);

@@ -13,9 +13,11 @@
 // a ticket barrier, and the LAST CTA to arrive reduces the partials in fixed order (run-to-run deterministic), runs the
 // trust-region logic on one thread and publishes the next trial point.  No host round trip inside a solve.
 #include <cfloat>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.cuh"
 #include "exact_math.cuh"
+#include "select.cuh"
 
 #define FULL 0xffffffffu
 #define NSUM 29          // 21 JtJ (upper, row-major) + 6 Jtr + cost + valid-block count
@@ -341,17 +343,22 @@ __device__ __forceinline__ double huber_weight(double sq, double a, double b, do
   rho0 = sq; return 1.0;
 }
 
-__device__ void setup_const(EvalConst& E, const double* x, const RegDevState* st) {
+// Per solve: everything that depends on the last pose and the loss only.
+__device__ void setup_static(EvalConst& E, const RegDevState* st) {
+  const double* ql = st->pose_last;
+  for (int k = 0; k < 3; k++) { double e[3] = {k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0}, o[3]; d_qrot(ql, e, o); E.Rl[0][k] = o[0]; E.Rl[1][k] = o[1]; E.Rl[2][k] = o[2]; }
+  E.tl[0] = st->pose_last[4]; E.tl[1] = st->pose_last[5]; E.tl[2] = st->pose_last[6];
+  E.huber_a = st->huber_a; E.huber_b = st->huber_a * st->huber_a;
+}
+// Per evaluation (on every CTA's critical path): the trial point, the parameterisation Jacobian and, for the *_mb functors only, the slerp terms.
+template <bool MB>
+__device__ __forceinline__ void setup_trial(EvalConst& E, const double* x) {
   for (int k = 0; k < 7; k++) E.x[k] = x[k];
   E.PJ[0][0] = x[3];  E.PJ[0][1] = x[2];  E.PJ[0][2] = -x[1];
   E.PJ[1][0] = -x[2]; E.PJ[1][1] = x[3];  E.PJ[1][2] = x[0];
   E.PJ[2][0] = x[1];  E.PJ[2][1] = -x[0]; E.PJ[2][2] = x[3];
   E.PJ[3][0] = -x[0]; E.PJ[3][1] = -x[1]; E.PJ[3][2] = -x[2];
-  const double* ql = st->pose_last;
-  for (int k = 0; k < 3; k++) { double e[3] = {k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0}, o[3]; d_qrot(ql, e, o); E.Rl[0][k] = o[0]; E.Rl[1][k] = o[1]; E.Rl[2][k] = o[2]; }
-  E.tl[0] = st->pose_last[4]; E.tl[1] = st->pose_last[5]; E.tl[2] = st->pose_last[6];
-  E.huber_a = st->huber_a; E.huber_b = st->huber_a * st->huber_a;
-  { const double d = x[3], ad = fabs(d);
+  if (MB) { const double d = x[3], ad = fabs(d);
     if (ad >= 1.0 - 2.220446049250313e-16) { E.sl_lerp = 1; E.sl_theta = 0; E.sl_sin = 1; E.sl_cos = 1; E.sl_dth_dw = 0; }
     else { E.sl_lerp = 0; E.sl_theta = acos(ad); E.sl_sin = sin(E.sl_theta); E.sl_cos = cos(E.sl_theta); E.sl_dth_dw = -(d < 0.0 ? -1.0 : 1.0) / sqrt(1.0 - ad * ad); } }
 }
@@ -426,6 +433,19 @@ __device__ __forceinline__ SmemSlots carve(unsigned char* base, int cap, bool mb
 #define SLOT_BYTES 64
 #define SLOT_BYTES_MB 56
 
+// Plain grid barrier on the same counter / generation pair the evaluation loop uses (cooperative launch: all CTAs are resident).
+__device__ __forceinline__ void grid_barrier(RegDevState* st, unsigned& gen, bool master, int tid) {
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(&st->bar_count, 1u);
+    if (master) { while (ld_acquire_u32(&st->bar_count) != gridDim.x) {} st->bar_count = 0; __threadfence(); st_release_u32(&st->bar_gen, gen + 1); }
+    else { while (ld_acquire_u32(&st->bar_gen) != gen + 1) {} }
+  }
+  gen++;
+  __syncthreads();
+}
+
 template <bool MB>
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a, int tiles_per_cta, int tile) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -434,12 +454,23 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
   __shared__ double s_sum[32];
   __shared__ int s_flag;
   __shared__ LmState s_lm;   // used by CTA 0 only: the solver state never leaves the chip during a solve
+  __shared__ SelectSmem s_sel;   // mode 4 (fused) only
   RegDevState* st = a.st;
+  if ((a.mode == 4 || a.mode <= 1) && *((volatile int*)&st->icp_done)) return;   // speculative launch after the ICP loop ended (uniform over the grid)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cap = tiles_per_cta * SOLVE_THREADS;
   const SmemSlots S = carve(s_dyn, cap, MB);
 
   const long long t_k0 = clock64();
+  // mode 4 = one whole ICP iteration's solver work in ONE launch: solve #1 (prerun iterations) -> L1 norms -> std::set de-duplication + order
+  // statistic (K10) -> drop outliers from the staged blocks -> solve #2 -> pose.  The hash set is cleared here; the first evaluation barrier
+  // orders the clear before any insert.
+  const bool fused = a.mode == 4;
+  int cur_mode = fused ? 0 : a.mode;
+  if (fused) {
+    for (unsigned idx = blockIdx.x * SOLVE_THREADS + threadIdx.x; idx <= a.table_mask; idx += gridDim.x * SOLVE_THREADS) a.table[idx] = L1_EMPTY;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.n_uniq = 0;
+  }
   // ---- stage this CTA's residual blocks
   double thr = 0;
   if (a.mode == 1) {   // K10 tail: threshold = max(inliner_dis, element floor(ratio * n_unique) of the sorted unique L1 norms)
@@ -477,22 +508,24 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
   // Every CTA computes the same value; CTA 0 (the master) owns the solver state in its shared memory for the whole solve.
   unsigned gen = ld_acquire_u32(&st->bar_gen);
   const bool master = blockIdx.x == 0;
+  for (int ph = 0; ph < (fused ? 2 : 1); ph++) {
   if (tid == 0) {
     double x0[7], z[6] = {0, 0, 0, 0, 0, 0}, tr[7];
-    for (int k = 0; k < 7; k++) x0[k] = st->x[k];
+    for (int k = 0; k < 7; k++) x0[k] = ((const volatile double*)st->x)[k];   // phase 2 of the fused mode starts from the master's result
     d_plus(x0, z, st->bound, tr);
-    setup_const(E, tr, st);
+    if (ph == 0) setup_static(E, st);
+    setup_trial<MB>(E, tr);
     s_flag = 0;
     if (master) {
       LmState& L = s_lm;
-      L.phase = 0; L.iteration = 0; L.max_iterations = a.max_iterations; L.num_invalid = 0; L.done = 0; L.termination = 0; L.last_successful = 1; L.reuse_diagonal = 0;
+      L.phase = 0; L.iteration = 0; L.max_iterations = (fused && ph == 0) ? a.prerun_iterations : a.max_iterations; L.num_invalid = 0; L.done = 0; L.termination = 0; L.last_successful = 1; L.reuse_diagonal = 0;
       L.ls_iters = 0; L.n_valid = 0; L.total_iterations = 0; L.total_evaluations = 0;
       for (int k = 0; k < 7; k++) L.trial[k] = tr[k];
     }
   }
   __syncthreads();
 
-  if (master && tid == 0) st->prof[6] += clock64() - t_k0;
+  if (master && tid == 0 && ph == 0) st->prof[6] += clock64() - t_k0;
   for (;;) {
     const long long t_e0 = clock64();
     // ---- evaluate: r, J, Huber, 29 partial sums per thread
@@ -582,7 +615,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
       if (tid == 0) {
         t_e3 = clock64();
         LmState& L = s_lm;
-        if (a.mode == 3) { for (int i = 0; i < 21; i++) L.H[i] = s_sum[i]; for (int i = 0; i < 6; i++) L.g[i] = s_sum[21 + i]; L.x_cost = s_sum[27]; L.n_valid = (int)(s_sum[28] + 0.5); L.done = 1; }
+        if (cur_mode == 3) { for (int i = 0; i < 21; i++) L.H[i] = s_sum[i]; for (int i = 0; i < 6; i++) L.g[i] = s_sum[21 + i]; L.x_cost = s_sum[27]; L.n_valid = (int)(s_sum[28] + 0.5); L.done = 1; }
         else lm_step(L, s_sum, st->bound);
         const long long t_e4 = clock64();
         // publish the next trial point (or the result)
@@ -590,11 +623,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
         if (!L.done) { for (int k = 0; k < 7; k++) st->lm.trial[k] = L.trial[k]; }
         else {
           st->lm = L;   // whole solver state (parity hooks / host diagnostics read it)
-          if (a.mode != 3) {
+          if (cur_mode != 3) {
             for (int k = 0; k < 7; k++) st->x[k] = L.x_best[k];
             st->total_lm_iterations += L.iteration; st->total_evaluations += L.total_evaluations;
           }
-          if (a.mode == 1) {   // :514-531 pose composition + ICP termination test
+          if (cur_mode == 1) {   // :514-531 pose composition + ICP termination test
             double qi[4] = {L.x_best[3], L.x_best[0], L.x_best[1], L.x_best[2]}, ti[3] = {L.x_best[4], L.x_best[5], L.x_best[6]};
             const double* ql = st->pose_last; double tcur[3], qcur[4];
             d_qrot(ql, ti, tcur); for (int k = 0; k < 3; k++) tcur[k] += st->pose_last[4 + k];
@@ -612,6 +645,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
               for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double t = 0; for (int k = 0; k < 3; k++) t += H[i * 3 + k] * H[k * 3 + j]; st->interp_hat_sq[i * 3 + j] = t; }
               st->interp_theta = ang;
             }
+            if (L.termination == -1) st->icp_done = 1;   // no residual block: the host reports the error; iterations launched ahead must not run
             st->final_cost = L.final_cost; st->initial_cost = L.initial_cost; st->num_residual_blocks = L.n_valid;
             double dt = 0; for (int k = 0; k < 3; k++) dt += (st->t_last_opt[k] - ti[k]) * (st->t_last_opt[k] - ti[k]);
             if (d_angdist(st->q_last_opt, qi) < 57.3 * st->min_icp_R && sqrt(dt) < st->min_icp_T) st->icp_done = 1;
@@ -635,16 +669,17 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
       double tr[7];
       if (L->done) for (int k = 0; k < 7; k++) tr[k] = ((const volatile double*)st->x)[k];
       else for (int k = 0; k < 7; k++) tr[k] = L->trial[k];
-      setup_const(E, tr, st);
+      setup_trial<MB>(E, tr);
     }
     __syncthreads();
     if (s_flag) break;
   }
   // ---- epilogue of solve #1: loss-corrected L1 norm of every block at the solution (problem.Evaluate, :476-481)
   const long long t_p0 = clock64();
-  if (a.mode == 0) {
+  if (cur_mode == 0) {
     for (int k = 0; k < tiles_per_cta; k++) {
       const int i = (blockIdx.x + gridDim.x * k) * tile + tid, li = k * SOLVE_THREADS + tid;
+      double my_l1 = INFINITY;
       if (i < a.M && tid < tile) {
         double l1 = INFINITY;
         Slot s; s.type = S.type[li];
@@ -668,10 +703,35 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
           l1 = fabs(sc * r[0]) + fabs(sc * r[1]) + fabs(sc * r[2]);
         }
         a.l1[i] = l1;
+        if (fused) my_l1 = l1;
       }
+      if (fused) l1_set_insert(a.table, a.table_mask, a.uniq, a.n_uniq, my_l1, my_l1 < INFINITY, (int*)s_sel.warp_sum);   // CTA-collective: every thread calls it
     }
   }
+  if (fused && ph == 0) {
+    const long long q0 = clock64();
+    grid_barrier(st, gen, master, tid);                      // every rank's distinct L1 norms are in uniq[0 .. *n_uniq)
+    const long long q1 = clock64();
+    if (master) {
+      const int nu = *((volatile int*)a.n_uniq);
+      double rt = 0.0;
+      if (nu > 0) rt = block_select<SOLVE_THREADS>(a.uniq, nu, st->inlier_ratio, s_sel);
+      if (tid == 0) { st->inlier_threshold = fmax(st->inliner_dis, rt); st->n_unique = nu; }   // :484-485
+    }
+    const long long q2 = clock64();
+    grid_barrier(st, gen, master, tid);
+    const long long q3 = clock64();
+    const double thr2 = *((volatile double*)&st->inlier_threshold);
+    for (int k = 0; k < tiles_per_cta; k++) {                // :487-499: blocks above the threshold leave the problem
+      const int i = (blockIdx.x + gridDim.x * k) * tile + tid, li = k * SOLVE_THREADS + tid;
+      if (i < a.M && tid < tile && S.type[li] != 0 && a.l1[i] > thr2) S.type[li] = 0;
+    }
+    cur_mode = 1;
+    __syncthreads();
+    if (master && tid == 0) { const long long q4 = clock64(); st->prof[8] += q0 - t_p0; st->prof[9] += q1 - q0; st->prof[10] += q2 - q1; st->prof[11] += q3 - q2; st->prof[12] += q4 - q3; }
+  }
   if (master && tid == 0) st->prof[7] += clock64() - t_p0;
+  }   // phase
 }
 
 #define SOLVE_MAX_SMEM (200 * 1024)
@@ -695,7 +755,7 @@ int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
     attr_set[ctx->device][mb] = true;
   }
   SolveArgs args = a; void* kargs[] = {&args, &tiles_per_cta, &tile};
-  LL_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SOLVE_THREADS), kargs, smem, ctx->stream));
+  LL_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SOLVE_THREADS), kargs, smem, ctx->stream));   // (an ordinary launch is not faster: measured)
   ctx->launches++;
   return LL_OK;
 }
