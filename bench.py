@@ -257,7 +257,7 @@ def run_gpu(args):
                        "map_index_build_ms": t_index * 1e3},
             "ms_per_icp_iter": float(np.sum(reg_ms) / max(1, np.sum(icp_iters))), "icp_iterations_mean": float(np.mean(icp_iters)),
             "clocks": clocks,
-            "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": N_SCAN * 16, "d2h_bytes_per_step": int(np.mean(icp_iters) + 1) * 1400,
+            "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": N_SCAN * 16, "d2h_bytes_per_step": int(round((np.mean(icp_iters) + 1) * ctx._lib.ll_state_snapshot_bytes() + 44)),
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "knn_blocks_kernel (transform + exact 5-NN + residual blocks), first ICP iteration of each step (cold L2)",

@@ -226,6 +226,8 @@ void ll_mapper_release(ll_mapper* mapper);
 int  ll_mapper_process_scan(ll_mapper* mapper, const void* raw, size_t n, int fmt, int where, double stamp, ll_reg_result* out, ll_mapper_stats* stats);
 int  ll_mapper_pose(const ll_mapper* mapper, double q_wxyz[4], double t[3], int* frame_index);
 
+/* Size of the registration-state snapshot copied to the host once per ICP iteration (for traffic accounting). */
+int  ll_state_snapshot_bytes(void);
 /* Diagnostics: cycle counters of the solver's master CTA over the last registration: eval, wait-for-slowest-CTA, grid reduce, lm_step, publish, #evaluations, staging, epilogue. */
 int  ll_debug_solver_cycles(ll_ctx* ctx, long long out16[16]);   /* [8..12]: fused K10 section: L1 + insert, barrier, select, barrier, drop */
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "ll_map_build_sharded", "ll_knn", "ll_reg_state_default", "ll_register", "ll_build_blocks", "ll_normal_equations", "ll_solve", "ll_transform",
     "ll_scan_to_pose", "ll_comm_local_handle", "ll_comm_connect", "ll_launch_count", "ll_cellmap_create", "ll_cellmap_release", "ll_cellmap_append",
     "ll_cellmap_assemble", "ll_cellmap_stats", "ll_voxel_downsample_dev", "ll_transform_dev", "ll_last_features_dev", "ll_mapper_config_default", "ll_mapper_create", "ll_mapper_release",
-    "ll_mapper_process_scan", "ll_mapper_pose", "ll_map_rebuild", "ll_debug_solver_cycles",
+    "ll_mapper_process_scan", "ll_mapper_pose", "ll_map_rebuild", "ll_debug_solver_cycles", "ll_state_snapshot_bytes",
 ]
 
 
@@ -123,6 +123,7 @@ def lib():
     L.ll_transform_dev.argtypes = [vp, vp, vp, vp, sz, vp]
     L.ll_last_features_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
     L.ll_debug_solver_cycles.argtypes = [vp, vp]
+    L.ll_state_snapshot_bytes.argtypes = []
     L.ll_map_rebuild.argtypes = [vp, vp, vp, sz, vp, sz, ci, ci]
     L.ll_mapper_config_default.argtypes = [C.POINTER(MapperConfig)]
     L.ll_mapper_create.argtypes = [vp, C.POINTER(MapperConfig), C.POINTER(vp)]

@@ -510,6 +510,8 @@ int ll_solve(ll_ctx* ctx, int max_iterations, double x_io[7], double* initial_co
   return LL_OK;
 }
 
+// Bytes read back per ICP iteration (the device-side registration state snapshot): what bench.py counts as d2h traffic.
+int ll_state_snapshot_bytes(void) { return (int)sizeof(RegDevState); }
 // Diagnostics: the master CTA's cycle counters of the last registration (kernels.cuh: RegDevState::prof).
 int ll_debug_solver_cycles(ll_ctx* ctx, long long out8[16]) {
   if (!ctx || !out8) return LL_ERR_INVALID;

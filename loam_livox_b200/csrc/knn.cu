@@ -369,7 +369,7 @@ __device__ __forceinline__ unsigned cell_owner(float x, float y, float z, float 
   return h % (unsigned)world;
 }
 
-// Spatial sort key of a feature at the current pose: class bit (corner/surface) | 30-bit Hilbert index inside the tree's box.
+// Spatial sort key of a feature at the current pose: class bit (corner/surface) | 21-bit Hilbert index (7 bits per axis) inside the tree's box.
 // Neighbouring queries then sit in the same warp / CTA, walk the same tree nodes and buckets, and hit them in L1.
 __global__ void query_key_kernel(KnnBlocksArgs a, unsigned* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,21 +383,21 @@ __global__ void query_key_kernel(KnnBlocksArgs a, unsigned* __restrict__ keys, i
   const float ext = fmaxf(fmaxf(bb[3] - bb[0], bb[4] - bb[1]), bb[5] - bb[2]);
   unsigned X[3]; bool ok = true;
 #pragma unroll
-  for (int k = 0; k < 3; k++) { if (!isfinite(c[k])) ok = false; float u = ext > 0.f ? (c[k] - bb[k]) / ext : 0.f; u = fminf(fmaxf(u, 0.f), 1.f); X[k] = (unsigned)fminf(u * 1024.0f, 1023.0f); }
-  for (unsigned Q = 1u << 9; Q > 1; Q >>= 1) {
+  for (int k = 0; k < 3; k++) { if (!isfinite(c[k])) ok = false; float u = ext > 0.f ? (c[k] - bb[k]) / ext : 0.f; u = fminf(fmaxf(u, 0.f), 1.f); X[k] = (unsigned)fminf(u * 128.0f, 127.0f); }   // 7 bits per axis: 21-bit curve + class bit = 3 radix passes, and tiles of ~0.3 m are fine enough
+  for (unsigned Q = 1u << 6; Q > 1; Q >>= 1) {
     const unsigned P = Q - 1;
 #pragma unroll
     for (int k = 0; k < 3; k++) { if (X[k] & Q) X[0] ^= P; else { unsigned tt = (X[0] ^ X[k]) & P; X[0] ^= tt; X[k] ^= tt; } }
   }
   X[1] ^= X[0]; X[2] ^= X[1];
   unsigned tt = 0;
-  for (unsigned Q = 1u << 9; Q > 1; Q >>= 1) if (X[2] & Q) tt ^= Q - 1;
+  for (unsigned Q = 1u << 6; Q > 1; Q >>= 1) if (X[2] & Q) tt ^= Q - 1;
   X[0] ^= tt; X[1] ^= tt; X[2] ^= tt;
   unsigned h = 0;
 #pragma unroll
-  for (int b = 9; b >= 0; b--) h = (h << 3) | (((X[0] >> b) & 1u) << 2) | (((X[1] >> b) & 1u) << 1) | ((X[2] >> b) & 1u);
-  if (!ok) h = 0x3fffffffu;
-  keys[i] = (is_corner ? 0u : 0x40000000u) | h; vals[i] = i;
+  for (int b = 6; b >= 0; b--) h = (h << 3) | (((X[0] >> b) & 1u) << 2) | (((X[1] >> b) & 1u) << 1) | ((X[2] >> b) & 1u);
+  if (!ok) h = 0x1fffffu;
+  keys[i] = (is_corner ? 0u : 0x200000u) | h; vals[i] = i;
 }
 
 // Gates + functor constructors (K7) for one feature whose 5 nearest neighbours are in `t`; writes the residual-block slot `w`.
@@ -503,12 +503,12 @@ int launch_query_sort(ll_ctx* ctx, const KnnBlocksArgs& a, int* d_perm) {
   const int M = a.n_corner + a.n_surf;
   if (M == 0) return LL_OK;
   size_t tmp = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, M, 0, 31, ctx->stream);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, M, 0, 22, ctx->stream);
   size_t o_k0 = 0, o_k1 = align256((size_t)M * 4), o_v0 = o_k1 + align256((size_t)M * 4), o_t = o_v0 + align256((size_t)M * 4);
   LL_CUDA(ctx, ctx->scratch.reserve(o_t + tmp + 256));
   char* base = ctx->scratch.as<char>();
   query_key_kernel<<<ll_div_up(M, 256), 256, 0, ctx->stream>>>(a, (unsigned*)(base + o_k0), (int*)(base + o_v0));
-  LL_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + o_t, tmp, (unsigned*)(base + o_k0), (unsigned*)(base + o_k1), (int*)(base + o_v0), d_perm, M, 0, 31, ctx->stream));
+  LL_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + o_t, tmp, (unsigned*)(base + o_k0), (unsigned*)(base + o_k1), (int*)(base + o_v0), d_perm, M, 0, 22, ctx->stream));
   ctx->launches += 4;
   return LL_OK;
 }
