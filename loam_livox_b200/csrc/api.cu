@@ -74,7 +74,7 @@ void ll_ctx_destroy(ll_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2);
   if (ctx->fg.exec) cudaGraphExecDestroy(ctx->fg.exec);
-  ctx->scratch2.release(); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+  ctx->scratch2.release(); ctx->scratch_fe.release(); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
   ctx->scratch.release(); ctx->stage_in.release(); ctx->extract_buf.release(); ctx->feat_buf.release(); ctx->reg_buf.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->d_reg) cudaFree(ctx->d_reg);
@@ -554,6 +554,9 @@ int scan_front_end(ll_ctx* ctx, const void* raw, size_t n, int fmt, int where, d
   cudaStream_t s = ctx->stream;
   LL_TRY(extract_prepare(ctx, raw, n, fmt, where, stamp));
   const int ncap = (int)n;
+  // the front end runs on its own scratch arena (swapped in under the usual name for the duration of this function)
+  struct ScratchSwap { ll_ctx* c; ScratchSwap(ll_ctx* c_) : c(c_) { DevBuf t = c->scratch; c->scratch = c->scratch_fe; c->scratch_fe = t; }
+                       ~ScratchSwap() { DevBuf t = c->scratch; c->scratch = c->scratch_fe; c->scratch_fe = t; } } swap_guard(ctx);
   ll_ctx::FrontGraph& g = ctx->fg;
   void* bufs[5] = {ctx->extract_buf.p, ctx->reg_buf.p, ctx->scratch.p, ctx->scratch2.p, (void*)(size_t)ctx->scratch.cap};
   const bool same = g.n == n && memcmp(&g.pc, pc, sizeof(*pc)) == 0 && memcmp(g.bufs, bufs, sizeof(bufs)) == 0;

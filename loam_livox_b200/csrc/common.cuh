@@ -106,7 +106,8 @@ struct ll_ctx {
   RegDevState* d_reg = nullptr;   // device
   // multi-GPU
   int rank = 0, world = 1;
-  cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_it[2] = {nullptr, nullptr}; DevBuf scratch2;   // side stream of the per-scan front end
+  cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_it[2] = {nullptr, nullptr}; DevBuf scratch2, scratch_fe;   // side stream of the per-scan front end; the front end's own scratch arenas (fixed once the scan size is
+                                 // known: the captured graph must never see them reallocated by the map refresh or the registration)
   // The per-scan front end (extract + get_features + 4 VoxelGrids + count read-back) replayed as ONE CUDA graph: ~60 launches whose
   // enqueue cost on the host (CUB dispatch included) was longer than their execution.  Re-captured when the shape or any buffer changes.
   struct FrontGraph { cudaGraphExec_t exec = nullptr; size_t n = 0; ll_pipeline_cfg pc; void* bufs[5] = {nullptr}; bool warm = false; uint64_t launches = 0; } fg;
