@@ -136,7 +136,7 @@ __global__ void node_kernel(const float4* __restrict__ pts, int n_valid, const f
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t) {
-  *t = BucketTree();
+  { DevBuf keep = t->storage; *t = BucketTree(); t->storage = keep; }   // re-indexing in place (ll_map_rebuild) reuses the allocation
   t->n_src = n_src;
   cudaStream_t s = ctx->stream;
   // scratch: bbox(8 ints) | keys | keys_out | vals | vals_out | cub temp
