@@ -3,6 +3,8 @@
 //   Livox_laser                      /root/reference/source/livox_feature_extractor.hpp:77   (extract_laser_features :722, get_features :219)
 //   Point_cloud_registration         /root/reference/source/point_cloud_registration.hpp:38  (find_out_incremental_transfrom :163/:585,
 //                                                                                               pointcloudAssociateToMap :673)
+//   Points_cloud_map                 /root/reference/source/cell_map_keyframe.hpp:264        (append_cloud :619, cells in radius + FOV :761, laser_mapping.hpp:475-516)
+//   Laser_mapping::process_new_scan  /root/reference/source/laser_mapping.hpp:1316
 // so that laser_feature_extractor.hpp / laser_mapping.hpp can switch with the small adapter shown in INTEGRATION.md.
 // No PCL / Eigen / Ceres needed: clouds are std::vector<ll200::PointXYZI> (layout-identical to pcl::PointXYZI, 32 bytes).
 #pragma once
@@ -132,6 +134,54 @@ class Point_cloud_registration {
   }
  private:
   Context& ctx_;
+};
+
+// ---- Points_cloud_map (cell_map_keyframe.hpp:264) as the matching path uses it -------------------------------------
+class Points_cloud_map {
+ public:
+  explicit Points_cloud_map(Context& ctx, float resolution = 1.0f, int minimum_revisit_threshold = 2000, int max_cells = 0) : ctx_(ctx) {
+    ctx_.check(ll_cellmap_create(ctx_.get(), resolution, minimum_revisit_threshold, max_cells, &map_));   // set_resolution (:674-679) + m_minimum_revisit_threshold
+  }
+  ~Points_cloud_map() { ll_cellmap_release(map_); }
+  Points_cloud_map(const Points_cloud_map&) = delete; Points_cloud_map& operator=(const Points_cloud_map&) = delete;
+  void append_cloud(const PointCloud& pts) { ctx_.check(ll_cellmap_append(ctx_.get(), map_, pts.data(), pts.size(), LL_FMT_PCL32, LL_HOST)); }   // :619-672
+  int get_cells_size() const { int c = 0, p = 0, f = 0; ctx_.check(ll_cellmap_stats(ctx_.get(), map_, &c, &p, &f)); return c; }
+  // update_buff_for_matching, matching_mode 1, for this map (laser_mapping.hpp:475-516): cells within search_range of t_w_curr and in the FOV,
+  // each down-sampled (and replaced when down_sample_replace), concatenated in ascending cell-index order
+  PointCloud cells_in_fov_downsampled(const std::array<double, 4>& q_w_curr, const std::array<double, 3>& t_w_curr, float search_range, float fov_deg, float leaf,
+                                      bool down_sample_replace = true, int* cells_in_fov = nullptr) {
+    int c = 0, p = 0, f = 0; ctx_.check(ll_cellmap_stats(ctx_.get(), map_, &c, &p, &f));
+    std::vector<ll_point> out((size_t)(p > 0 ? p : 1)); size_t n = 0;
+    ctx_.check(ll_cellmap_assemble(ctx_.get(), map_, q_w_curr.data(), t_w_curr.data(), search_range, fov_deg, leaf, down_sample_replace ? 1 : 0, out.data(), out.size(), &n, cells_in_fov, nullptr));
+    out.resize(n); return to_cloud(out);
+  }
+  ll_cellmap* get() const { return map_; }
+ private:
+  Context& ctx_; ll_cellmap* map_ = nullptr;
+};
+
+// ---- Laser_mapping::process_new_scan with everything on the device (laser_mapping.hpp:1316-1521 + :460-566 mode 1) ----
+class Laser_mapping {
+ public:
+  explicit Laser_mapping(Context& ctx, const ll_mapper_config* cfg = nullptr) : ctx_(ctx) {
+    if (cfg) cfg_ = *cfg; else ll_mapper_config_default(&cfg_);
+    ctx_.check(ll_mapper_create(ctx_.get(), &cfg_, &mapper_));
+  }
+  ~Laser_mapping() { ll_mapper_release(mapper_); }
+  Laser_mapping(const Laser_mapping&) = delete; Laser_mapping& operator=(const Laser_mapping&) = delete;
+  // one raw scan (what Laser_feature::laserCloudHandler receives); returns the int of find_out_incremental_transfrom
+  int process_new_scan(const PointCloud& raw, double time_stamp, ll_reg_result* result = nullptr, ll_mapper_stats* stats = nullptr) {
+    ll_reg_result r; ll_mapper_stats st;
+    ctx_.check(ll_mapper_process_scan(mapper_, raw.data(), raw.size(), LL_FMT_PCL32, LL_HOST, time_stamp, &r, &st));
+    ctx_.check(ll_mapper_pose(mapper_, m_q_w_curr.data(), m_t_w_curr.data(), &m_current_frame_index));
+    if (result) *result = r; if (stats) *stats = st;
+    return r.status;
+  }
+  std::array<double, 4> m_q_w_curr{{1, 0, 0, 0}};   // (w, x, y, z)
+  std::array<double, 3> m_t_w_curr{{0, 0, 0}};
+  int m_current_frame_index = 0;
+ private:
+  Context& ctx_; ll_mapper_config cfg_; ll_mapper* mapper_ = nullptr;
 };
 
 }  // namespace ll200

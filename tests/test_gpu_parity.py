@@ -452,3 +452,40 @@ def test_deblur_register_parity_on_distorted_scan(ctx, oracle):
         assert dtn < 1e-6 and da < 1e-6, (dtn, da)
         assert abs(r.final_cost - ores.final_cost) <= 1e-6 * ores.final_cost
         assert np.linalg.norm(np.array(r.t_w_curr) - curr.t) < 0.01 and S.quat_angle(np.array(r.q_w_curr), curr.q) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE.json full size (C2): size-independent properties
+@pytest.mark.gpu
+def test_full_size_map_knn_and_registration_properties(oracle):
+    """100k-feature-scale queries against the 5M-point map of config C2: sampled queries agree with brute force bit for bit, every result is sorted
+    and duplicate-free, re-indexing the same clouds in place changes nothing, and a registration from a perturbed pose lands on the truth."""
+    from loam_livox_b200.registration import Context, Map, Point_cloud_registration
+    from loam_livox_b200 import capi
+    ctx = Context(0, max_scan_points=100000, max_features=100000)
+    mc, ms = S.make_map(500000, 4500000)
+    m = Map(ctx, mc, ms)
+    assert (m.size(0), m.size(1)) == (500000, 4500000)
+    pose = S.default_pose()
+    fc, fs = S.make_features(3000, 60000, pose)
+    world = np.concatenate([fs[:, :3] @ pose.R().T + pose.t, np.zeros((fs.shape[0], 1))], axis=1).astype(np.float32)
+    idx, d2 = m.nearestKSearch(1, world)
+    assert np.all(np.diff(d2, axis=1) >= 0) and np.all(idx >= 0) and np.all(idx < 4500000)
+    assert all(len(set(r)) == 5 for r in idx[::97])
+    sample = np.random.default_rng(5).choice(world.shape[0], 192, replace=False)
+    bidx, bd2, found = oracle.knn_brute(ms, world[sample])
+    assert np.array_equal(idx[sample], bidx) and np.array_equal(d2[sample], bd2)
+    # in-place re-index of the same clouds: identical answers (ll_map_rebuild reuses the buffers)
+    ctx.check(ctx._lib.ll_map_rebuild(ctx.h, m.h, mc.ctypes.data, mc.shape[0], ms.ctypes.data, ms.shape[0], capi.LL_FMT_XYZI16, capi.LL_HOST))
+    idx2, d22 = m.nearestKSearch(1, world[:5000])
+    assert np.array_equal(idx2, idx[:5000]) and np.array_equal(d22, d2[:5000])
+    # registration at full feature count recovers the injected motion; running it twice gives the same bits (no order-dependent reduction)
+    guess = S.perturb_pose(pose, np.random.default_rng(9))
+    out = []
+    for _ in range(2):
+        reg = Point_cloud_registration(ctx)
+        reg.set_pose(guess.q, guess.t)
+        assert reg.find_out_incremental_transfrom(m, fc, fs) == 1
+        out.append((np.array(reg.result.q_w_curr), np.array(reg.result.t_w_curr), reg.result.final_cost))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
+    assert np.linalg.norm(out[0][1] - pose.t) < 5e-3 and S.quat_angle(out[0][0], pose.q) < 1e-3
+    ctx.close()
