@@ -21,7 +21,7 @@ extern "C" {
 typedef struct { float x, y, z, intensity; } ll_point;                   /* 16 B, the device format     */
 typedef struct { float x, y, z, _pad0, intensity, _pad1, _pad2, _pad3; } ll_pcl_xyzi; /* == pcl::PointXYZI (32 B),
                                                the reference's PointType: /root/reference/include/tools/common.h:9 */
-enum { LL_FMT_XYZI16 = 0, LL_FMT_PCL32 = 1 };
+enum { LL_FMT_XYZI16 = 0, LL_FMT_PCL32 = 1, LL_FMT_STRIDED = 2 /* records described by ll_set_point_layout, e.g. a sensor_msgs/PointCloud2 payload */ };
 enum { LL_HOST = 0, LL_DEVICE = 1 };           /* where an input pointer lives                           */
 
 /* ---- status codes --------------------------------------------------------------------------------- */
@@ -225,6 +225,17 @@ void ll_mapper_release(ll_mapper* mapper);
  * (out->status 1 accepted/skipped, 0 rejected and discarded), world-frame features appended to the cell maps, pose adopted. */
 int  ll_mapper_process_scan(ll_mapper* mapper, const void* raw, size_t n, int fmt, int where, double stamp, ll_reg_result* out, ll_mapper_stats* stats);
 int  ll_mapper_pose(const ll_mapper* mapper, double q_wxyz[4], double t[3], int* frame_index);
+
+/* ---- wire formats ---------------------------------------------------------------------------------------------- */
+/* Layout of one point record of an LL_FMT_STRIDED input: what pcl::fromROSMsg (laser_feature_extractor.hpp:275) resolves by field name from a
+ * sensor_msgs/PointCloud2 (point_step, the offsets of the little-endian fields x, y, z, intensity and intensity's datatype).  The payload is
+ * copied to the device as it is and unpacked there into 16-byte points; n = width * height. */
+enum { LL_I_NONE = 0, LL_I_FLOAT32 = 7, LL_I_UINT8 = 2, LL_I_UINT16 = 4 };   /* = sensor_msgs/PointField datatype codes (0: no intensity field -> 0.0) */
+typedef struct { int point_step, offset_x, offset_y, offset_z, offset_intensity, intensity_datatype; } ll_point_layout;
+int  ll_set_point_layout(ll_ctx* ctx, const ll_point_layout* layout);
+/* One accepted scan in the format of the reference's poses.log (laser_mapping.hpp:1506-1511; the Ceres BriefReport line is not reproduced).
+ * Returns the number of characters written (excluding the terminating 0), or -1 when cap is too small. */
+int  ll_format_pose_log(const ll_reg_result* r, char* buf, size_t cap);
 
 /* Size of the registration-state snapshot copied to the host once per ICP iteration (for traffic accounting). */
 int  ll_state_snapshot_bytes(void);

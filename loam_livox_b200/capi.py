@@ -13,7 +13,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libloamlivox_b200.so")
 
-LL_FMT_XYZI16, LL_FMT_PCL32 = 0, 1
+LL_FMT_XYZI16, LL_FMT_PCL32, LL_FMT_STRIDED = 0, 1, 2
+LL_I_NONE, LL_I_UINT8, LL_I_UINT16, LL_I_FLOAT32 = 0, 2, 4, 7   # sensor_msgs/PointField datatype codes
 LL_HOST, LL_DEVICE = 0, 1
 LL_OK, LL_ERR_INVALID, LL_ERR_CUDA, LL_ERR_CAPACITY, LL_ERR_NO_BLOCKS, LL_ERR_CAP_BINDS = 0, -1, -2, -3, -4, -5
 LL_IPC_HANDLE_BYTES = 64
@@ -24,7 +25,7 @@ EXPORTS = [
     "ll_map_build_sharded", "ll_knn", "ll_reg_state_default", "ll_register", "ll_build_blocks", "ll_normal_equations", "ll_solve", "ll_transform",
     "ll_scan_to_pose", "ll_comm_local_handle", "ll_comm_connect", "ll_launch_count", "ll_cellmap_create", "ll_cellmap_release", "ll_cellmap_append",
     "ll_cellmap_assemble", "ll_cellmap_stats", "ll_voxel_downsample_dev", "ll_transform_dev", "ll_last_features_dev", "ll_mapper_config_default", "ll_mapper_create", "ll_mapper_release",
-    "ll_mapper_process_scan", "ll_mapper_pose", "ll_map_rebuild", "ll_debug_solver_cycles", "ll_state_snapshot_bytes",
+    "ll_mapper_process_scan", "ll_mapper_pose", "ll_map_rebuild", "ll_debug_solver_cycles", "ll_state_snapshot_bytes", "ll_set_point_layout", "ll_format_pose_log",
 ]
 
 
@@ -55,6 +56,10 @@ class RegResult(C.Structure):
 class PipelineCfg(C.Structure):
     _fields_ = [("pieces", C.c_int), ("use_piece", C.c_int), ("extractor_leaf_corner", C.c_float), ("extractor_leaf_surf", C.c_float),
                 ("mapping_leaf_corner", C.c_float), ("mapping_leaf_surf", C.c_float), ("whole_frame", C.c_int)]
+
+
+class PointLayout(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("point_step", "offset_x", "offset_y", "offset_z", "offset_intensity", "intensity_datatype")]
 
 
 class MapperConfig(C.Structure):
@@ -124,6 +129,8 @@ def lib():
     L.ll_last_features_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
     L.ll_debug_solver_cycles.argtypes = [vp, vp]
     L.ll_state_snapshot_bytes.argtypes = []
+    L.ll_set_point_layout.argtypes = [vp, C.POINTER(PointLayout)]
+    L.ll_format_pose_log.argtypes = [C.POINTER(RegResult), C.c_char_p, sz]
     L.ll_map_rebuild.argtypes = [vp, vp, vp, sz, vp, sz, ci, ci]
     L.ll_mapper_config_default.argtypes = [C.POINTER(MapperConfig)]
     L.ll_mapper_create.argtypes = [vp, C.POINTER(MapperConfig), C.POINTER(vp)]

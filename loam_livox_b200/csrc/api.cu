@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -510,6 +511,24 @@ int ll_solve(ll_ctx* ctx, int max_iterations, double x_io[7], double* initial_co
   return LL_OK;
 }
 
+int ll_set_point_layout(ll_ctx* ctx, const ll_point_layout* L) {
+  if (!ctx || !L) return LL_ERR_INVALID;
+  const int isz = L->intensity_datatype == LL_I_FLOAT32 ? 4 : L->intensity_datatype == LL_I_UINT16 ? 2 : L->intensity_datatype == LL_I_UINT8 ? 1 : 0;
+  if (L->intensity_datatype != LL_I_NONE && isz == 0) { ctx->set_error("unsupported intensity datatype"); return LL_ERR_INVALID; }
+  const int offs[3] = {L->offset_x, L->offset_y, L->offset_z};
+  for (int k = 0; k < 3; k++) if (offs[k] < 0 || offs[k] + 4 > L->point_step) { ctx->set_error("field outside the point record"); return LL_ERR_INVALID; }
+  if (isz && (L->offset_intensity < 0 || L->offset_intensity + isz > L->point_step)) { ctx->set_error("intensity outside the point record"); return LL_ERR_INVALID; }
+  ctx->layout = *L;
+  return LL_OK;
+}
+int ll_format_pose_log(const ll_reg_result* r, char* buf, size_t cap) {
+  if (!r || !buf) return -1;
+  const int n = snprintf(buf, cap, "--------------------\nCurr_Q = %f,%f,%f,%f\r\nCurr_T = %f,%f,%f\r\nIncre_Q = %f,%f,%f,%f\r\nIncre_T = %f,%f,%f\r\nCost=%f,blk_size = %d \r\n",
+                         r->q_w_curr[0], r->q_w_curr[1], r->q_w_curr[2], r->q_w_curr[3], r->t_w_curr[0], r->t_w_curr[1], r->t_w_curr[2],
+                         r->q_w_incre[0], r->q_w_incre[1], r->q_w_incre[2], r->q_w_incre[3], r->t_w_incre[0], r->t_w_incre[1], r->t_w_incre[2],
+                         r->final_cost, r->num_residual_blocks);
+  return (n < 0 || (size_t)n >= cap) ? -1 : n;
+}
 // Bytes read back per ICP iteration (the device-side registration state snapshot): what bench.py counts as d2h traffic.
 int ll_state_snapshot_bytes(void) { return (int)sizeof(RegDevState); }
 // Diagnostics: the master CTA's cycle counters of the last registration (kernels.cuh: RegDevState::prof).

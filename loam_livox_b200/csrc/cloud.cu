@@ -25,6 +25,19 @@ __global__ void repack_pcl32_kernel(const float* __restrict__ src, int n, float4
   dst[i] = make_float4(a.x, a.y, a.z, b.x);
 }
 
+// LL_FMT_STRIDED: byte-wise little-endian loads (the offsets of a PointCloud2 record need not be aligned)
+__device__ __forceinline__ float load_f32_le(const unsigned char* p) { const unsigned v = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24); return __uint_as_float(v); }
+__global__ void repack_strided_kernel(const unsigned char* __restrict__ src, int n, ll_point_layout L, float4* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* r = src + (size_t)i * L.point_step;
+  float it = 0.f;
+  if (L.intensity_datatype == LL_I_FLOAT32) it = load_f32_le(r + L.offset_intensity);
+  else if (L.intensity_datatype == LL_I_UINT8) it = (float)r[L.offset_intensity];
+  else if (L.intensity_datatype == LL_I_UINT16) it = (float)((unsigned)r[L.offset_intensity] | ((unsigned)r[L.offset_intensity + 1] << 8));
+  dst[i] = make_float4(load_f32_le(r + L.offset_x), load_f32_le(r + L.offset_y), load_f32_le(r + L.offset_z), it);
+}
+
 int upload_cloud(ll_ctx* ctx, const void* src, size_t n, int fmt, int where, float4* d_dst) {
   if (n == 0) return LL_OK;
   cudaStream_t s = ctx->stream;
@@ -38,6 +51,16 @@ int upload_cloud(ll_ctx* ctx, const void* src, size_t n, int fmt, int where, flo
       d_src = ctx->stage_in.as<float>();
     }
     repack_pcl32_kernel<<<ll_div_up((int)n, 256), 256, 0, s>>>(d_src, (int)n, d_dst); ctx->launches++;
+    LL_CUDA(ctx, cudaGetLastError());
+  } else if (fmt == LL_FMT_STRIDED) {
+    const ll_point_layout L = ctx->layout;
+    const unsigned char* d_src = (const unsigned char*)src;
+    if (where == LL_HOST) {
+      LL_CUDA(ctx, ctx->stage_in.reserve(n * (size_t)L.point_step));
+      LL_CUDA(ctx, cudaMemcpyAsync(ctx->stage_in.p, src, n * (size_t)L.point_step, cudaMemcpyHostToDevice, s));
+      d_src = ctx->stage_in.as<unsigned char>();
+    }
+    repack_strided_kernel<<<ll_div_up((int)n, 256), 256, 0, s>>>(d_src, (int)n, L, d_dst); ctx->launches++;
     LL_CUDA(ctx, cudaGetLastError());
   } else { ctx->set_error("unknown point format"); return LL_ERR_INVALID; }
   return LL_OK;

@@ -99,6 +99,7 @@ struct ll_ctx {
   // arenas
   DevBuf scratch;      // CUB temp storage
   DevBuf stage_in;     // raw uploads (PCL32 or XYZI16)
+  ll_point_layout layout = {16, 0, 4, 8, 12, LL_I_FLOAT32};   // LL_FMT_STRIDED records
   DevBuf extract_buf;  // ExtractState arrays
   DevBuf feat_buf;     // feature clouds / voxel-grid temporaries
   DevBuf reg_buf;      // registration arrays

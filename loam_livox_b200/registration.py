@@ -47,6 +47,11 @@ class Context:
         if st != capi.LL_OK:
             raise LoamLivoxError(f"status {st}: {self._lib.ll_last_error(self.h).decode()}")
 
+    def set_point_layout(self, point_step, offset_x=0, offset_y=4, offset_z=8, offset_intensity=12, intensity_datatype=capi.LL_I_FLOAT32):
+        """Record layout of LL_FMT_STRIDED inputs (a sensor_msgs/PointCloud2 payload: what pcl::fromROSMsg resolves by field name)."""
+        L = capi.PointLayout(point_step, offset_x, offset_y, offset_z, offset_intensity, intensity_datatype)
+        self.check(self._lib.ll_set_point_layout(self.h, C.byref(L)))
+
     def launches(self) -> int:
         return int(self._lib.ll_launch_count(self.h))
 
@@ -55,6 +60,15 @@ class Context:
 
     def stream(self) -> int:
         return int(self._lib.ll_ctx_stream(self.h) or 0)
+
+
+def format_pose_log(result: capi.RegResult) -> str:
+    """One accepted scan in the reference's poses.log format (laser_mapping.hpp:1506-1511)."""
+    buf = C.create_string_buffer(1024)
+    n = capi.lib().ll_format_pose_log(C.byref(result), buf, 1024)
+    if n < 0:
+        raise LoamLivoxError("ll_format_pose_log failed")
+    return buf.value.decode()
 
 
 class Livox_laser:
@@ -71,6 +85,15 @@ class Livox_laser:
         self.n = pts.shape[0]
         ns = C.c_int(0)
         self.ctx.check(self.ctx._lib.ll_extract(self.ctx.h, pts.ctypes.data, self.n, fmt, capi.LL_HOST, float(time_stamp), C.byref(ns)))
+        return ns.value
+
+    def extract_from_pointcloud2(self, data: bytes, n_points: int, time_stamp: float) -> int:
+        """Same, from the raw payload of a sensor_msgs/PointCloud2 (layout set with Context.set_point_layout): replaces pcl::fromROSMsg +
+        extract_laser_features (laser_feature_extractor.hpp:275,285); the payload is unpacked on the device."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        self.n = int(n_points)
+        ns = C.c_int(0)
+        self.ctx.check(self.ctx._lib.ll_extract(self.ctx.h, buf.ctypes.data, self.n, capi.LL_FMT_STRIDED, capi.LL_HOST, float(time_stamp), C.byref(ns)))
         return ns.value
 
     def get_features(self, minimum_blur: float = 0.0, maximum_blur: float = 0.3):

@@ -46,3 +46,16 @@ def test_no_cpu_fallback():
     assert capi.lib().ll_ctx_create(None, 0, C.byref(h)) == capi.LL_ERR_CUDA and not h.value
     src = "".join(open(os.path.join(ROOT, "loam_livox_b200", f)).read() for f in ("capi.py", "registration.py", "distributed.py", "__init__.py"))
     assert "oracle" not in src.replace("no CPU or PyTorch fallback", "")
+
+
+def test_pose_log_format_matches_reference_printf():
+    """ll_format_pose_log is host-only code: the poses.log block of /root/reference/source/laser_mapping.hpp:1506-1511."""
+    from loam_livox_b200 import capi
+    from loam_livox_b200.registration import format_pose_log
+    r = capi.RegResult()
+    r.q_w_curr[:] = [0.9, 0.1, -0.2, 0.3]; r.t_w_curr[:] = [1.5, -2.25, 0.125]
+    r.q_w_incre[:] = [1.0, 0.001, 0.002, -0.003]; r.t_w_incre[:] = [0.01, 0.02, -0.03]
+    r.final_cost = 12.3456789; r.num_residual_blocks = 4321
+    want = "--------------------\n" + "Curr_Q = %f,%f,%f,%f\r\n" % (0.9, 0.1, -0.2, 0.3) + "Curr_T = %f,%f,%f\r\n" % (1.5, -2.25, 0.125) + \
+           "Incre_Q = %f,%f,%f,%f\r\n" % (1.0, 0.001, 0.002, -0.003) + "Incre_T = %f,%f,%f\r\n" % (0.01, 0.02, -0.03) + "Cost=%f,blk_size = %d \r\n" % (12.3456789, 4321)
+    assert format_pose_log(r) == want

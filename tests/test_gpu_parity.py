@@ -489,3 +489,30 @@ def test_full_size_map_knn_and_registration_properties(oracle):
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
     assert np.linalg.norm(out[0][1] - pose.t) < 5e-3 and S.quat_angle(out[0][0], pose.q) < 1e-3
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- N3: PointCloud2 payload in
+@pytest.mark.gpu
+def test_pointcloud2_payload_equals_float4_input(ctx, oracle):
+    """A livox_ros_driver-style PointCloud2 record (x, y, z, intensity float32 + tag, line uint8; point_step 18, unaligned records) and a record with a
+    uint8 intensity give exactly the features of the plain float4 input."""
+    from loam_livox_b200 import capi
+    from loam_livox_b200.registration import Livox_laser
+    raw = S.make_scan(20000, S.default_pose())
+    raw[:, 3] = np.round(np.clip(np.nan_to_num(raw[:, 3]), 0, 255))   # reflectivity as the driver sends it: integral 0..255
+    gl = Livox_laser(ctx)
+    n0 = gl.extract_laser_features(raw, 100.0)
+    ref = gl.get_features(0.0, 1.0)
+    for step, itype in ((18, capi.LL_I_FLOAT32), (13, capi.LL_I_UINT8)):
+        rec = np.zeros((raw.shape[0], step), np.uint8)
+        rec[:, 0:12] = raw[:, :3].copy().view(np.uint8).reshape(-1, 12)
+        if itype == capi.LL_I_FLOAT32:
+            rec[:, 12:16] = raw[:, 3:4].copy().view(np.uint8).reshape(-1, 4); rec[:, 16] = 7; rec[:, 17] = 3
+        else:
+            rec[:, 12] = raw[:, 3].astype(np.uint8)
+        ctx.set_point_layout(step, 0, 4, 8, 12, itype)
+        g2 = Livox_laser(ctx)
+        assert g2.extract_from_pointcloud2(rec.tobytes(), raw.shape[0], 100.0) == n0
+        got = g2.get_features(0.0, 1.0)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b, equal_nan=True)
