@@ -516,3 +516,44 @@ def test_pointcloud2_payload_equals_float4_input(ctx, oracle):
         got = g2.get_features(0.0, 1.0)
         for a, b in zip(ref, got):
             assert np.array_equal(a, b, equal_nan=True)
+
+
+# ---------------------------------------------------------------------------------------------- config C5 in small: triple-lidar frame
+@pytest.mark.gpu
+def test_triple_lidar_frame_parity(ctx, oracle):
+    """Mid-100 flow (laser_feature_extractor.hpp:303-380, launch/rosbag_mid100.launch: piecewise_number 2): ONE extractor object handles the three
+    heads in turn, the per-piece feature clouds of the heads are summed, then VoxelGrid (plane_res / 2, line_res), then the registration of the merged
+    300k-pt frame.  Every stage against the oracle."""
+    from loam_livox_b200.registration import Livox_laser, Map, Point_cloud_registration, voxel_grid_filter
+    pose = S.default_pose()
+    heads = S.make_triple_scan(300000, pose)
+    gl, ol = Livox_laser(ctx), oracle.Extractor()
+    pieces = 2
+    g_parts, o_parts = [], []
+    for k, raw in enumerate(heads):
+        stamp = 100.0 + 0.1 * 0 + 1e-3 * k
+        ng, no = gl.extract_laser_features(raw, stamp), ol.extract(raw, stamp)
+        assert ng == no and ng > 5
+        gs, ge = gl.piece_bounds(pieces); os_, oe = ol.piece_bounds(pieces)
+        assert np.array_equal(gs, os_) and np.array_equal(ge, oe)
+        g_parts.append([gl.get_features(float(gs[i]), float(ge[i])) for i in range(pieces)])
+        o_parts.append([ol.get_features(float(os_[i]), float(oe[i])) for i in range(pieces)])
+    for i in range(pieces):
+        gc = np.concatenate([g_parts[h][i][0] for h in range(3)]); gsf = np.concatenate([g_parts[h][i][1] for h in range(3)])
+        oc = np.concatenate([o_parts[h][i][0] for h in range(3)]); osf = np.concatenate([o_parts[h][i][1] for h in range(3)])
+        assert np.array_equal(gc, oc) and np.array_equal(gsf, osf)
+        gsf_d, gc_d = voxel_grid_filter(ctx, gsf, 0.2), voxel_grid_filter(ctx, gc, 0.1)          # :372-373, :379-380
+        assert np.array_equal(gsf_d, oracle.voxel_grid(osf, 0.2)) and np.array_equal(gc_d, oracle.voxel_grid(oc, 0.1))
+        if i == 0:
+            mc, ms = S.make_map(20000, 180000)
+            m = Map(ctx, mc, ms)
+            guess = S.perturb_pose(pose, np.random.default_rng(3), dt=0.05, dang_deg=1.0)
+            fc, fs = voxel_grid_filter(ctx, gc_d, 0.1), voxel_grid_filter(ctx, gsf_d, 0.4)      # laser_mapping.hpp:1367-1373
+            reg = Point_cloud_registration(ctx)
+            reg.set_pose(guess.q, guess.t)
+            st = reg.find_out_incremental_transfrom(m, fc, fs)
+            p = oracle.default_params(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t)
+            ost, ores = oracle.register(mc, oracle.KdTree(mc), ms, oracle.KdTree(ms), fc, fs, p)
+            assert st == ost and reg.result.icp_iterations == ores.icp_iterations
+            assert np.linalg.norm(np.array(reg.result.t_w_curr) - np.array(ores.t_w_curr)) < 1e-6
+            assert S.quat_angle(np.array(reg.result.q_w_curr), np.array(ores.q_w_curr)) < 1e-6
