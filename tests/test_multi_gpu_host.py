@@ -43,7 +43,26 @@ def _worker(rank, world, port, q):
     cf, gf, Hf = O.evaluate(blocks, guess.q, guess.t, x)
     ok_sum = abs(total[0] - cf) <= 1e-12 * cf and np.allclose(total[1:7], gf, rtol=1e-10, atol=1e-12) and np.allclose(total[7:43].reshape(6, 6), Hf, rtol=1e-10)
     ok_part = int(total[43]) == blocks.shape[0] and own.min() >= 0 and own.max() < world and len(set(own.tolist())) == world
-    q.put((rank, ok_handles, ok_sum, ok_part))
+    # 4. K10 in sharded mode: every rank fills a slot-indexed exchange array with the loss-corrected L1 norms of the blocks it owns (NaN elsewhere),
+    #    the arrays are merged slot by slot (what l1_exchange_kernel does with NVLink stores), and the order statistic over the merged array equals
+    #    the single-rank one (point_cloud_registration.hpp:153-161)
+    def l1_of(b):
+        r = O.evaluate(b, guess.q, guess.t, x, want_full=True)[3].reshape(-1, 3)
+        return np.abs(r).sum(1)
+    xl1 = np.full(feats.shape[0], np.nan)
+    sel = own[slot] == rank
+    if sel.any():
+        xl1[slot[sel]] = l1_of(blocks[sel])
+    gathered = [torch.zeros(feats.shape[0], dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.tensor(xl1))
+    stack = np.stack([t.numpy() for t in gathered])
+    owners_per_slot = (~np.isnan(stack)).sum(0)
+    merged = np.nanmin(np.where(np.isnan(stack), np.inf, stack), axis=0)
+    full = np.full(feats.shape[0], np.inf); full[slot] = l1_of(blocks)
+    thr_merged = O.inlier_threshold(np.repeat(merged[np.isfinite(merged)] / 3.0, 3), 0.8)    # three equal residuals whose L1 norm is the value
+    thr_full = O.inlier_threshold(np.repeat(full[np.isfinite(full)] / 3.0, 3), 0.8)
+    ok_k10 = owners_per_slot.max() == 1 and np.array_equal(merged, full) and thr_merged == thr_full
+    q.put((rank, ok_handles, ok_sum, ok_part and ok_k10))
     dist.barrier()
     dist.destroy_process_group()
 
