@@ -303,7 +303,7 @@ def run_stream(args):
     from loam_livox_b200 import capi
     from loam_livox_b200.registration import Context, Laser_mapping
     n_total = args.steps + args.warmup
-    poses = S.trajectory(n_scans=n_total, n_static=3, speed=1.0)
+    poses = S.trajectory(n_scans=n_total, n_static=4, speed=1.0)
     raws = [torch.from_numpy(S.make_scan(N_SCAN, p, seed=S.SEED + k)).pin_memory() for k, p in enumerate(poses)]
     ctx = Context(0, max_scan_points=N_SCAN, max_features=N_SCAN)
     gm = Laser_mapping(ctx, reg=capi.default_reg_state(mapping_init_accumulate_frames=3))

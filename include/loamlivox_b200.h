@@ -32,8 +32,8 @@ enum {
   LL_ERR_CAPACITY = -3,   /* input larger than the context was created for                             */
   LL_ERR_NO_BLOCKS = -4,  /* no residual block survived the gates (reference would dereference an empty
                              std::set at point_cloud_registration.hpp:160)                              */
-  LL_ERR_CAP_BINDS = -5   /* maximum_allow_residual_block would bind: the reference then drops blocks with a
-                             std::random_device RNG (:232-238,:438-458); not reproducible, not implemented */
+  LL_ERR_CAP_BINDS = -5   /* no longer returned (kept for ABI stability): the residual-block cap (:232-238,:339-345,:434-458) is implemented,
+                             see ll_reg_state::rng_seed */
 };
 
 /* ---- pt_type / pt_label bit masks (livox_feature_extractor.hpp:82-103) --------------------------- */
@@ -120,8 +120,10 @@ typedef struct {
   int    cere_max_iterations;             /* m_para_cere_max_iterations                                */
   int    cere_prerun_times;               /* m_para_cere_prerun_times (2)                              */
   int    icp_plane, icp_line;             /* ICP_PLANE, ICP_LINE                                       */
-  int    maximum_allow_residual_block;    /* m_maximum_allow_residual_block                            */
-  int    _reserved;
+  int    maximum_allow_residual_block;    /* m_maximum_allow_residual_block: features are pre-skipped when their class has more than 2 x this
+                                             (:232-238,:339-345) and blocks dropped with probability 1 - cap/M when M exceed it (:434-458)     */
+  int    rng_seed;                        /* seed of the counter-based generator that replaces the reference's std::random_device-seeded
+                                             m_rand_float (tools_random.hpp:18-25): same seed, same kept blocks, on any GPU count             */
   double para_max_angular_rate;           /* m_para_max_angular_rate (deg, reject gate)                */
   double para_max_speed;                  /* m_para_max_speed (bound on |t_incre[j]|)                  */
   double max_final_cost;                  /* m_max_final_cost                                          */
@@ -135,7 +137,14 @@ typedef struct {
   double q_w_curr[4], t_w_curr[3];        /* m_q_w_curr, m_t_w_curr                                    */
   double para_buffer_incremental[7];      /* m_para_buffer_incremental: q (x,y,z,w) then t             */
 } ll_reg_state;
-void ll_reg_state_default(ll_reg_state* s);   /* performance_precision.yaml + launch/rosbag.launch values */
+/* performance_precision.yaml + launch/rosbag.launch values, EXCEPT the two knobs SURVEY.md 8(d) raises for the 30k-feature benchmark scans:
+ * maximum_allow_residual_block = 1e6 (no random drop) and max_final_cost = 1e9 (the shipped 2.0 assumes <= 200 blocks). */
+void ll_reg_state_default(ll_reg_state* s);
+/* The shipped values exactly: config/performance_precision.yaml (realtime = 0: cap 200) or performance_realtime.yaml (realtime = 1: cap 150),
+ * max_allow_final_cost 2.0, launch/rosbag.launch:9-11 (20 deg, 0.3 m). */
+void ll_reg_state_yaml(ll_reg_state* s, int realtime);
+/* The uniform float in [0,1) the cap draws for (seed, ICP iteration, stream 0 corner pre-skip / 1 surface pre-skip / 2 drop, index). */
+float ll_cap_uniform(int seed, int icp_iteration, int stream, int index);
 
 typedef struct {
   int    status;                 /* return value of find_out_incremental_transfrom: 1 accepted or skipped, 0 rejected */

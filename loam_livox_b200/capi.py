@@ -25,7 +25,7 @@ EXPORTS = [
     "ll_map_build_sharded", "ll_knn", "ll_reg_state_default", "ll_register", "ll_build_blocks", "ll_normal_equations", "ll_solve", "ll_transform",
     "ll_scan_to_pose", "ll_comm_local_handle", "ll_comm_connect", "ll_launch_count", "ll_cellmap_create", "ll_cellmap_release", "ll_cellmap_append",
     "ll_cellmap_assemble", "ll_cellmap_stats", "ll_voxel_downsample_dev", "ll_transform_dev", "ll_last_features_dev", "ll_mapper_config_default", "ll_mapper_create", "ll_mapper_release",
-    "ll_mapper_process_scan", "ll_mapper_pose", "ll_map_rebuild", "ll_debug_solver_cycles", "ll_state_snapshot_bytes", "ll_set_point_layout", "ll_format_pose_log",
+    "ll_mapper_process_scan", "ll_mapper_pose", "ll_map_rebuild", "ll_debug_solver_cycles", "ll_state_snapshot_bytes", "ll_set_point_layout", "ll_format_pose_log", "ll_reg_state_yaml", "ll_cap_uniform",
 ]
 
 
@@ -36,7 +36,7 @@ class Config(C.Structure):
 
 class RegState(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("if_motion_deblur", "current_frame_index", "mapping_init_accumulate_frames", "icp_max_iterations", "cere_max_iterations",
-                                       "cere_prerun_times", "icp_plane", "icp_line", "maximum_allow_residual_block", "_reserved")] + \
+                                       "cere_prerun_times", "icp_plane", "icp_line", "maximum_allow_residual_block", "rng_seed")] + \
                [(n, C.c_double) for n in ("para_max_angular_rate", "para_max_speed", "max_final_cost", "minimum_pt_time_stamp", "maximum_pt_time_stamp",
                                           "minimum_icp_R_diff", "minimum_icp_T_diff", "inliner_dis", "inlier_ratio", "maximum_dis_plane_for_match",
                                           "maximum_dis_line_for_match", "huber_a")] + \
@@ -111,6 +111,9 @@ def lib():
     L.ll_map_size.restype = sz
     L.ll_knn.argtypes = [vp, vp, ci, vp, sz, vp, vp]
     L.ll_reg_state_default.argtypes = [C.POINTER(RegState)]
+    L.ll_reg_state_yaml.argtypes = [C.POINTER(RegState), ci]
+    L.ll_cap_uniform.argtypes = [ci, ci, ci, ci]
+    L.ll_cap_uniform.restype = cf
     L.ll_register.argtypes = [vp, vp, vp, sz, vp, sz, ci, ci, C.POINTER(RegState), C.POINTER(RegResult)]
     L.ll_build_blocks.argtypes = [vp, vp, vp, sz, vp, sz, ci, ci, C.POINTER(RegState), vp, vp, vp, C.POINTER(ci), C.POINTER(ci)]
     L.ll_normal_equations.argtypes = [vp, vp, vp]
@@ -154,6 +157,18 @@ def default_config(**kw) -> Config:
 def default_reg_state(**kw) -> RegState:
     s = RegState()
     lib().ll_reg_state_default(C.byref(s))
+    for k, v in kw.items():
+        if isinstance(getattr(s, k), C.Array):
+            getattr(s, k)[:] = list(v)
+        else:
+            setattr(s, k, v)
+    return s
+
+
+def yaml_reg_state(realtime: bool = False, **kw) -> RegState:
+    """The shipped YAML values exactly (cap 200 / 150, max_allow_final_cost 2.0)."""
+    s = RegState()
+    lib().ll_reg_state_yaml(C.byref(s), int(bool(realtime)))
     for k, v in kw.items():
         if isinstance(getattr(s, k), C.Array):
             getattr(s, k)[:] = list(v)

@@ -47,43 +47,56 @@ void ll_reg_state_default(ll_reg_state* s) {
   s->q_w_last[0] = 1; s->q_w_curr[0] = 1; s->para_buffer_incremental[3] = 1;
 }
 
+void ll_reg_state_yaml(ll_reg_state* s, int realtime) {
+  ll_reg_state_default(s);
+  s->maximum_allow_residual_block = realtime ? 150 : 200;   // config/performance_realtime.yaml:23 / performance_precision.yaml:23
+  s->max_final_cost = 2.0;                                  // optimization/max_allow_final_cost
+}
+float ll_cap_uniform(int seed, int icp_iteration, int stream, int index) { return ll_cap_uniform_f(seed, icp_iteration, stream, index); }
+
 int ll_ctx_create(const ll_config* cfg, int device, ll_ctx** out) {
   if (!out) return LL_ERR_INVALID;
   *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return LL_ERR_CUDA;   // no silent CPU fallback: the CUDA path is the product
   if (device < 0 || device >= ndev) return LL_ERR_INVALID;
+  // ex_scatter_kernel packs the three running counts of get_features in 21 bits each; the cap on a scan is therefore 2^21 - 1 points
+  if (cfg && (cfg->max_scan_points < 1 || cfg->max_scan_points >= (1 << 21) || cfg->max_features < 1)) return LL_ERR_INVALID;
   ll_ctx* ctx = new ll_ctx();
   ctx->device = device;
   if (cfg) ctx->cfg = *cfg; else ll_config_default(&ctx->cfg);
-  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return LL_ERR_CUDA; }
-  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device); ctx->num_sms = prop.multiProcessorCount;
-  cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&ctx->ev_it[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_it[1], cudaEventDisableTiming);
-  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->ev2); cudaEventCreate(&ctx->ev3);
-  for (int i = 0; i < 5 * 16 + 2; i++) cudaEventCreate(&ctx->evp[i]);
-  ctx->pinned_cap = 1 << 16; cudaHostAlloc(&ctx->pinned, ctx->pinned_cap, cudaHostAllocDefault);
-  void* dreg = nullptr; cudaMalloc(&dreg, sizeof(RegDevState)); cudaMemset(dreg, 0, sizeof(RegDevState)); ctx->d_reg = (RegDevState*)dreg;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { delete ctx; return LL_ERR_CUDA; }
+  // every call is checked: the first failure wins and the half-built context is torn down by ll_ctx_destroy (which tolerates null members)
+  cudaError_t e = cudaSetDevice(device);
+  auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; };
+  cudaDeviceProp prop; ok(cudaGetDeviceProperties(&prop, device)); ctx->num_sms = prop.multiProcessorCount;
+  ok(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ok(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  ok(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); ok(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  ok(cudaEventCreateWithFlags(&ctx->ev_it[0], cudaEventDisableTiming)); ok(cudaEventCreateWithFlags(&ctx->ev_it[1], cudaEventDisableTiming));
+  ok(cudaEventCreate(&ctx->ev0)); ok(cudaEventCreate(&ctx->ev1)); ok(cudaEventCreate(&ctx->ev2)); ok(cudaEventCreate(&ctx->ev3));
+  for (int i = 0; i < 5 * 16 + 2; i++) ok(cudaEventCreate(&ctx->evp[i]));
+  ctx->pinned_cap = 1 << 16; ok(cudaHostAlloc(&ctx->pinned, ctx->pinned_cap, cudaHostAllocDefault));
+  void* dreg = nullptr; ok(cudaMalloc(&dreg, sizeof(RegDevState))); if (dreg) ok(cudaMemset(dreg, 0, sizeof(RegDevState))); ctx->d_reg = (RegDevState*)dreg;
+  if (e == cudaSuccess && solve_prepare(ctx) != LL_OK) e = cudaErrorUnknown;   // per-function attributes of the solver kernels (no process-global flag: contexts are created from any thread)
+  if (e != cudaSuccess) { cudaGetLastError(); ll_ctx_destroy(ctx); return LL_ERR_CUDA; }
   *out = ctx; return LL_OK;
 }
 void ll_ctx_destroy(ll_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream); if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   if (ctx->fg.exec) cudaGraphExecDestroy(ctx->fg.exec);
-  ctx->scratch2.release(); ctx->scratch_fe.release(); cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+  ctx->scratch2.release(); ctx->scratch_fe.release(); if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork); if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  for (int i = 0; i < 2; i++) if (ctx->ev_it[i]) cudaEventDestroy(ctx->ev_it[i]);
   ctx->scratch.release(); ctx->stage_in.release(); ctx->extract_buf.release(); ctx->feat_buf.release(); ctx->reg_buf.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->d_reg) cudaFree(ctx->d_reg);
   if (ctx->comm_local) cudaFree(ctx->comm_local);
   for (int i = 0; i < 8; i++) if (ctx->comm_peers[i] && i != ctx->rank) cudaIpcCloseMemHandle(ctx->comm_peers[i]);
   for (int i = 0; i < 5 * 16 + 2; i++) if (ctx->evp[i]) cudaEventDestroy(ctx->evp[i]);
-  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev2); cudaEventDestroy(ctx->ev3);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0); if (ctx->ev1) cudaEventDestroy(ctx->ev1); if (ctx->ev2) cudaEventDestroy(ctx->ev2); if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 const char* ll_last_error(const ll_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -313,13 +326,15 @@ static void fill_state(RegDevState* h, const ll_reg_state* in) {
   h->q_last_opt[0] = 1.0;
   h->bound = (double)(float)in->para_max_speed; h->huber_a = in->huber_a; h->inliner_dis = in->inliner_dis; h->inlier_ratio = in->inlier_ratio;
   h->min_icp_R = in->minimum_icp_R_diff; h->min_icp_T = in->minimum_icp_T_diff;
+  h->cap = in->maximum_allow_residual_block; h->rng_seed = in->rng_seed;
   h->if_motion_deblur = in->if_motion_deblur ? 1 : 0; h->min_ts = in->minimum_pt_time_stamp; h->max_ts = in->maximum_pt_time_stamp;   // interp_* = 0: reset_incremtal_parameter (:120-125)
 }
 static KnnBlocksArgs knn_args(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, int ns, const ll_reg_state* in, bool debug) {
   KnnBlocksArgs a; a.corner = make_view(map->corner); a.surf = make_view(map->surf); a.feat = A.feat; a.n_corner = nc; a.n_surf = ns;
   a.pose = ctx->d_reg->pose_curr; a.max_dis_line = in->maximum_dis_line_for_match; a.max_dis_plane = in->maximum_dis_plane_for_match;
   a.icp_line = in->icp_line; a.icp_plane = in->icp_plane; a.blk_a = A.blk_a; a.blk_v = A.blk_v;
-  a.corner_avail = &ctx->d_reg->corner_avail; a.surf_avail = &ctx->d_reg->surf_avail;
+  a.corner_avail = &ctx->d_reg->corner_avail; a.surf_avail = &ctx->d_reg->surf_avail; a.n_blocks = &ctx->d_reg->n_blocks;
+  a.cap = in->maximum_allow_residual_block; a.rng_seed = in->rng_seed;
   a.seed_ids = A.knn_idx; a.knn_d = debug ? A.knn_d : nullptr; a.perm = A.perm;
   ctx->solve_world = (map->world > 1 && ctx->world > 1) ? ctx->world : 1;   // replicas of the whole map never exchange anything
   a.st = ctx->d_reg; a.deblur = in->if_motion_deblur ? 1 : 0; ctx->reg_deblur = a.deblur;
@@ -330,7 +345,7 @@ static SolveArgs solve_args(ll_ctx* ctx, const RegArrays& A, int M, int mode, in
   SolveArgs s; s.st = ctx->d_reg; s.feat = A.feat; s.blk_a = A.blk_a; s.blk_v = A.blk_v; s.l1 = A.l1; s.l1_sorted_unique = A.l1_unique; s.d_n_unique = A.n_unique;
   s.partials = A.partials; s.M = M; s.max_iterations = max_iter; s.mode = mode; s.rank = ctx->rank; s.world = ctx->solve_world; s.comm_local = (double*)ctx->comm_local;
   for (int i = 0; i < 8; i++) s.comm_peer[i] = (double*)ctx->comm_peers[i];
-  s.deblur = ctx->reg_deblur; s.prerun_iterations = 0; s.table = nullptr; s.table_mask = 0; s.uniq = nullptr; s.n_uniq = nullptr;
+  s.cap_check = 0; s.deblur = ctx->reg_deblur; s.prerun_iterations = 0; s.table = nullptr; s.table_mask = 0; s.uniq = nullptr; s.n_uniq = nullptr;
   return s;
 }
 
@@ -347,7 +362,7 @@ int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, 
   if (!(map->corner.n_src > 0 && map->surf.n_src > 50 && in->current_frame_index > in->mapping_init_accumulate_frames)) return LL_OK;
   const int M = nc + ns;
   ctx->last_nc = nc; ctx->last_ns = ns;
-  if (nc > 2 * in->maximum_allow_residual_block || ns > 2 * in->maximum_allow_residual_block) { ctx->set_error("feature count exceeds 2 x maximum_allow_residual_block (reference would drop features at random)"); return LL_ERR_CAP_BINDS; }
+  const int cap_check = M > in->maximum_allow_residual_block ? 1 : 0;   // fewer slots than the cap: neither the pre-skip nor the drop rule can fire
   if (M == 0) { ctx->set_error("no features"); return LL_ERR_NO_BLOCKS; }
   RegDevState* h = (RegDevState*)ctx->pinned;
   fill_state(h, in);
@@ -370,7 +385,7 @@ int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, 
   RegDevState* slots[2] = {hs, (RegDevState*)((char*)hs + align256(sizeof(RegDevState)))};
   auto enqueue_iteration = [&](int it) -> int {
     cudaEvent_t* e = it < 16 ? &ctx->evp[5 * it] : nullptr;
-    LL_CUDA(ctx, cudaMemsetAsync(&ctx->d_reg->corner_avail, 0, 2 * sizeof(int), s));
+    LL_CUDA(ctx, cudaMemsetAsync(&ctx->d_reg->corner_avail, 0, 3 * sizeof(int), s));   // corner_avail, surf_avail, n_blocks
     if (sharded) LL_CUDA(ctx, cudaMemsetAsync(x_l1, 0xff, (size_t)M * sizeof(double), s));   // NaN = nobody owns a block here (peers fill it after solve #1)
     if (it == 0) LL_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     if (e) LL_CUDA(ctx, cudaEventRecord(e[0], s));
@@ -381,16 +396,17 @@ int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, 
       // one launch: solve #1 -> L1 norms -> de-duplication + order statistic -> outlier drop -> solve #2 -> pose (lm_solve_kernel, mode 4)
       SolveArgs sa = solve_args(ctx, A, M, 4, in->cere_max_iterations);
       sa.prerun_iterations = in->cere_prerun_times; sa.table = (unsigned long long*)ctx->scratch.p; sa.table_mask = set_cap - 1;
-      sa.n_uniq = (int*)A.l1_sorted; sa.uniq = A.l1_sorted + 2;
+      sa.n_uniq = (int*)A.l1_sorted; sa.uniq = A.l1_sorted + 2; sa.cap_check = cap_check;
       if (e) { LL_CUDA(ctx, cudaEventRecord(e[2], s)); LL_CUDA(ctx, cudaEventRecord(e[3], s)); }
       LL_TRY(launch_solve(ctx, sa));
     } else {
-      LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 0, in->cere_prerun_times)));
+      if (cap_check) LL_TRY(launch_count_exchange(ctx));
+      { SolveArgs sa = solve_args(ctx, A, M, 0, in->cere_prerun_times); sa.cap_check = cap_check; LL_TRY(launch_solve(ctx, sa)); }
       if (e) LL_CUDA(ctx, cudaEventRecord(e[2], s));
       LL_TRY(launch_l1_exchange(ctx, A.l1, M));
       LL_TRY(launch_inlier_select(ctx, x_l1, M, in->inlier_ratio, A.l1_sorted, A.l1_unique, A.n_unique));
       if (e) LL_CUDA(ctx, cudaEventRecord(e[3], s));
-      LL_TRY(launch_solve(ctx, solve_args(ctx, A, M, 1, in->cere_max_iterations)));
+      { SolveArgs sa = solve_args(ctx, A, M, 1, in->cere_max_iterations); sa.cap_check = cap_check; LL_TRY(launch_solve(ctx, sa)); }
     }
     if (e) LL_CUDA(ctx, cudaEventRecord(e[4], s));
     LL_CUDA(ctx, cudaMemcpyAsync(slots[it & 1], ctx->d_reg, sizeof(RegDevState), cudaMemcpyDeviceToHost, s));
@@ -405,9 +421,8 @@ int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, 
     if (speculate && iter + 1 < in->icp_max_iterations) LL_TRY(enqueue_iteration(iter + 1));
     LL_CUDA(ctx, cudaEventSynchronize(ctx->ev_it[iter & 1]));
     hs = slots[iter & 1];
-    if (hs->lm.termination == -1) { ctx->set_error("no residual block survived the gates / inlier selection"); return LL_ERR_NO_BLOCKS; }
-    if (iter == 0 && (hs->corner_avail + (in->icp_plane ? hs->surf_avail : 0)) > in->maximum_allow_residual_block) {
-      ctx->set_error("residual blocks exceed maximum_allow_residual_block (reference would drop blocks at random)"); return LL_ERR_CAP_BINDS;
+    if (hs->lm.termination == -1) {   // the iteration enqueued ahead returns at once (icp_done is set on the device); drain it before the arena is reused
+      cudaStreamSynchronize(s); ctx->set_error("no residual block survived the gates / cap / inlier selection"); return LL_ERR_NO_BLOCKS;
     }
     if (hs->icp_done) break;
     if (!speculate && iter + 1 < in->icp_max_iterations) LL_TRY(enqueue_iteration(iter + 1));
@@ -564,8 +579,8 @@ static int front_end_enqueue(ll_ctx* ctx, const ll_pipeline_cfg* pc, const RegAr
   LL_TRY(launch_voxel_grid(ctx, A.tmp_c, ncap, cnt + 6, pc->mapping_leaf_surf, A.tmp_b, cnt + 7));
   LL_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
   int* h = (int*)ctx->pinned + 8192;
-  LL_CUDA(ctx, cudaMemcpyAsync(h, cnt, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
-  LL_CUDA(ctx, cudaMemcpyAsync(h + 8, ctx->ex.d_meta, 12, cudaMemcpyDeviceToHost, s));
+  LL_CUDA(ctx, cudaMemcpyAsync(h, cnt, 12 * sizeof(int), cudaMemcpyDeviceToHost, s));   // [10], [11]: min / max time stamp of the full cloud
+  LL_CUDA(ctx, cudaMemcpyAsync(h + 12, ctx->ex.d_meta, 12, cudaMemcpyDeviceToHost, s));
   return LL_OK;
 }
 
@@ -609,7 +624,8 @@ int scan_front_end(ll_ctx* ctx, const void* raw, size_t n, int fmt, int where, d
   }
   LL_CUDA(ctx, cudaStreamSynchronize(s));
   int* h = (int*)ctx->pinned + 8192;
-  const int nc = h[5], ns = h[7], meta_scans = h[9];
+  const int nc = h[5], ns = h[7], meta_scans = h[13];
+  { int lo = h[10], hi = h[11]; lo = lo >= 0 ? lo : lo ^ 0x7fffffff; hi = hi >= 0 ? hi : hi ^ 0x7fffffff; memcpy(&ctx->last_full_min_t, &lo, 4); memcpy(&ctx->last_full_max_t, &hi, 4); }
   *nc_out = nc; *ns_out = ns;
   *dropped = (meta_scans <= 5 && !pc->whole_frame) ? 1 : 0;
   if (*dropped) return LL_OK;

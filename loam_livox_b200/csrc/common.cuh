@@ -95,6 +95,7 @@ struct ll_ctx {
   uint64_t launches = 0;
   int hook_slots = 0;      // slot count left behind by ll_build_blocks for the parity hooks
   int last_nc = 0, last_ns = 0;   // features of the last registration (ll_last_features_dev)
+  float last_full_min_t = 10000.f, last_full_max_t = -10000.f;   // find_min_max_intensity over the last front end's full cloud (laser_mapping.hpp:1336)
   int num_sms = 0;
   // arenas
   DevBuf scratch;      // CUB temp storage
@@ -121,3 +122,13 @@ struct ll_ctx {
 };
 
 inline int ll_div_up(int a, int b) { return (a + b - 1) / b; }
+
+// Residual-block cap (point_cloud_registration.hpp:232-238,339-345,434-458): the reference draws from a std::random_device-seeded mt19937
+// (include/tools/tools_random.hpp:18-25).  The rule is kept, the numbers come from a counter-based generator keyed on the caller's seed
+// (ll_reg_state::rng_seed), the ICP iteration, a stream (0 corner pre-skip, 1 surface pre-skip, 2 drop) and the feature / slot index:
+// splitmix64 finaliser, top 24 bits -> float in [0,1).  Exported as ll_cap_uniform so that a test can pin it.
+__host__ __device__ inline float ll_cap_uniform_f(int seed, int icp_iter, int stream, int index) {
+  unsigned long long z = (unsigned long long)(unsigned)seed * 0x9E3779B97F4A7C15ull + (((unsigned long long)(unsigned)icp_iter << 40) | ((unsigned long long)(unsigned)stream << 32) | (unsigned long long)(unsigned)index);
+  z ^= z >> 30; z *= 0xbf58476d1ce4e5b9ull; z ^= z >> 27; z *= 0x94d049bb133111ebull; z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}

@@ -200,10 +200,12 @@ __global__ void ex_piece_kernel(const int* __restrict__ scan_first, const int* _
   out[2 * i + 1] = ((float)scan_last[end_scans < 0 ? 0 : end_scans]) / (float)n;
 }
 
+__device__ __forceinline__ int ts_ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }   // order-preserving float -> int
 // K3: membership flags packed for one 64-bit prefix sum: bits 0-20 corner, 21-41 surface, 42-62 full
 __global__ void ex_flags_kernel(int n, const int* __restrict__ pt_type, const int* __restrict__ pt_label, const float* __restrict__ depth, const float* __restrict__ d_bounds,
-                                float min_blur, float max_blur, unsigned long long* __restrict__ packed) {
+                                float min_blur, float max_blur, unsigned long long* __restrict__ packed, int* __restrict__ counts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { counts[10] = ts_ord(10000.0f); counts[11] = ts_ord(-10000.0f); }   // find_min_max_intensity's start values (laser_mapping.hpp:1246-1247)
   if (i >= n) return;
   if (d_bounds) { min_blur = d_bounds[0]; max_blur = d_bounds[1]; }
   const float maximum_idx = max_blur * (float)n, minimum_idx = min_blur * (float)n;
@@ -225,9 +227,14 @@ __global__ void ex_flags_kernel(int n, const int* __restrict__ pt_type, const in
 __global__ void ex_scatter_kernel(int n, const float4* __restrict__ raw, const float* __restrict__ time_stamp, const unsigned long long* __restrict__ packed,
                                   const unsigned long long* __restrict__ offs, float4* __restrict__ corners, float4* __restrict__ surf, float4* __restrict__ full, int* __restrict__ counts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned long long f = packed[i], o = offs[i];
-  float4 p = raw[i]; p.w = time_stamp[i];
+  const bool in = i < n;
+  const unsigned long long f = in ? packed[i] : 0ull, o = in ? offs[i] : 0ull;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f); if (in) { p = raw[i]; p.w = time_stamp[i]; }
+  // find_min_max_intensity over the full cloud (laser_mapping.hpp:1243-1253, :1336): min / max time stamp of the points that go to `full`
+  { const bool fl = (f >> 42) & 1ull; const int k = ts_ord(p.w);
+    const int mn = __reduce_min_sync(0xffffffffu, fl ? k : 0x7fffffff), mx = __reduce_max_sync(0xffffffffu, fl ? k : (int)0x80000000);
+    if ((threadIdx.x & 31) == 0 && mn != 0x7fffffff) { atomicMin(&counts[10], mn); atomicMax(&counts[11], mx); } }
+  if (!in) return;
   if (f & 1ull) corners[(int)(o & 0x1fffff)] = p;
   if (f & (1ull << 21)) surf[(int)((o >> 21) & 0x1fffff)] = p;
   if ((f & (1ull << 42)) && full) full[(int)((o >> 42) & 0x1fffff)] = p;
@@ -289,7 +296,7 @@ int launch_get_features(ll_ctx* ctx, const float* d_bounds, float min_blur, floa
   char* base = ctx->scratch.as<char>();
   unsigned long long* packed = (unsigned long long*)(base + o_p); unsigned long long* offs = (unsigned long long*)(base + o_o);
   const int blocks = ll_div_up(n, 256);
-  ex_flags_kernel<<<blocks, 256, 0, s>>>(n, e.pt_type, e.pt_label, e.depth_sq2, d_bounds, min_blur, max_blur, packed);
+  ex_flags_kernel<<<blocks, 256, 0, s>>>(n, e.pt_type, e.pt_label, e.depth_sq2, d_bounds, min_blur, max_blur, packed, d_counts);
   LL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(base + o_t, scan_bytes, packed, offs, n, s));
   ex_scatter_kernel<<<blocks, 256, 0, s>>>(n, e.raw, e.time_stamp, packed, offs, d_corners, d_surf, d_full, d_counts);
   ctx->launches += 4;

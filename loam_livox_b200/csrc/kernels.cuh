@@ -21,7 +21,8 @@ struct KnnBlocksArgs {
   double max_dis_line, max_dis_plane;
   int icp_line, icp_plane;
   float4* blk_a; double* blk_v;
-  int* corner_avail; int* surf_avail;
+  int* corner_avail; int* surf_avail; int* n_blocks;   // three consecutive counters in RegDevState, cleared before every launch
+  int cap, rng_seed;            // residual-block cap (pre-skip of features at 2 x cap, :232-238, :339-345)
   int* seed_ids;                // [M x 5] neighbour ids of the previous ICP iteration (-1 = none): seeds of the next search
   float* knn_d;                 // optional debug output [M x 5]
   const int* perm;              // spatially sorted feature order (corners then surfaces), or null = caller order
@@ -57,8 +58,11 @@ struct RegDevState {
   double q_last_opt[4], t_last_opt[3];   // q_last_optimize / t_last_optimize of the ICP loop
   double bound, huber_a, inliner_dis, inlier_ratio, min_icp_R, min_icp_T;
   double inlier_threshold, angular_diff, t_diff, final_cost, initial_cost;
-  int corner_avail, surf_avail, icp_done, icp_iter, num_residual_blocks, status, total_lm_iterations, total_evaluations;
+  int corner_avail, surf_avail, n_blocks, icp_done, icp_iter, num_residual_blocks, status, total_lm_iterations, total_evaluations;
   int n_unique; int if_motion_deblur;
+  // residual-block cap: m_maximum_allow_residual_block, the seed of ll_cap_uniform_f, and the number of blocks the kNN kernel of this ICP
+  // iteration emitted (n_blocks, next to corner_avail: this rank; n_blocks_all: all ranks, = n_blocks unless the map is sharded)
+  int cap, rng_seed, n_blocks_all;
   // motion deblur (N1): time-stamp range of refine_blur, and compute_interpolatation_rodrigue's outputs (:607-620) after every solve #2
   double min_ts, max_ts, interp_theta, interp_hat[9], interp_hat_sq[9];
   unsigned int bar_count, bar_gen;
@@ -83,19 +87,24 @@ struct SolveArgs {
   int rank, world; double* comm_local; double* comm_peer[8];
   // mode 4 (one launch per ICP iteration: solve #1 -> K10 -> solve #2)
   int prerun_iterations; unsigned long long* table; unsigned table_mask; double* uniq; int* n_uniq;
+  int cap_check;             // 1: the block count can exceed the cap (host: slots > cap): apply the drop rule (:434-458) while staging
   int deblur;                // 1: *_mb functors (ceres_icp.hpp:81-233), s per block from the feature's time stamp
 };
 // Layout of the IPC-exported staging buffer of a rank (ll_comm_local_handle):
 //   [0, 8192)            2 parities x 8 ranks x 64 doubles: the 29 sums of one evaluation + a generation flag at double index 32
-//   [8192, 8192+256)     control words: [0] comm_gen (local, monotonic over the life of the context: never reset, so a stale flag can never
+//   [8192, 8192+1024)    control words ([3] count-exchange generation (local), [64..80) 2 parities x 8 block counts written by the peers,
+//                        [80..88) count-exchange flags written by the peers): [0] comm_gen (local, monotonic over the life of the context: never reset, so a stale flag can never
 //                        match), [1] exchange generation (local), [2] block counter (local), [16..24) exchange flags written by the peers
 //   [16384, ...)         L1 exchange buffer X: one double per residual-block slot (max_features)
 #define LL_COMM_CTRL_OFF 8192
 #define LL_COMM_X_OFF 16384
 int launch_solve(ll_ctx* ctx, const SolveArgs& a);
+int solve_prepare(ll_ctx* ctx);   // once per context: opt the solver kernels in to their dynamic shared memory
 // Sharded mode, K10: every rank pushes the loss-corrected L1 norms of the slots it owns into every peer's X buffer (NVLink stores), then a
 // flag barrier; afterwards X is identical on all ranks (NaN where nobody produced a block).
 int launch_l1_exchange(ll_ctx* ctx, const double* d_l1, int M);
+// Sharded mode, residual-block cap: all ranks' block counts of this ICP iteration summed into RegDevState::n_blocks_all (peer stores + flags).
+int launch_count_exchange(ll_ctx* ctx);
 int solve_max_slots(ll_ctx* ctx);
 
 // ---------------------------------------------------------------------------------------------- clouds (cloud.cu)

@@ -443,6 +443,7 @@ __device__ __forceinline__ void emit_block(const KnnBlocksArgs& a, const TreeVie
       }
     }
   }
+  if (type != 0) atomicAdd(a.n_blocks, 1);   // residual_block_ids.size() of this ICP iteration (the cap's drop rule needs it, :436)
   a.blk_a[w] = make_float4((float)ax, (float)ay, (float)az, __int_as_float(type));
   a.blk_v[(size_t)w * 3 + 0] = vx; a.blk_v[(size_t)w * 3 + 1] = vy; a.blk_v[(size_t)w * 3 + 2] = vz;
 }
@@ -481,10 +482,17 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a
       qx = (float)(ox + st->pose_last[4]); qy = (float)(oy + st->pose_last[5]); qz = (float)(oz + st->pose_last[6]);
     }
   }
+  // Non-finite features: the corner loop skips them explicitly (:242-245); the surface loop does not (:347-351), but a NaN query makes every
+  // squared distance NaN and `NaN < 50.0` (:353) rejects the match, so the block set is the same.
   const bool finite_in = isfinite(f.x) && isfinite(f.y) && isfinite(f.z);
   bool owned = true;
   if (a.world > 1) owned = cell_owner(qx, qy, qz, a.inv_cell, a.world) == (unsigned)a.rank;
-  const bool active = have && owned && finite_in;
+  // Residual-block cap, pre-skip (:232-238 corners, :339-345 surfaces): with N features of this class and N > 2 cap, a feature is skipped when
+  // rand * N > 2 cap (float arithmetic, like m_rand_float), before it is transformed or searched.  Drawn per (seed, ICP iteration, class, index).
+  bool skipped = false;
+  { const int ncls = is_corner ? a.n_corner : a.n_surf;
+    if (have && ncls > 2 * a.cap) skipped = ll_cap_uniform_f(a.rng_seed, a.st->icp_iter, is_corner ? 0 : 1, is_corner ? w : w - a.n_corner) * (float)ncls > (float)(2 * a.cap); }
+  const bool active = have && owned && finite_in && !skipped;
   Top5 t;
   group_knn5(tv, stacks[threadIdx.x / GROUP], active, qx, qy, qz, t, (a.seed_ids && have) ? a.seed_ids + (size_t)w * LL_KNN : nullptr);
 

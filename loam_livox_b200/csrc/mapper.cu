@@ -28,6 +28,7 @@ struct ll_mapper {
   ll_cellmap* cells_corner = nullptr; ll_cellmap* cells_surf = nullptr;
   ll_map* match_map = nullptr;
   int frame_index = 0;
+  double last_time_stamp = 0;   // m_last_time_stamp (laser_mapping.hpp:140)
   double q_w_curr[4] = {1, 0, 0, 0}, t_w_curr[3] = {0, 0, 0};
   DevBuf work;   // transformed / down-sampled feature clouds
   DevBuf snap;   // match-map snapshot clouds (corner, surf) between refreshes
@@ -90,6 +91,11 @@ int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int
   if (stats) { stats->n_corner = nc; stats->n_surf = ns; stats->ms_front_end = (float)(now_ms() - tp); }
   tp = now_ms();
   if (dropped) return LL_OK;                                                     // laser_feature_extractor.hpp:287
+  // :1336-1350: the time-stamp range of this scan comes from the full cloud (min of refine_blur = the previous scan's maximum), and
+  // init_pointcloud_registration copies m_current_frame_index BEFORE it is incremented
+  const int frame_index_for_reg = m->frame_index;
+  const double minimum_pt_time_stamp = m->last_time_stamp, maximum_pt_time_stamp = (double)ctx->last_full_max_t;
+  m->last_time_stamp = maximum_pt_time_stamp;
   m->frame_index++;                                                              // m_current_frame_index++ (:1350)
   // ---- update_buff_for_matching (mode 1): snapshot of the cells in range and in the FOV, whole-map VoxelGrid, index
   if (m->map_dirty) {
@@ -122,7 +128,9 @@ int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int
   int hc[2] = {0, 0};
   // ---- init_pointcloud_registration + find_out_incremental_transfrom (:1266-1297, :1405)
   ll_reg_state st = m->cfg.reg;
-  st.current_frame_index = m->frame_index;
+  st.current_frame_index = frame_index_for_reg;
+  st.minimum_pt_time_stamp = minimum_pt_time_stamp; st.maximum_pt_time_stamp = maximum_pt_time_stamp;   // :1287-1288
+  st.rng_seed = m->cfg.reg.rng_seed + frame_index_for_reg;   // a fresh Point_cloud_registration (and m_rand_float) per scan (:1348)
   for (int k = 0; k < 4; k++) { st.q_w_last[k] = m->q_w_curr[k]; st.q_w_curr[k] = m->q_w_curr[k]; }
   for (int k = 0; k < 3; k++) { st.t_w_last[k] = m->t_w_curr[k]; st.t_w_curr[k] = m->t_w_curr[k]; }
   st.para_buffer_incremental[0] = st.para_buffer_incremental[1] = st.para_buffer_incremental[2] = 0; st.para_buffer_incremental[3] = 1;

@@ -481,11 +481,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
     thr = fmax(st->inliner_dis, rt);
     if (blockIdx.x == 0 && tid == 0) st->inlier_threshold = thr;
   }
+  // Residual-block cap, drop rule (:434-458): with M blocks and M > cap, block i leaves the problem when rand_i > (float)cap / (float)M.
+  float cap_keep = 2.0f; int cap_iter = 0, cap_seed = 0;
+  if (a.cap_check) {
+    const int nb = a.world > 1 ? st->n_blocks_all : st->n_blocks;
+    if (nb > st->cap) cap_keep = (float)st->cap / (float)nb;
+    cap_iter = st->icp_iter; cap_seed = st->rng_seed;
+  }
   for (int k = 0; k < tiles_per_cta; k++) {
     const int i = (blockIdx.x + gridDim.x * k) * tile + tid, li = k * SOLVE_THREADS + tid;   // tile <= SOLVE_THREADS slots per CTA and pass: threads >= tile idle
     int type = 0;
     if (i < a.M && tid < tile) {
       const float4 ba = a.blk_a[i]; type = __float_as_int(ba.w);
+      if (type != 0 && cap_keep <= 1.0f && ll_cap_uniform_f(cap_seed, cap_iter, 2, i) > cap_keep) type = 0;
       if (type != 0 && a.mode == 1 && (a.l1[i] > thr)) type = 0;
       if (type != 0) {
         const float4 f = a.feat[i];
@@ -737,8 +745,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
 #define SOLVE_MAX_SMEM (200 * 1024)
 int solve_max_slots(ll_ctx* ctx) { return ctx->num_sms * ((SOLVE_MAX_SMEM / SLOT_BYTES) / SOLVE_THREADS) * SOLVE_THREADS; }
 
+int solve_prepare(ll_ctx* ctx) {
+  LL_CUDA(ctx, cudaFuncSetAttribute((void*)lm_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_MAX_SMEM));
+  LL_CUDA(ctx, cudaFuncSetAttribute((void*)lm_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_MAX_SMEM));
+  return LL_OK;
+}
 int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
-  static bool attr_set[64][2] = {{false, false}};
   // The evaluation is fp64-throughput bound (64 DFMA/clk/SM): spread the slots over ALL SMs, even when that leaves CTAs partly empty.
   // tile = slots per CTA and pass (a multiple of 32, <= SOLVE_THREADS); measured: 61 full CTAs 8.3 us/evaluation, 148 CTAs x 224 slots 3.5 us.
   const int M1 = a.M > 0 ? a.M : 1;
@@ -750,10 +762,6 @@ int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
   const size_t smem = (size_t)tiles_per_cta * SOLVE_THREADS * (mb ? SLOT_BYTES_MB : SLOT_BYTES);
   if (smem > SOLVE_MAX_SMEM) { ctx->set_error("too many residual-block slots for the shared-memory-resident solver"); return LL_ERR_CAPACITY; }
   void* fn = mb ? (void*)lm_solve_kernel<true> : (void*)lm_solve_kernel<false>;
-  if (ctx->device < 64 && !attr_set[ctx->device][mb]) {
-    LL_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_MAX_SMEM));
-    attr_set[ctx->device][mb] = true;
-  }
   SolveArgs args = a; void* kargs[] = {&args, &tiles_per_cta, &tile};
   LL_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SOLVE_THREADS), kargs, smem, ctx->stream));   // (an ordinary launch is not faster: measured)
   ctx->launches++;
@@ -780,6 +788,34 @@ __global__ void __launch_bounds__(256) l1_exchange_kernel(L1ExchangeArgs a) {
   __threadfence_system();
   for (int p = 0; p < a.world; p++) st_release_sys_u32((unsigned*)(a.comm_peer[p] + LL_COMM_CTRL_OFF) + 16 + a.rank, g);
   for (int p = 0; p < a.world; p++) { const unsigned* f = ctrl + 16 + p; while (ld_acquire_sys_u32(f) != g) {} }
+}
+// Residual-block cap in sharded mode: the drop probability depends on the number of blocks of ALL ranks.  One warp: push this rank's count into
+// every peer's slot (double-buffered by generation parity), flag, wait for every peer's flag, sum in rank order.
+struct CountExchangeArgs { RegDevState* st; int rank, world; char* comm_local; char* comm_peer[8]; };
+__global__ void count_exchange_kernel(CountExchangeArgs a) {
+  const int lane = threadIdx.x;
+  unsigned* ctrl = (unsigned*)(a.comm_local + LL_COMM_CTRL_OFF);
+  const unsigned g = ctrl[3] + 1u; const int par = g & 1u;
+  if (lane < a.world) {
+    unsigned* pc = (unsigned*)(a.comm_peer[lane] + LL_COMM_CTRL_OFF);
+    pc[64 + par * 8 + a.rank] = (unsigned)a.st->n_blocks;
+    __threadfence_system();
+    st_release_sys_u32(pc + 80 + a.rank, g);
+    while (ld_acquire_sys_u32(ctrl + 80 + lane) != g) {}
+  }
+  __syncwarp();
+  if (lane == 0) {
+    int tot = 0; for (int p = 0; p < a.world; p++) tot += (int)*((volatile unsigned*)(ctrl + 64 + par * 8 + p));
+    a.st->n_blocks_all = tot; ctrl[3] = g;
+  }
+}
+int launch_count_exchange(ll_ctx* ctx) {
+  if (ctx->world <= 1) return LL_OK;
+  CountExchangeArgs a; a.st = ctx->d_reg; a.rank = ctx->rank; a.world = ctx->world; a.comm_local = (char*)ctx->comm_local;
+  for (int i = 0; i < 8; i++) a.comm_peer[i] = (char*)ctx->comm_peers[i];
+  count_exchange_kernel<<<1, 32, 0, ctx->stream>>>(a); ctx->launches++;
+  LL_CUDA(ctx, cudaGetLastError());
+  return LL_OK;
 }
 int launch_l1_exchange(ll_ctx* ctx, const double* d_l1, int M) {
   if (ctx->world <= 1 || M == 0) return LL_OK;

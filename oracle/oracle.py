@@ -21,7 +21,7 @@ i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 class RegParams(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("if_motion_deblur", "current_frame_index", "mapping_init_accumulate_frames", "icp_max_iterations",
-                                       "cere_max_iterations", "cere_prerun_times", "icp_plane", "icp_line", "maximum_allow_residual_block", "num_threads")] + \
+                                       "cere_max_iterations", "cere_prerun_times", "icp_plane", "icp_line", "maximum_allow_residual_block", "num_threads", "rng_seed", "_pad")] + \
                [(n, C.c_double) for n in ("para_max_angular_rate", "para_max_speed", "max_final_cost", "minimum_pt_time_stamp", "maximum_pt_time_stamp",
                                           "minimum_icp_R_diff", "minimum_icp_T_diff", "inliner_dis", "inlier_ratio", "maximum_dis_plane_for_match",
                                           "maximum_dis_line_for_match", "huber_a")] + \
@@ -96,6 +96,8 @@ def lib():
     so = build()   # rebuilds only when a source is newer than the library
     L = C.CDLL(so)
     L.orc_hw_threads.restype = C.c_int
+    L.orc_cap_uniform.argtypes = [C.c_int] * 4
+    L.orc_cap_uniform.restype = C.c_float
     L.orc_voxel_grid.argtypes = [f32p, C.c_int, C.c_float, f32p]
     L.orc_voxel_grid.restype = C.c_int
     L.orc_kdtree_build.argtypes = [f32p, C.c_int]
@@ -348,6 +350,7 @@ class Mapper:
         self.q = np.array(list(self.params.q_w_curr), np.float64)
         self.t = np.array(list(self.params.t_w_curr), np.float64)
         self.frame_index = 0
+        self.last_time_stamp = 0.0
         self.dirty = False
         self.map_c = self.map_s = None
         self.tree_c = self.tree_s = None
@@ -356,9 +359,14 @@ class Mapper:
 
     def process_scan(self, raw, stamp):
         self.ex.extract(raw, stamp)
-        c, s, _ = self.ex.get_features(0.0, 1.0)
+        c, s, full = self.ex.get_features(0.0, 1.0)
         c = voxel_grid(voxel_grid(c, self.leaf_c), self.line_resolution)       # laser_feature_extractor.hpp:379-380 then laser_mapping.hpp:1367-1370
         s = voxel_grid(voxel_grid(s, self.leaf_s), self.plane_resolution)      # :372-373 then :1371-1373
+        # :1336-1350: time-stamp range from the full cloud; init_pointcloud_registration sees the frame index BEFORE the increment
+        max_t = max(np.float32(-10000.0), full[:, 3].max()) if full.shape[0] else np.float32(-10000.0)   # find_min_max_intensity (:1243-1253)
+        min_ts, max_ts = self.last_time_stamp, float(max_t)
+        self.last_time_stamp = float(max_t)
+        frame_index_for_reg = self.frame_index
         self.frame_index += 1
         if self.dirty:
             mc, fc = self.cells_corner.assemble(self.q, self.t, self.search_range, self.fov_angle, self.line_resolution, self.replace)
@@ -371,7 +379,9 @@ class Mapper:
         status, res = 1, None
         if self.tree_c is not None and self.tree_s is not None:
             p = RegParams.from_buffer_copy(self.params)
-            p.current_frame_index = self.frame_index
+            p.current_frame_index = frame_index_for_reg
+            p.minimum_pt_time_stamp, p.maximum_pt_time_stamp = min_ts, max_ts
+            p.rng_seed = self.params.rng_seed + frame_index_for_reg
             p.num_threads = self.threads
             p.q_w_last[:] = list(self.q); p.q_w_curr[:] = list(self.q)
             p.t_w_last[:] = list(self.t); p.t_w_curr[:] = list(self.t)

@@ -17,11 +17,12 @@ extern "C" {
 
 int orc_hw_threads() {
 #ifdef _OPENMP
-  return omp_get_max_threads();
+  return omp_get_num_procs();   // not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 and the caller passes its team size explicitly
 #else
   return 1;
 #endif
 }
+float orc_cap_uniform(int seed, int icp_iter, int stream, int index) { return cap_uniform(seed, icp_iter, stream, index); }
 
 // ---------------------------------------------------------------- VoxelGrid / kNN
 int orc_voxel_grid(const float* in, int n, float leaf, float* out) { return voxel_grid(in, n, leaf, out); }
@@ -74,7 +75,7 @@ double orc_extractor_current_time(void* ev) { return ((Extractor*)ev)->current_t
 // C mirror of RegParams/RegResult (plain doubles/ints so ctypes stays trivial)
 struct orc_reg_params {
   int if_motion_deblur, current_frame_index, mapping_init_accumulate_frames, icp_max_iterations, cere_max_iterations, cere_prerun_times;
-  int icp_plane, icp_line, maximum_allow_residual_block, num_threads;
+  int icp_plane, icp_line, maximum_allow_residual_block, num_threads, rng_seed, _pad;
   double para_max_angular_rate, para_max_speed, max_final_cost, minimum_pt_time_stamp, maximum_pt_time_stamp;
   double minimum_icp_R_diff, minimum_icp_T_diff, inliner_dis, inlier_ratio, maximum_dis_plane_for_match, maximum_dis_line_for_match, huber_a;
   double q_w_last[4], t_w_last[3], q_w_curr[4], t_w_curr[3], para_buffer_incremental[7];
@@ -87,7 +88,7 @@ struct orc_reg_result {
 static RegParams to_params(const orc_reg_params* p) {
   RegParams P; P.if_motion_deblur = p->if_motion_deblur; P.current_frame_index = p->current_frame_index; P.mapping_init_accumulate_frames = p->mapping_init_accumulate_frames;
   P.icp_max_iterations = p->icp_max_iterations; P.cere_max_iterations = p->cere_max_iterations; P.cere_prerun_times = p->cere_prerun_times; P.icp_plane = p->icp_plane; P.icp_line = p->icp_line;
-  P.maximum_allow_residual_block = p->maximum_allow_residual_block; P.num_threads = p->num_threads < 1 ? 1 : p->num_threads;
+  P.maximum_allow_residual_block = p->maximum_allow_residual_block; P.num_threads = p->num_threads < 1 ? 1 : p->num_threads; P.rng_seed = p->rng_seed;
   P.para_max_angular_rate = (float)p->para_max_angular_rate; P.para_max_speed = (float)p->para_max_speed; P.max_final_cost = (float)p->max_final_cost;
   P.minimum_pt_time_stamp = (float)p->minimum_pt_time_stamp; P.maximum_pt_time_stamp = (float)p->maximum_pt_time_stamp;
   P.minimum_icp_R_diff = p->minimum_icp_R_diff; P.minimum_icp_T_diff = p->minimum_icp_T_diff; P.inliner_dis = p->inliner_dis; P.inlier_ratio = p->inlier_ratio;

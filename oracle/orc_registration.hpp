@@ -6,10 +6,13 @@
 //     :622-661 pointAssociateToMap (+ :607-620 compute_interpolatation_rodrigue, :128-141 refine_blur)
 //     :153-161 compute_inlier_residual_threshold
 //   state hand-off  /root/reference/source/laser_mapping.hpp:1266-1297 init_pointcloud_registration
-// Deviation (documented): the reference drops residual blocks at random (std::random_device seeded) when
-// their number exceeds m_maximum_allow_residual_block (:232-238,:339-345,:438-458). The oracle implements the
-// cap deterministically OFF: parity is only defined when the cap does not bind; if it would
-// bind the oracle reports status -2.
+// Residual-block cap (:232-238,:339-345,:434-458): the reference draws from a std::random_device-seeded mt19937
+// (include/tools/tools_random.hpp:18-25), which no second implementation can reproduce.  The RULE is restated exactly
+// (pre-skip of a feature when rand*N > 2*cap with N the feature count of its class; after the block list is built, when its size M exceeds
+// the cap, block i is dropped when rand_i > (float)cap/(float)M), and the random numbers come from a counter-based generator
+// cap_uniform(seed, icp_iteration, stream, index) with a caller-supplied seed (RegParams::rng_seed), so that the CUDA path can draw the
+// very same numbers: stream 0 / 1 = corner / surface pre-skip (index = feature index), stream 2 = drop (index = slot of the block =
+// feature index, surfaces offset by the corner count; the reference indexes its array by list position, an i.i.d. relabelling).
 #pragma once
 #include <set>
 #include <vector>
@@ -36,7 +39,15 @@ struct RegParams {  // fields init_pointcloud_registration copies + the members 
   double t_w_curr[3] = {0, 0, 0};
   double para_buffer_incremental[7] = {0, 0, 0, 1, 0, 0, 0};  // q (x,y,z,w), t
   int num_threads = 1;  // CPU-baseline knob (reference is single-threaded)
+  int rng_seed = 0;     // seed of the counter-based generator that stands in for m_rand_float (see the header comment)
 };
+
+// Counter-based uniform float in [0,1): splitmix64 finaliser over (seed, ICP iteration, stream, index), top 24 bits.
+inline float cap_uniform(int seed, int icp_iter, int stream, int index) {
+  unsigned long long z = (unsigned long long)(unsigned)seed * 0x9E3779B97F4A7C15ull + (((unsigned long long)(unsigned)icp_iter << 40) | ((unsigned long long)(unsigned)stream << 32) | (unsigned long long)(unsigned)index);
+  z ^= z >> 30; z *= 0xbf58476d1ce4e5b9ull; z ^= z >> 27; z *= 0x94d049bb133111ebull; z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
 
 struct RegResult {
   int status = 1;  // return value of find_out_incremental_transfrom: 1 accepted-or-skipped, 0 rejected
@@ -112,7 +123,7 @@ struct Registration {
 
   // Builds the residual blocks of one ICP iteration (:230-432). knn_*: precomputed trees.
   void build_blocks(const float* map_c, const KdTree& tree_c, const float* map_s, const KdTree& tree_s,
-                    const float* scan_c, int nc, const float* scan_s, int ns, std::vector<ResidualBlock>& blocks, int* corner_avail, int* surf_avail) const {
+                    const float* scan_c, int nc, const float* scan_s, int ns, std::vector<ResidualBlock>& blocks, int* corner_avail, int* surf_avail, int icp_iter = 0) const {
     const int K = 5; const int if_undistore_in_matching = 1;
     std::vector<int> c_idx((size_t)nc * K, -1), s_idx((size_t)ns * K, -1); std::vector<float> c_d((size_t)nc * K, 0.f), s_d((size_t)ns * K, 0.f);
     std::vector<int> c_found(nc, 0), s_found(ns, 0);
@@ -120,6 +131,7 @@ struct Registration {
 #pragma omp parallel for num_threads(P.num_threads) schedule(dynamic, 256) if (P.num_threads > 1)
     for (int i = 0; i < nc; i++) {
       const float* po = scan_c + (size_t)i * 4;
+      if (nc > 2 * P.maximum_allow_residual_block && cap_uniform(P.rng_seed, icp_iter, 0, i) * nc > 2 * P.maximum_allow_residual_block) { c_found[i] = -1; continue; }  // :232-238
       if (!std::isfinite(po[0]) || !std::isfinite(po[1]) || !std::isfinite(po[2])) { c_found[i] = -1; continue; }
       pointAssociateToMap(po, &c_sel[(size_t)i * 4], refine_blur(po[3], P.minimum_pt_time_stamp, P.maximum_pt_time_stamp), if_undistore_in_matching);
       c_found[i] = tree_c.knn(&c_sel[(size_t)i * 4], K, &c_idx[(size_t)i * K], &c_d[(size_t)i * K]);
@@ -127,6 +139,7 @@ struct Registration {
 #pragma omp parallel for num_threads(P.num_threads) schedule(dynamic, 256) if (P.num_threads > 1)
     for (int i = 0; i < ns; i++) {
       const float* po = scan_s + (size_t)i * 4;
+      if (ns > 2 * P.maximum_allow_residual_block && cap_uniform(P.rng_seed, icp_iter, 1, i) * ns > 2 * P.maximum_allow_residual_block) { s_found[i] = -1; continue; }  // :339-345
       pointAssociateToMap(po, &s_sel[(size_t)i * 4], refine_blur(po[3], P.minimum_pt_time_stamp, P.maximum_pt_time_stamp), if_undistore_in_matching);
       s_found[i] = tree_s.knn(&s_sel[(size_t)i * 4], K, &s_idx[(size_t)i * K], &s_d[(size_t)i * K]);
     }
@@ -175,8 +188,14 @@ struct Registration {
       Qd q_last_optimize{1, 0, 0, 0}; V3d t_last_optimize{0, 0, 0};
       for (iterCount = 0; iterCount < P.icp_max_iterations; iterCount++) {
         Problem prob; prob.q_last = q_w_last; prob.t_last = t_w_last; prob.huber_a = P.huber_a; prob.t_bound = P.para_max_speed; prob.num_threads = P.num_threads;
-        build_blocks(map_c, tree_c, map_s, tree_s, scan_c, nc, scan_s, ns, prob.blocks, &corner_avail, &surf_avail);
-        if (nc > 2 * P.maximum_allow_residual_block || ns > 2 * P.maximum_allow_residual_block || (int)prob.blocks.size() > P.maximum_allow_residual_block) { out->status = -2; return -2; }
+        build_blocks(map_c, tree_c, map_s, tree_s, scan_c, nc, scan_s, ns, prob.blocks, &corner_avail, &surf_avail, iterCount);
+        if (prob.blocks.size() > (size_t)P.maximum_allow_residual_block) {  // :434-458 drop some of the residual blocks
+          const float threshold_to_reserve = (float)P.maximum_allow_residual_block / (float)prob.blocks.size();
+          std::vector<ResidualBlock> kept0; kept0.reserve(prob.blocks.size());
+          for (const ResidualBlock& b : prob.blocks)
+            if (!(cap_uniform(P.rng_seed, iterCount, 2, b.src == 0 ? b.src_index : nc + b.src_index) > threshold_to_reserve)) kept0.push_back(b);
+          prob.blocks.swap(kept0);
+        }
         IcpIterTrace tr{}; tr.corner_avail = corner_avail; tr.surf_avail = surf_avail; tr.blocks_before_select = (int)prob.blocks.size();
         if (prob.blocks.empty()) { out->status = -3; return -3; }  // reference would dereference an empty std::set (:160)
         SolveOptions so; so.max_num_iterations = P.cere_prerun_times;  // :466-467

@@ -278,11 +278,63 @@ def test_register_edge_cases(ctx, oracle):
     reg3.set_pose(pose.q, pose.t)
     with pytest.raises(LoamLivoxError):
         reg3.find_out_incremental_transfrom(m, far[:50], far)
-    # the residual-block cap would bind -> refused (the reference drops blocks at random there)
-    reg4 = Point_cloud_registration(ctx, maximum_allow_residual_block=100)
-    reg4.set_pose(pose.q, pose.t)
-    with pytest.raises(LoamLivoxError):
-        reg4.find_out_incremental_transfrom(m, fc, fs)
+
+
+# ---------------------------------------------------------------------------------------------- a12 (i): residual-block cap
+@pytest.mark.parametrize("cap,seed", [(200, 0), (200, 7), (150, 1), (3000, 2)])
+def test_residual_cap_parity(ctx, oracle, cap, seed):
+    """maximum_allow_residual_block of the shipped YAMLs (200 / 150; 3000 = only the drop rule binds, not the pre-skip): the pre-skipped feature set,
+    the dropped block set (same counter-based draws as the oracle), the block counts of every ICP iteration and the pose."""
+    from loam_livox_b200.registration import Map, Point_cloud_registration
+    mc, ms, fc, fs, pose = _mk(5000, 45000, 1000, 9000)
+    m = Map(ctx, mc, ms)
+    tc, ts = oracle.KdTree(mc), oracle.KdTree(ms)
+    guess = S.perturb_pose(pose, np.random.default_rng(seed))
+    kw = dict(maximum_allow_residual_block=cap, rng_seed=seed)
+    p = oracle.default_params(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t, **kw)
+    # pre-skip (:232-238, :339-345): the features that reach the kNN search in ICP iteration 0
+    reg = Point_cloud_registration(ctx, **kw)
+    reg.set_pose(guess.q, guess.t)
+    typ, a3, v3, ca, sa = reg.build_blocks(m, fc, fs)
+    blocks, src, oca, osa = oracle.build_blocks(mc, tc, ms, ts, fc, fs, p)
+    slot = src[:, 1] + np.where(src[:, 0] == 1, fc.shape[0], 0)
+    assert (ca, sa) == (oca, osa) and np.array_equal(np.nonzero(typ)[0], slot)
+    if fs.shape[0] > 2 * cap:
+        assert 0.7 * 2 * cap < sa < 1.3 * 2 * cap      # keep probability 2 cap / N
+    # whole registration: same block counts after the drop (:434-458) and after the inlier selection, same pose
+    st = reg.find_out_incremental_transfrom(m, fc, fs)
+    ost, ores, tr = oracle.register(mc, tc, ms, ts, fc, fs, p, want_trace=True)
+    r = reg.result
+    assert st == ost == 1 and r.icp_iterations == ores.icp_iterations
+    assert (r.corner_used, r.surf_used, r.num_residual_blocks) == (ores.corner_used, ores.surf_used, ores.num_residual_blocks)
+    assert all(t.blocks_before_select <= 1.3 * cap for t in tr)
+    dt = np.linalg.norm(np.array(r.t_w_curr) - np.array(ores.t_w_curr))
+    da = S.quat_angle(np.array(r.q_w_curr), np.array(ores.q_w_curr))
+    assert dt < 1e-7 and da < 1e-7, (dt, da)
+    assert abs(r.final_cost - ores.final_cost) <= 1e-7 * ores.final_cost
+    # a different seed draws a different subset
+    reg2 = Point_cloud_registration(ctx, maximum_allow_residual_block=cap, rng_seed=seed + 1)
+    reg2.set_pose(guess.q, guess.t)
+    typ2 = reg2.build_blocks(m, fc, fs)[0]
+    assert (fc.shape[0] <= 2 * cap and fs.shape[0] <= 2 * cap) or not np.array_equal(typ2 != 0, typ != 0)
+
+
+def test_shipped_yaml_values_run(ctx, oracle):
+    """ll_reg_state_yaml: cap 200 / 150 and max_allow_final_cost 2.0 -- the library must register a real scan under the reference's own configs."""
+    from loam_livox_b200 import capi
+    from loam_livox_b200.registration import Map, Point_cloud_registration
+    mc, ms, fc, fs, pose = _mk(5000, 45000, 1000, 9000)
+    m = Map(ctx, mc, ms)
+    for realtime in (False, True):
+        y = capi.yaml_reg_state(realtime)
+        assert (y.maximum_allow_residual_block, y.max_final_cost) == (150 if realtime else 200, 2.0)
+        guess = S.perturb_pose(pose, np.random.default_rng(11))
+        reg = Point_cloud_registration(ctx)
+        reg.state = capi.yaml_reg_state(realtime, rng_seed=5)
+        reg.set_pose(guess.q, guess.t)
+        assert reg.find_out_incremental_transfrom(m, fc, fs) == 1 and reg.result.registered == 1
+        assert reg.result.num_residual_blocks <= 1.3 * y.maximum_allow_residual_block
+        assert np.linalg.norm(np.array(reg.result.t_w_curr) - pose.t) < 0.03
 
 
 # ---------------------------------------------------------------------------------------------- a14: device cell map, streaming mapper (C3)
@@ -337,7 +389,7 @@ def test_streaming_mapper_parity(ctx, oracle):
     """Config C3 in small: the device mapper against the oracle's process_new_scan loop, scan by scan (pose within 1e-4 m / 1e-4 rad)."""
     from loam_livox_b200 import capi
     from loam_livox_b200.registration import Laser_mapping
-    poses = S.trajectory(n_scans=9, n_static=3, speed=1.0)
+    poses = S.trajectory(n_scans=9, n_static=4, speed=1.0)
     reg = capi.default_reg_state(mapping_init_accumulate_frames=3)
     gm = Laser_mapping(ctx, reg=reg)
     om = oracle.Mapper(oracle.default_params(mapping_init_accumulate_frames=3, num_threads=4), threads=4)
@@ -352,6 +404,9 @@ def test_streaming_mapper_parity(ctx, oracle):
         q, t, f = gm.pose()
         assert f == om.frame_index
         assert np.linalg.norm(t - ot) < 1e-4 and S.quat_angle(q, oq) < 1e-4, (k, t, ot)
+        # init_pointcloud_registration copies m_current_frame_index BEFORE the increment (laser_mapping.hpp:1349-1350): with
+        # mapping_init_accumulate_frames = 3 the scans with index 0..3 are inserted unregistered, index 4 is the first ICP
+        assert res.registered == (1 if k > 3 else 0), k
         if om.last["res"] is not None and om.last["res"].registered:
             assert res.registered == 1 and res.icp_iterations == om.last["res"].icp_iterations
     assert gm.pose()[2] == 9
@@ -363,7 +418,7 @@ def test_streaming_mapper_long_sequence(ctx, oracle):
     together (pose 1e-4, identical feature / map / append counts) all the way."""
     from loam_livox_b200 import capi
     from loam_livox_b200.registration import Laser_mapping
-    poses = S.trajectory(n_scans=60, n_static=3, speed=2.0, yaw_rate_deg=20.0)
+    poses = S.trajectory(n_scans=60, n_static=4, speed=2.0, yaw_rate_deg=20.0)
     gm = Laser_mapping(ctx, reg=capi.default_reg_state(mapping_init_accumulate_frames=3))
     om = oracle.Mapper(oracle.default_params(mapping_init_accumulate_frames=3, num_threads=4), threads=4)
     worst = 0.0

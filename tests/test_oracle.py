@@ -268,3 +268,39 @@ def test_deblur_registration_recovers_motion_of_distorted_scan(oracle):
         errs[mode] = (np.linalg.norm(np.array(res.t_w_curr) - curr.t), S.quat_angle(np.array(res.q_w_curr), curr.q))
     assert errs[1][0] < 0.01 and errs[1][1] < 2e-3, errs
     assert errs[1][0] < 0.5 * errs[0][0], errs
+
+
+# ---------------------------------------------------------------------------------------------- a12 (i): residual-block cap
+def test_cap_generator_pinned_between_oracle_and_library(oracle):
+    """The counter-based uniform generator that stands in for the reference's std::random_device-seeded m_rand_float (tools_random.hpp:18-25) is
+    implemented twice (oracle/orc_registration.hpp, csrc/common.cuh): same bits for every (seed, iteration, stream, index); plausible uniformity."""
+    import itertools
+    from loam_livox_b200 import capi
+    L = capi.lib()   # host-side export, no GPU needed
+    for s, it, stream, i in itertools.product((0, 1, -5, 123456789), (0, 1, 7, 14), (0, 1, 2), (0, 1, 2, 999, 30000, 399999)):
+        a, b = L.ll_cap_uniform(s, it, stream, i), oracle.lib().orc_cap_uniform(s, it, stream, i)
+        assert a == b and 0.0 <= a < 1.0
+    u = np.array([L.ll_cap_uniform(3, 0, 2, i) for i in range(20000)])
+    assert abs(u.mean() - 0.5) < 0.01 and abs(u.std() - 12 ** -0.5) < 0.01
+    assert np.histogram(u, 10, (0, 1))[0].min() > 1800
+    # known answers (pins the constants of the hash)
+    assert [L.ll_cap_uniform(0, 0, 0, 0), L.ll_cap_uniform(1, 2, 1, 3)] == [0.0, oracle.lib().orc_cap_uniform(1, 2, 1, 3)]
+
+
+def test_cap_rule_in_the_oracle(oracle):
+    """point_cloud_registration.hpp:232-238,339-345,434-458 with the shipped caps (200 / 150): about 2 x cap features of a class survive the pre-skip,
+    about cap blocks survive the drop, the registration still converges; a cap above the feature count changes nothing."""
+    mc, ms = S.make_map(5000, 45000)
+    pose = S.default_pose()
+    fc, fs = S.make_features(1000, 9000, pose)
+    tc, ts = oracle.KdTree(mc), oracle.KdTree(ms)
+    guess = S.perturb_pose(pose, np.random.default_rng(0))
+    base = dict(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t)
+    _, full = oracle.register(mc, tc, ms, ts, fc, fs, oracle.default_params(**base))
+    _, same = oracle.register(mc, tc, ms, ts, fc, fs, oracle.default_params(maximum_allow_residual_block=10000, rng_seed=9, **base))
+    assert np.array_equal(np.array(full.t_w_curr), np.array(same.t_w_curr))
+    for cap in (200, 150):
+        st, res, tr = oracle.register(mc, tc, ms, ts, fc, fs, oracle.default_params(maximum_allow_residual_block=cap, rng_seed=1, **base), want_trace=True)
+        assert st == 1 and 0.7 * 2 * cap < res.surf_used < 1.3 * 2 * cap and 0.7 * 2 * cap < res.corner_used < 1.3 * 2 * cap
+        assert all(0.7 * cap < t.blocks_before_select < 1.3 * cap for t in tr)
+        assert np.linalg.norm(np.array(res.t_w_curr) - pose.t) < 0.03

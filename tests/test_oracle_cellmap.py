@@ -77,7 +77,7 @@ def test_cellmap_assemble_matches_per_cell_voxelgrid(oracle):
 
 def test_streaming_mapper_tracks_trajectory(oracle):
     """Oracle end to end on a short C3 sequence: poses relative to the first scan within a few centimetres of ground truth."""
-    poses = S.trajectory(n_scans=9, n_static=3, speed=1.0)
+    poses = S.trajectory(n_scans=9, n_static=4, speed=1.0)
     p = oracle.default_params(mapping_init_accumulate_frames=3, num_threads=4)
     mp = oracle.Mapper(p, threads=4)
     R0, t0 = poses[0].R(), poses[0].t
@@ -88,7 +88,9 @@ def test_streaming_mapper_tracks_trajectory(oracle):
         assert st == 1
         t_true = R0.T @ (pose.t - t0)
         errs.append(np.linalg.norm(t - t_true))
-        if k < 3:
+        # the registration sees the frame index BEFORE process_new_scan increments it (laser_mapping.hpp:1349-1350): with
+        # mapping_init_accumulate_frames = 3, scans 0..3 are inserted unregistered and scan 4 is the first to run the ICP
+        if k <= 3:
             assert mp.last["res"] is None or mp.last["res"].registered == 0
         else:
             assert mp.last["res"].registered == 1
