@@ -99,11 +99,21 @@ int  ll_map_build(ll_ctx* ctx, const void* corner, size_t n_corner, const void* 
 int  ll_map_rebuild(ll_ctx* ctx, ll_map* map, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where);
 void ll_map_release(ll_map* map);
 size_t ll_map_size(const ll_map* map, int which /*0 corner, 1 surface*/);
-/* Multi-GPU: keep only the points whose cell (cell_size metres) is owned by `rank` of `world`, plus a halo of
- * sqrt(max_dis_line) / sqrt(max_dis_plane) metres.  ll_register then only emits residual
- * blocks for the queries whose cell this rank owns and all-reduces the normal equations (ll_comm_*). */
+/* Multi-GPU (config C4): every rank is given the same two clouds and keeps (copies to HBM and indexes) only its shard: the points of the cells
+ * it owns plus every point within halo_corner / halo_surf metres of one of those cells.  Cells are cubes of cell_size metres on a grid over the
+ * bounding box of the whole map; in Morton order they are cut into `world` contiguous ranges of (nearly) equal point count, rank r owns range r;
+ * border cells extend outwards without bound.  With halo >= sqrt(maximum_dis_line_for_match) (1.42 m) and sqrt(maximum_dis_plane_for_match)
+ * (7.07 m) -- the squared-distance gates of point_cloud_registration.hpp:64-65,254,353 -- every accepted correspondence has exactly the neighbours
+ * a search of the whole map finds (ll_register refuses gates wider than the halo).  ll_register on a sharded map emits residual blocks only for the
+ * features whose cell (at the current pose) this rank owns and all-reduces the normal equations inside the solver kernel (ll_comm_*).
+ * Indices returned by ll_knn on a sharded map refer to the shard's own compacted clouds. */
 int  ll_map_build_sharded(ll_ctx* ctx, const void* corner, size_t n_corner, const void* surf, size_t n_surf, int fmt, int where,
                           int rank, int world, float cell_size, float halo_corner, float halo_surf, ll_map** out);
+typedef struct { int rank, world; float cell_size, halo_corner, halo_surf; float origin[3]; int dims[3]; long long kept_corner, kept_surf, total_corner, total_surf; } ll_shard_info;
+/* Grid, halo and shard sizes of a map; owner_out (dims[0]*dims[1]*dims[2] ints, x fastest; may be NULL) receives the rank owning every cell. */
+int  ll_map_shard_info(const ll_map* map, ll_shard_info* info, int* owner_out, size_t owner_cap);
+/* The partition rule alone (pure host code): points per cell in, owner per cell out. */
+int  ll_shard_plan(const int* cell_counts, const int dims[3], int world, int* owner_out);
 
 /* Parity hook for pcl::KdTreeFLANN::nearestKSearch(k = 5) (point_cloud_registration.hpp:249,351): world-frame
  * queries in, 5 indices (into the cloud given to ll_map_build, -1 when fewer exist) and float squared distances out. */

@@ -25,7 +25,7 @@ EXPORTS = [
     "ll_map_build_sharded", "ll_knn", "ll_reg_state_default", "ll_register", "ll_build_blocks", "ll_normal_equations", "ll_solve", "ll_transform",
     "ll_scan_to_pose", "ll_comm_local_handle", "ll_comm_connect", "ll_launch_count", "ll_cellmap_create", "ll_cellmap_release", "ll_cellmap_append",
     "ll_cellmap_assemble", "ll_cellmap_stats", "ll_voxel_downsample_dev", "ll_transform_dev", "ll_last_features_dev", "ll_mapper_config_default", "ll_mapper_create", "ll_mapper_release",
-    "ll_mapper_process_scan", "ll_mapper_pose", "ll_map_rebuild", "ll_debug_solver_cycles", "ll_state_snapshot_bytes", "ll_set_point_layout", "ll_format_pose_log", "ll_reg_state_yaml", "ll_cap_uniform",
+    "ll_mapper_process_scan", "ll_mapper_pose", "ll_map_rebuild", "ll_debug_solver_cycles", "ll_state_snapshot_bytes", "ll_set_point_layout", "ll_format_pose_log", "ll_reg_state_yaml", "ll_cap_uniform", "ll_map_shard_info", "ll_shard_plan",
 ]
 
 
@@ -73,6 +73,11 @@ class MapperStats(C.Structure):
                [(n, C.c_float) for n in ("ms_front_end", "ms_refresh", "ms_register", "ms_append")]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("cell_size", C.c_float), ("halo_corner", C.c_float), ("halo_surf", C.c_float), ("origin", C.c_float * 3),
+                ("dims", C.c_int * 3), ("kept_corner", C.c_longlong), ("kept_surf", C.c_longlong), ("total_corner", C.c_longlong), ("total_surf", C.c_longlong)]
+
+
 class LoamLivoxError(RuntimeError):
     pass
 
@@ -106,6 +111,8 @@ def lib():
     L.ll_voxel_downsample.argtypes = [vp, vp, sz, ci, ci, cf, vp, C.POINTER(sz)]
     L.ll_map_build.argtypes = [vp, vp, sz, vp, sz, ci, ci, C.POINTER(vp)]
     L.ll_map_build_sharded.argtypes = [vp, vp, sz, vp, sz, ci, ci, ci, ci, cf, cf, cf, C.POINTER(vp)]
+    L.ll_map_shard_info.argtypes = [vp, C.POINTER(ShardInfo), vp, sz]
+    L.ll_shard_plan.argtypes = [vp, vp, ci, vp]
     L.ll_map_release.argtypes = [vp]
     L.ll_map_size.argtypes = [vp, ci]
     L.ll_map_size.restype = sz

@@ -299,7 +299,7 @@ int ll_map_build(ll_ctx* ctx, const void* corner, size_t nc, const void* surf, s
 void ll_map_release(ll_map* map) {
   if (!map) return;
   cudaSetDevice(map->device);
-  map->corner.storage.release(); map->surf.storage.release(); delete map;
+  map->corner.storage.release(); map->surf.storage.release(); map->shard_owner.release(); delete map;
 }
 size_t ll_map_size(const ll_map* map, int which) { return map ? (size_t)(which == 0 ? map->corner.n : map->surf.n) : 0; }
 
@@ -338,7 +338,7 @@ static KnnBlocksArgs knn_args(ll_ctx* ctx, const ll_map* map, const RegArrays& A
   a.seed_ids = A.knn_idx; a.knn_d = debug ? A.knn_d : nullptr; a.perm = A.perm;
   ctx->solve_world = (map->world > 1 && ctx->world > 1) ? ctx->world : 1;   // replicas of the whole map never exchange anything
   a.st = ctx->d_reg; a.deblur = in->if_motion_deblur ? 1 : 0; ctx->reg_deblur = a.deblur;
-  a.rank = map->rank; a.world = map->world; a.inv_cell = map->cell_size > 0.f ? 1.0f / map->cell_size : 1.0f;
+  a.rank = map->rank; a.world = map->world; a.grid = map->grid; a.shard_owner = (const int*)map->shard_owner.p;
   return a;
 }
 static SolveArgs solve_args(ll_ctx* ctx, const RegArrays& A, int M, int mode, int max_iter) {
@@ -377,6 +377,10 @@ int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, 
   int iter = 0; RegDevState* hs = (RegDevState*)((char*)ctx->pinned + align256(sizeof(RegDevState)));
   const bool sharded = ctx->world > 1 && map->world > 1;
   if (sharded && (map->world != ctx->world || map->rank != ctx->rank)) { ctx->set_error("map shard and context disagree on rank/world"); return LL_ERR_INVALID; }
+  if (map->world > 1 && (std::sqrt(in->maximum_dis_line_for_match) > (double)map->halo[0] || std::sqrt(in->maximum_dis_plane_for_match) > (double)map->halo[1])) {
+    ctx->set_error("match gates wider than the halo this shard was built with: owner + halo search would no longer be exact"); return LL_ERR_INVALID;
+  }
+  if (map->world > 1 && ctx->world != map->world) { ctx->set_error("a sharded map needs a context connected to the same number of ranks (ll_comm_connect)"); return LL_ERR_INVALID; }
   if (sharded && M > ctx->cfg.max_features) { ctx->set_error("more features than max_features (exchange buffer)"); return LL_ERR_CAPACITY; }
   double* x_l1 = sharded ? (double*)((char*)ctx->comm_local + LL_COMM_X_OFF) : nullptr;
   unsigned set_cap = 1024; while (set_cap < (unsigned)(2 * M)) set_cap <<= 1;   // hash set of the L1 norms (K10)
@@ -672,14 +676,4 @@ int ll_comm_connect(ll_ctx* ctx, int rank, int world, const unsigned char* all) 
   }
   return LL_OK;
 }
-int ll_map_build_sharded(ll_ctx* ctx, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where, int rank, int world, float cell_size,
-                         float halo_corner, float halo_surf, ll_map** out) {
-  (void)halo_corner; (void)halo_surf;
-  // Round 1: every rank indexes the full snapshot (20M points = 320 MB, trivially resident) and owns the queries whose cell hashes
-  // to it; the per-rank halo-trimmed index is the next step (multi-GPU).
-  int st = map_build_common(ctx, corner, nc, surf, ns, fmt, where, out);
-  if (st == LL_OK) { (*out)->rank = rank; (*out)->world = world; (*out)->cell_size = cell_size; }
-  return st;
-}
-
 }  // extern "C"

@@ -60,11 +60,22 @@ struct BucketTree {
   DevBuf storage;                          // one allocation backing all of the above
 };
 
+// Regular grid of cubic cells over the bounding box of the whole map (shard.cu): cell of a point = clamp(floor((p - origin) * inv_cell), 0, dims - 1)
+// per axis, i.e. the border cells extend outwards without bound and every point of space has exactly one cell.
+struct ShardGrid { float origin[3] = {0, 0, 0}; float cell = 1.f, inv_cell = 1.f; int dims[3] = {1, 1, 1}; };
+__host__ __device__ inline int shard_cell_index(const ShardGrid& g, float x, float y, float z) {
+  const float c[3] = {x, y, z}; int ci[3];
+  for (int k = 0; k < 3; k++) { int v = (int)floorf((c[k] - g.origin[k]) * g.inv_cell); ci[k] = v < 0 ? 0 : (v > g.dims[k] - 1 ? g.dims[k] - 1 : v); }
+  return (ci[2] * g.dims[1] + ci[1]) * g.dims[0] + ci[0];
+}
+
 struct ll_map {
   int device = 0;
   BucketTree corner, surf;
-  // sharding (world == 1: everything owned)
+  // sharding (world == 1: everything owned).  A sharded snapshot indexes only the points of the cells this rank owns plus the halo of the match
+  // gates around them; the owner table (rank per cell) lives on the device for the query side and on the host for ll_map_shard_info.
   int rank = 0, world = 1; float cell_size = 0.f;
+  ShardGrid grid; float halo[2] = {0.f, 0.f}; DevBuf shard_owner; std::vector<int> h_owner; long long shard_total[2] = {0, 0};
 };
 
 // per-scan feature-extraction state (device)

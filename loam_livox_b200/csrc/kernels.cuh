@@ -26,7 +26,7 @@ struct KnnBlocksArgs {
   int* seed_ids;                // [M x 5] neighbour ids of the previous ICP iteration (-1 = none): seeds of the next search
   float* knn_d;                 // optional debug output [M x 5]
   const int* perm;              // spatially sorted feature order (corners then surfaces), or null = caller order
-  int rank, world; float inv_cell;
+  int rank, world; ShardGrid grid; const int* shard_owner;   // sharded map: a query is processed by the rank that owns its cell
   const RegDevState* st;        // motion deblur reads q_last/t_last, t_incre and the Rodrigues terms from here
   int deblur;
 };

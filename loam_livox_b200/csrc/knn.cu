@@ -363,11 +363,6 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query_kernel(TreeView tv, con
   }
 }
 
-__device__ __forceinline__ unsigned cell_owner(float x, float y, float z, float inv_cell, int world) {
-  int ix = (int)floorf(x * inv_cell), iy = (int)floorf(y * inv_cell), iz = (int)floorf(z * inv_cell);
-  unsigned h = (unsigned)ix * 73856093u ^ (unsigned)iy * 19349663u ^ (unsigned)iz * 83492791u;
-  return h % (unsigned)world;
-}
 
 // Spatial sort key of a feature at the current pose: class bit (corner/surface) | 21-bit Hilbert index (7 bits per axis) inside the tree's box.
 // Neighbouring queries then sit in the same warp / CTA, walk the same tree nodes and buckets, and hit them in L1.
@@ -486,7 +481,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a
   // squared distance NaN and `NaN < 50.0` (:353) rejects the match, so the block set is the same.
   const bool finite_in = isfinite(f.x) && isfinite(f.y) && isfinite(f.z);
   bool owned = true;
-  if (a.world > 1) owned = cell_owner(qx, qy, qz, a.inv_cell, a.world) == (unsigned)a.rank;
+  if (a.world > 1) owned = finite_in && __ldg(&a.shard_owner[shard_cell_index(a.grid, qx, qy, qz)]) == a.rank;   // shard.cu: every point of space has exactly one owner
   // Residual-block cap, pre-skip (:232-238 corners, :339-345 surfaces): with N features of this class and N > 2 cap, a feature is skipped when
   // rand * N > 2 cap (float arithmetic, like m_rand_float), before it is transformed or searched.  Drawn per (seed, ICP iteration, class, index).
   bool skipped = false;

@@ -139,7 +139,7 @@ def voxel_grid_filter(ctx: Context, cloud, leaf: float):
 class Map:
     """The match-map snapshot: two world-frame clouds + their exact-kNN indices (m_kdtree_{corner,surf}_from_map_last)."""
 
-    def __init__(self, ctx: Context, corner, surf, rank: int = 0, world: int = 1, cell_size: float = 8.0):
+    def __init__(self, ctx: Context, corner, surf, rank: int = 0, world: int = 1, cell_size: float = 2.0):
         self.ctx = ctx
         c, fmt = _pts(corner)
         s, fmt2 = _pts(surf)
@@ -155,6 +155,14 @@ class Map:
 
     def size(self, which):
         return int(self.ctx._lib.ll_map_size(self.h, which))
+
+    def shard_info(self):
+        """(ShardInfo, owner table [dims z,y,x] int32) of a sharded snapshot (ll_map_shard_info)."""
+        info = capi.ShardInfo()
+        self.ctx.check(self.ctx._lib.ll_map_shard_info(self.h, C.byref(info), None, 0))
+        owner = np.zeros(int(info.dims[0]) * int(info.dims[1]) * int(info.dims[2]), np.int32)
+        self.ctx.check(self.ctx._lib.ll_map_shard_info(self.h, C.byref(info), owner.ctypes.data, owner.shape[0]))
+        return info, owner
 
     def nearestKSearch(self, which: int, queries_world):
         """k = 5 search of either tree; returns (indices [nq,5] int32, squared distances [nq,5] float32)."""

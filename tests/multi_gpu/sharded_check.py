@@ -1,5 +1,6 @@
-"""Run under torchrun with >= 2 GPUs: sharded registration (queries owned by 8 m cell hash, 29 sums all-reduced inside the solver kernel over
-peer memory, L1 norms exchanged over peer memory) against the same registration on one GPU with the whole map.
+"""Run under torchrun with >= 2 GPUs: sharded registration (every rank indexes only the cells it owns + the 1.42 m / 7.07 m halos of the match gates
+and processes the features that fall into its cells; 29 sums all-reduced inside the solver kernel over peer memory, L1 norms and -- when the residual
+cap binds -- block counts exchanged over peer memory) against the same registration on one GPU with the whole map.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/multi_gpu/sharded_check.py
 
@@ -37,13 +38,27 @@ def main():
         reg.set_pose(guess.q, guess.t)
         st = reg.find_out_incremental_transfrom(m1, fc, fs)
         cases.append((fc, fs, guess, st, reg.result))
-    # sharded: every rank holds the map, owns the queries whose cell hashes to it
+    # the residual-block cap of the shipped YAML on top (pre-skip + drop: the drop probability needs the block count of ALL ranks)
+    for k in range(2):
+        fc, fs = S.make_features(3000, 27000, pose, seed=S.SEED + 17 * k)
+        guess = S.perturb_pose(pose, np.random.default_rng(50 + k), dt=0.08, dang_deg=1.5)
+        reg = Point_cloud_registration(solo, maximum_allow_residual_block=200, rng_seed=3 + k)
+        reg.set_pose(guess.q, guess.t)
+        st = reg.find_out_incremental_transfrom(m1, fc, fs)
+        cases.append((fc, fs, guess, st, reg.result, dict(maximum_allow_residual_block=200, rng_seed=3 + k)))
+    # sharded: every rank indexes its cells + halo only, and owns the queries that fall into its cells
     ctx = Context(local)
     connect(ctx, rank, world, dist)
-    m = Map(ctx, mc, ms, rank=rank, world=world, cell_size=8.0)
+    m = Map(ctx, mc, ms, rank=rank, world=world, cell_size=2.0)
+    info, owner = m.shard_info()
+    sizes = torch.tensor([info.kept_corner, info.kept_surf], dtype=torch.int64, device="cuda")
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    ok = ok and (info.kept_surf < info.total_surf and info.kept_corner < info.total_corner)   # a real subset on every rank
     for rep in range(2):            # twice: the cross-GPU generation counters must survive a new registration
-        for k, (fc, fs, guess, st1, r1) in enumerate(cases):
-            reg = Point_cloud_registration(ctx)
+        for k, case in enumerate(cases):
+            fc, fs, guess, st1, r1 = case[:5]
+            reg = Point_cloud_registration(ctx, **(case[5] if len(case) > 5 else {}))
             reg.set_pose(guess.q, guess.t)
             st = reg.find_out_incremental_transfrom(m, fc, fs)
             r = reg.result
@@ -63,6 +78,7 @@ def main():
     if rank == 0:
         for r in report:
             print("case rep=%d k=%d status=%d icp=%d blocks=%d owned_here=%d dt=%.3e dq=%.3e" % r)
+        print("shard sizes (corner, surf) per rank of (%d, %d): %s" % (info.total_corner, info.total_surf, [tuple(int(v) for v in t.tolist()) for t in all_sizes]))
         print(("SHARDED_OK" if int(flag.item()) else "SHARDED_MISMATCH") + f" world={world}")
     dist.barrier()
     dist.destroy_process_group()

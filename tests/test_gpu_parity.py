@@ -437,7 +437,7 @@ def test_streaming_mapper_long_sequence(ctx, oracle):
 
 # ---------------------------------------------------------------------------------------------- 8(e): sharded registration on >= 2 GPUs
 @pytest.mark.gpu
-def test_sharded_registration_two_gpus():
+def test_sharded_registration_two_gpus():   # halo-trimmed shards (csrc/shard.cu) + in-kernel all-reduce + L1 / count exchanges vs one GPU with the whole map
     """Spawns tests/multi_gpu/sharded_check.py under torchrun when the box has >= 2 GPUs (skipped on the 1-GPU round-end box)."""
     import os
     import subprocess
@@ -544,6 +544,77 @@ def test_full_size_map_knn_and_registration_properties(oracle):
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
     assert np.linalg.norm(out[0][1] - pose.t) < 5e-3 and S.quat_angle(out[0][0], pose.q) < 1e-3
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_full_size_c2_pose_parity_with_the_oracle(oracle):
+    """BASELINE config C2 at full size (100k-pt raw scans, 0.5M + 4.5M-pt map, the bench's pipeline leaves): two scans through ll_scan_to_pose AND
+    through the oracle -- same feature counts after the four VoxelGrids, same ICP iteration count, same block counts, pose within 1e-7 (bar 1e-4)."""
+    import bench
+    from loam_livox_b200 import capi
+    from loam_livox_b200.registration import Context, Map, scan_to_pose
+    ctx = Context(0, max_scan_points=bench.N_SCAN, max_features=bench.N_SCAN)
+    inputs = bench.make_inputs(0, "c2")
+    mc, ms, scans, guesses, truths = inputs
+    m = Map(ctx, mc, ms)
+    trees = (oracle.KdTree(mc), oracle.KdTree(ms))
+    ex = oracle.Extractor()
+    pc = capi.PipelineCfg(**bench.PIPE)
+    for k in (0, 3):
+        st = capi.default_reg_state(q_w_last=guesses[k].q, t_w_last=guesses[k].t, q_w_curr=guesses[k].q, t_w_curr=guesses[k].t)
+        res, nc, ns = scan_to_pose(ctx, m, scans[k], 100.0, pc, st)
+        ost, ores, onc, ons = bench.oracle_step(oracle, ex, trees, mc, ms, scans[k], guesses[k], 8)
+        assert (nc, ns) == (onc, ons) and ns > 20000
+        assert res.status == ost == 1 and res.icp_iterations == ores.icp_iterations
+        assert (res.corner_used, res.surf_used, res.num_residual_blocks) == (ores.corner_used, ores.surf_used, ores.num_residual_blocks)
+        dt = np.linalg.norm(np.array(res.t_w_curr) - np.array(ores.t_w_curr))
+        da = S.quat_angle(np.array(res.q_w_curr), np.array(ores.q_w_curr))
+        assert dt < 1e-7 and da < 1e-7, (k, dt, da)
+        assert abs(res.final_cost - ores.final_cost) <= 1e-7 * ores.final_cost
+    m.release()
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_two_contexts_on_two_host_threads_share_one_map(oracle):
+    """S3 is called from up to maximum_parallel_thread std::async workers, each with its own Point_cloud_registration, sharing the read-only map
+    snapshot (/root/reference/source/laser_mapping.hpp:1348,1737-1742).  Two ll_ctx on two threads against ONE ll_map: every result equals the
+    result of the same registration run alone, bit for bit."""
+    import threading
+    from loam_livox_b200.registration import Context, Map, Point_cloud_registration
+    mc, ms, fc, fs, pose = _mk(20000, 180000, 3000, 27000)
+    ctxs = [Context(0, max_scan_points=40000, max_features=40000) for _ in range(2)]
+    m = Map(ctxs[0], mc, ms)
+    guesses = [S.perturb_pose(pose, np.random.default_rng(100 + k)) for k in range(6)]
+
+    def run(c, g):
+        reg = Point_cloud_registration(c)
+        reg.set_pose(g.q, g.t)
+        assert reg.find_out_incremental_transfrom(m, fc, fs) == 1
+        r = reg.result
+        return (tuple(r.q_w_curr), tuple(r.t_w_curr), r.final_cost, r.icp_iterations, r.num_residual_blocks)
+    alone = [run(ctxs[0], g) for g in guesses]
+    out = [[None] * len(guesses) for _ in range(2)]
+    errs = []
+
+    def worker(w):
+        try:
+            for rep in range(3):
+                order = range(len(guesses)) if w == 0 else reversed(range(len(guesses)))
+                for k in order:
+                    out[w][k] = run(ctxs[w], guesses[k])
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+    ths = [threading.Thread(target=worker, args=(w,)) for w in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    assert out[0] == alone and out[1] == alone
+    m.release()
+    for c in ctxs:
+        c.close()
 
 
 # ---------------------------------------------------------------------------------------------- N3: PointCloud2 payload in

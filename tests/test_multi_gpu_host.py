@@ -14,7 +14,7 @@ def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
     from loam_livox_b200 import synthetic as S
-    from loam_livox_b200.distributed import all_gather_handles, cell_owner
+    from loam_livox_b200.distributed import all_gather_handles, cell_owner, plan_shards
     from oracle import oracle as O
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -32,7 +32,8 @@ def _worker(rank, world, port, q):
     feats = np.concatenate([fc, fs])
     slot = src[:, 1] + np.where(src[:, 0] == 1, fc.shape[0], 0)
     world_pts = O.transform(feats, guess.q, guess.t)
-    own = cell_owner(world_pts, 8.0, world)
+    origin, dims, table = plan_shards(np.concatenate([mc, ms]), world, 2.0)   # the partition ll_map_build_sharded computes
+    own = cell_owner(world_pts, origin, 2.0, dims, table)
     x = O.plus([0, 0, 0, 1, 0, 0, 0], [0.01, -0.02, 0.015, 0.05, -0.04, 0.03])
     mine_blocks = blocks[own[slot] == rank]
     c, g, H = O.evaluate(mine_blocks, guess.q, guess.t, x) if len(mine_blocks) else (0.0, np.zeros(6), np.zeros((6, 6)))
@@ -80,3 +81,65 @@ def test_two_rank_host_protocol():
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] and r[2] and r[3] for r in res), res
+
+
+def _numpy_shard(points, origin, cell, dims, owner, rank, halo):
+    """Reference restatement of sh_keep_kernel: the points within `halo` of a cell owned by `rank` (border cells reach to infinity)."""
+    p = points[:, :3].astype(np.float64)
+    keep = np.zeros(p.shape[0], bool)
+    d = [int(v) for v in dims]
+    for c in np.nonzero(owner == rank)[0]:
+        ci = (c % d[0], (c // d[0]) % d[1], c // (d[0] * d[1]))
+        d2 = np.zeros(p.shape[0])
+        for a in range(3):
+            lo = float(origin[a]) + ci[a] * cell
+            hi = lo + cell
+            e = np.zeros(p.shape[0])
+            if ci[a] > 0:
+                e = np.maximum(e, lo - p[:, a])
+            if ci[a] < d[a] - 1:
+                e = np.maximum(e, p[:, a] - hi)
+            d2 += e * e
+        keep |= d2 <= halo * halo
+    return keep
+
+
+def test_owner_plus_halo_shards_give_the_full_map_blocks():
+    """with a halo of sqrt(gate) around the cells a rank owns, the residual blocks of the features that rank owns are exactly the
+    blocks a search of the whole map gives (gates :254 / :353 compare SQUARED distances with 2.0 / 50.0).  Checked with the oracle on numpy shards,
+    for the partition rule the library exports (ll_shard_plan): every cell has one owner, ranges are balanced, all features are covered once."""
+    sys.path.insert(0, ROOT)
+    from loam_livox_b200 import synthetic as S
+    from loam_livox_b200.distributed import cell_owner, plan_shards
+    from oracle import oracle as O
+    mc, ms = S.make_map(3000, 30000)
+    pose = S.default_pose()
+    fc, fs = S.make_features(300, 2700, pose)
+    guess = S.perturb_pose(pose, np.random.default_rng(3))
+    p = O.default_params(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t)
+    full, src, ca, sa = O.build_blocks(mc, O.KdTree(mc), ms, O.KdTree(ms), fc, fs, p)
+    key = {(int(s0), int(s1)): b for (s0, s1), b in zip(src, full)}
+    for world, cell in ((2, 2.0), (4, 2.0), (8, 3.0)):
+        origin, dims, owner = plan_shards(np.concatenate([mc, ms]), world, cell)
+        counts = np.bincount(owner, minlength=world)
+        assert owner.min() >= 0 and owner.max() == world - 1 and counts.min() > 0
+        n_all = mc.shape[0] + ms.shape[0]
+        per_rank = np.bincount(cell_owner(np.concatenate([mc, ms]), origin, cell, dims, owner), minlength=world)
+        assert per_rank.sum() == n_all and per_rank.max() < 1.5 * n_all / world + 0.05 * n_all     # balanced by point count (up to one cell)
+        own_c = cell_owner(O.transform(fc, guess.q, guess.t), origin, cell, dims, owner)
+        own_s = cell_owner(O.transform(fs, guess.q, guess.t), origin, cell, dims, owner)
+        seen = 0
+        for r in range(world):
+            kc = _numpy_shard(mc, origin, cell, dims, owner, r, 2.0 ** 0.5)
+            ks = _numpy_shard(ms, origin, cell, dims, owner, r, 50.0 ** 0.5)
+            assert ks.sum() < ms.shape[0] or world == 2            # the shard really is a subset (the 7.07 m halo covers a lot of a 42 m room)
+            ic, is_ = np.nonzero(own_c == r)[0], np.nonzero(own_s == r)[0]
+            shc, shs = mc[kc], ms[ks]
+            if shc.shape[0] == 0 or shs.shape[0] < 5:
+                continue
+            blk, s2, _, _ = O.build_blocks(shc, O.KdTree(shc), shs, O.KdTree(shs), fc[ic], fs[is_], p)
+            for (s0, s1), b in zip(s2, blk):
+                g = (int(s0), int(ic[s1] if s0 == 0 else is_[s1]))
+                assert g in key and np.array_equal(key[g], b, equal_nan=True), (world, r, g)
+            seen += blk.shape[0]
+        assert seen == full.shape[0]

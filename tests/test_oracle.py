@@ -304,3 +304,53 @@ def test_cap_rule_in_the_oracle(oracle):
         assert st == 1 and 0.7 * 2 * cap < res.surf_used < 1.3 * 2 * cap and 0.7 * 2 * cap < res.corner_used < 1.3 * 2 * cap
         assert all(0.7 * cap < t.blocks_before_select < 1.3 * cap for t in tr)
         assert np.linalg.norm(np.array(res.t_w_curr) - pose.t) < 0.03
+
+
+# ---------------------------------------------------------------------------------------------- independent witnesses
+def test_knn_matches_real_flann_kdtree_single_index(oracle):
+    """PCL's KdTreeFLANN wraps FLANN's KDTreeSingleIndex (leaf_max_size 15, exact search, sorted).  OpenCV ships a copy of FLANN with that very index
+    (cv2.flann, algorithm 4): the oracle's restatement must return the same neighbours and the same fp32 squared distances, bit for bit, as the real
+    library on a map-like cloud (no exact ties here; FLANN leaves the order of exact ties unspecified, the oracle uses the smaller index)."""
+    cv2 = pytest.importorskip("cv2")
+    mc, ms = S.make_map(5000, 45000)
+    rng = np.random.default_rng(1)
+    for cloud in (ms, mc):
+        q = cloud[rng.integers(0, cloud.shape[0], 4000)].copy()
+        q[:, :3] += rng.normal(0, 0.05, (4000, 3)).astype(np.float32)
+        pts = np.ascontiguousarray(cloud[:, :3])
+        index = cv2.flann_Index(pts, dict(algorithm=4, leaf_max_size=15))
+        fi, fd = index.knnSearch(np.ascontiguousarray(q[:, :3]), 5, params=dict(checks=-1, eps=0.0, sorted=True))
+        oi, od, found = oracle.KdTree(cloud).knn(q)
+        assert (found == 5).all()
+        assert np.array_equal(fd, od), "fp32 squared distances differ from FLANN's"
+        distinct = np.all(np.diff(od, axis=1) > 0, axis=1)
+        assert distinct.mean() > 0.99 and np.array_equal(fi[distinct], oi[distinct])
+    # the LINEAR index (brute force inside FLANN) as a second witness of the distance arithmetic
+    lin = cv2.flann_Index(np.ascontiguousarray(ms[:, :3]), dict(algorithm=0))
+    li, ld = lin.knnSearch(np.ascontiguousarray(q[:200, :3]), 5, params=dict(checks=-1, eps=0.0, sorted=True))
+    bi, bd, _ = oracle.knn_brute(ms, q[:200])
+    assert np.array_equal(ld, bd)
+
+
+def test_converged_solution_is_a_stationary_point_of_the_huber_objective(oracle):
+    """Independent of the trust-region schedule the restatement follows: restart the solve from its own result until it stops moving; at that point the
+    gradient of sum rho(|r_i|^2)/2 in the tangent space (finite differences of the oracle's own cost, NOT its Jacobian code) vanishes to the level the
+    function tolerance allows, and no neighbouring point has a lower cost."""
+    b, guess, _, _ = _blocks(oracle, seed=5)
+    x = np.array([0, 0, 0, 1, 0, 0, 0], float)
+    for _ in range(8):
+        x, so = oracle.solve(b, guess.q, guess.t, x, 200, bound=10.0)
+    cost0 = oracle.evaluate(b, guess.q, guess.t, x)[0]
+    h = 1e-6
+    g_fd = np.zeros(6)
+    for c in range(6):
+        e = np.zeros(6); e[c] = h
+        g_fd[c] = (oracle.evaluate(b, guess.q, guess.t, oracle.plus(x, e, bound=10.0))[0] - oracle.evaluate(b, guess.q, guess.t, oracle.plus(x, -e, bound=10.0))[0]) / (2 * h)
+    _, g, H = oracle.evaluate(b, guess.q, guess.t, x)
+    scale = np.sqrt(np.diag(H)) * np.sqrt(2 * cost0)          # |J_c| |f|: the natural size of a gradient component
+    assert np.all(np.abs(g_fd) < 1e-4 * scale), (g_fd, scale)
+    assert np.allclose(g, g_fd, atol=1e-5 * scale.max())      # and the analytic gradient agrees with the finite differences there
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        d = rng.normal(0, 1e-4, 6)
+        assert oracle.evaluate(b, guess.q, guess.t, oracle.plus(x, d, bound=10.0))[0] >= cost0 * (1 - 1e-9)
