@@ -500,51 +500,70 @@ def run_gpu(args):
 
 # ------------------------------------------------------------------------------------------------ C3: streaming odometry (not the default line)
 def run_stream(args):
-    """BASELINE.json configs[2]: a synthetic sequence through the device mapper (ll_mapper_process_scan): features, match-map refresh from the
-    growing cell map (radius + FOV select, per-cell VoxelGrid, whole-map VoxelGrid, index build), registration, append.  Raw scans come from
-    pinned host memory; host wall clock around each call (this IS the end-to-end path).  Precision-YAML resolutions (0.1 / 0.4 m)."""
+    """BASELINE.json configs[2]: a synthetic sequence (stationary for the first init_accumulate_frames + 1 scans, then ~0.3 m/s with sinusoidal yaw)
+    through the device mapper (ll_mapper_process_scan): features, match-map refresh (--matching-mode 0: the sliding window of the last 400 feature
+    clouds, the shipped YAMLs' mode; 1: radius + FOV select from the growing cell map, per-cell VoxelGrid), whole-map VoxelGrid, index build,
+    registration, append.  Raw scans come from pinned host memory; host wall clock around each call (this IS the end-to-end path).
+    Leaves 0.05 / 0.1 m (denser than the precision YAML's 0.1 / 0.4 so that a scan carries several thousand features and the map grows into the
+    hundreds of thousands of points).  The oracle runs the first scans of the same sequence beside it: its drift is printed next to the GPU's."""
     import torch
     from loam_livox_b200 import capi
     from loam_livox_b200.registration import Context, Laser_mapping
     n_total = args.steps + args.warmup
-    poses = S.trajectory(n_scans=n_total, n_static=4, speed=1.0)
-    raws = [torch.from_numpy(S.make_scan(N_SCAN, p, seed=S.SEED + k)).pin_memory() for k, p in enumerate(poses)]
+    init = 50 if n_total > 200 else 3                # mapping/init_accumulate_frames (50 in both YAMLs); short smoke runs start registering earlier
+    LINE, PLANE = 0.05, 0.1
+    poses = S.trajectory(n_scans=n_total, n_static=init + 1, speed=1.0)
     ctx = Context(0, max_scan_points=N_SCAN, max_features=N_SCAN)
-    gm = Laser_mapping(ctx, reg=capi.default_reg_state(mapping_init_accumulate_frames=3))
+    pipe = capi.PipelineCfg(pieces=3, use_piece=0, extractor_leaf_corner=LINE, extractor_leaf_surf=PLANE / 2, mapping_leaf_corner=LINE, mapping_leaf_surf=PLANE, whole_frame=1)
+    gm = Laser_mapping(ctx, reg=capi.default_reg_state(mapping_init_accumulate_frames=init), pipeline=pipe, line_resolution=LINE, plane_resolution=PLANE,
+                       matching_mode=args.matching_mode, maximum_history_size=400)
+    pin = [torch.empty((N_SCAN, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
     sampler = ClockSampler(0); sampler.start()
-    times, stats_last, l0, phases = [], None, 0, []
+    times, stats_last, l0, phases, checkpoints = [], None, 0, [], {}
+    R0, t0w = poses[0].R(), poses[0].t
+    n_cpu = 0 if args.no_cpu else min(n_total, init + 30)
     for k in range(n_total):
+        raw = S.make_scan(N_SCAN, poses[k], seed=S.SEED + k)          # generated outside the timed call
+        pin[k & 1].copy_(torch.from_numpy(raw))
         if k == args.warmup:
             l0 = ctx.launches()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res, st = gm.process_new_scan(raws[k].numpy(), 100.0 + 0.1 * k)   # pinned host buffer, H2D inside the call
+        res, st = gm.process_new_scan(pin[k & 1].numpy(), 100.0 + 0.1 * k)   # pinned host buffer, H2D inside the call
         dt = time.perf_counter() - t0
         if k >= args.warmup:
             times.append(dt)
             phases.append((st.ms_front_end, st.ms_refresh, st.ms_register, st.ms_append))
         stats_last = st
+        if k + 1 in (n_cpu, n_total):
+            q, t, f = gm.pose()
+            checkpoints[k + 1] = float(np.linalg.norm(t - R0.T @ (poses[k].t - t0w)))
     clocks = sampler.stop()
-    q, t, f = gm.pose()
-    R0, t0w = poses[0].R(), poses[0].t
-    drift = float(np.linalg.norm(t - R0.T @ (poses[-1].t - t0w)))
     line = {"metric": "scans_per_sec", "value": len(times) / float(np.sum(times)), "unit": "scans/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 kNN / f64 solve", "data": "synthetic",
-            "config": {"workload": "C3: streaming sequence, growing device cell map (matching_mode 1), match map rebuilt after every scan; 100k-pt scans, leaves 0.1/0.4 m",
+            "config": {"workload": f"C3: streaming sequence of {n_total} 100k-pt scans, matching_mode {args.matching_mode} "
+                                   f"({'history window of 400 feature clouds' if args.matching_mode == 0 else 'growing device cell map, radius + FOV select'}), match map re-indexed after every scan; leaves {LINE}/{PLANE} m",
                        "final_map_points": [stats_last.map_corner, stats_last.map_surf], "features_per_scan": [stats_last.n_corner, stats_last.n_surf],
-                       "final_position_error_m": drift},
+                       "final_position_error_m": checkpoints.get(n_total), "position_error_m_at_scan": checkpoints},
             "clocks": clocks, "e2e": {"value": len(times) / float(np.sum(times)), "unit": "scans/s", "h2d_bytes_per_step": N_SCAN * 16, "d2h_bytes_per_step": 1400},
             "gpu_launches": int(ctx.launches() - l0), "p50_ms": 1e3 * float(np.median(times)), "p99_ms": 1e3 * float(np.quantile(times, 0.99)),
             "phase_ms_median": dict(zip(("front_end", "refresh", "register", "append"), [float(x) for x in np.median(np.array(phases), axis=0)])),
             "slowest": [(int(i), round(1e3 * times[i], 2), [round(float(x), 2) for x in phases[i]]) for i in np.argsort(times)[-4:]]}
-    if not args.no_cpu:
+    if n_cpu:
         from oracle import oracle
-        om = oracle.Mapper(oracle.default_params(mapping_init_accumulate_frames=3, num_threads=1), threads=1)
-        n = min(n_total, 40)
-        t0 = time.perf_counter()
-        for k in range(n):
-            om.process_scan(raws[k].numpy(), 100.0 + 0.1 * k)
-        line["cpu_baseline"] = {"value": n / (time.perf_counter() - t0), "unit": "scans/s", "cores": 1, "kind": "port", "sample": f"first {n} scans of the same sequence through oracle.Mapper (1 thread)"}
+        om = oracle.Mapper(oracle.default_params(mapping_init_accumulate_frames=init, num_threads=1), threads=1, line_resolution=LINE, plane_resolution=PLANE,
+                           extractor_leaf_corner=LINE, extractor_leaf_surf=PLANE / 2, matching_mode=args.matching_mode, maximum_history_size=400)
+        t_reg = 0.0
+        for k in range(n_cpu):
+            raw = S.make_scan(N_SCAN, poses[k], seed=S.SEED + k)
+            t0 = time.perf_counter()
+            st_o, q_o, t_o = om.process_scan(raw, 100.0 + 0.1 * k)
+            if k > init:
+                t_reg += time.perf_counter() - t0
+        err_o = float(np.linalg.norm(t_o - R0.T @ (poses[n_cpu - 1].t - t0w)))
+        line["cpu_baseline"] = {"value": max(1, n_cpu - init - 1) / max(t_reg, 1e-9), "unit": "scans/s", "cores": 1, "kind": "port",
+                                "sample": f"the registered scans among the first {n_cpu} of the same sequence through oracle.Mapper (1 thread, same leaves and matching mode)"}
+        line["config"]["oracle_position_error_m_at_scan"] = {n_cpu: err_o}
     print(json.dumps(line))
 
 
@@ -558,6 +577,7 @@ def main():
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"], help="replicas = every GPU registers its own scans against its own map (default, weak scaling); "
                     "sharded = config C4: ONE scan registered by all GPUs together against the 20M-point map sharded by spatial cell (strong scaling)")
     ap.add_argument("--contexts", type=int, default=1, help="scans in flight per GPU (throughput mode: K contexts on K host threads sharing one map; the reference runs maximum_parallel_thread of them)")
+    ap.add_argument("--matching-mode", type=int, default=0, choices=[0, 1], help="c3 only: mapping/matching_mode (0 = history window, the shipped YAMLs' mode; 1 = cell map)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-scans", type=int, default=5)
     args = ap.parse_args()

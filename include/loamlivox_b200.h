@@ -187,6 +187,24 @@ int ll_normal_equations(ll_ctx* ctx, const double x[7], double out28[28]);
 /* ... and one ceres::Solve-equivalent on the blocks currently resident (max_iterations as in Solver::Options). */
 int ll_solve(ll_ctx* ctx, int max_iterations, double x_io[7], double* initial_cost, double* final_cost, int* iterations);
 
+/* ---- N4: loop-closure reuse of S3 ----------------------------------------------------------------------- */
+/* Replaces Scene_alignment::find_tranfrom_of_two_mappings (scene_alignment.hpp:269-353) from the point where the four feature clouds exist:
+ * three coarse-to-fine registrations (leaf x8, x4, x1; twice the ICP iterations at the finest) of the target keyframe's features against the source
+ * keyframe's, ICP_LINE = 0, on one persistent registration object (increment and pose carry over between scales, :233-243,292-306).
+ * out = the state after the last scale run (q_w_curr / t_w_curr = the transform of keyframe b into keyframe a; inlier_threshold = the score
+ * Scene_alignment returns).  *scales_run <= 3 (stops early when inlier_threshold > 2 x accepted_threshold, :349-350). */
+typedef struct {
+  float  line_res, plane_res;          /* Scene_alignment::m_line_res / m_plane_res (0.4 / 0.4, :27-28)                                  */
+  int    maximum_icp_iteration;        /* m_maximum_icp_iteration (10, :35)                                                              */
+  int    maximum_residual_block;       /* m_para_scene_alignments_maximum_residual_block (5000, :34)                                     */
+  float  accepted_threshold;           /* m_accepted_threshold (0.2, :36)                                                                */
+  int    rng_seed;                     /* see ll_reg_state::rng_seed                                                                      */
+  double t_init[3];                    /* keyframe_a->get_center() - keyframe_b->get_center() (:303)                                     */
+} ll_align_cfg;
+void ll_align_cfg_default(ll_align_cfg* cfg);
+int  ll_scene_align(ll_ctx* ctx, const void* source_line, size_t n_sl, const void* source_plane, size_t n_sp, const void* target_line, size_t n_tl,
+                    const void* target_plane, size_t n_tp, int fmt, int where, const ll_align_cfg* cfg, ll_reg_result* out, int* scales_run);
+
 /* ---- a7: pointAssociateToMap over a cloud ----------------------------------------------------------- */
 /* Replaces Point_cloud_registration::pointcloudAssociateToMap (point_cloud_registration.hpp:673-685, non-deblur
  * branch of :622-661): p_w = q*p + t in fp64, stored as fp32, intensity passed through. */
@@ -223,7 +241,7 @@ int  ll_cellmap_assemble(ll_ctx* ctx, ll_cellmap* map, const double q_w_curr[4],
                          int down_sample_replace, ll_point* out_host, size_t cap, size_t* n_out, int* cells_in_fov, const ll_point** out_dev);
 int  ll_cellmap_stats(ll_ctx* ctx, ll_cellmap* map, int* cells, int* stored_points, int* frame_idx);
 
-/* ---- streaming odometry: Laser_mapping::process_new_scan + update_buff_for_matching (matching_mode 1) ------------------------------- */
+/* ---- streaming odometry: Laser_mapping::process_new_scan + update_buff_for_matching (matching_mode 0 and 1) ------------------------- */
 typedef struct {
   float line_resolution, plane_resolution;      /* feature_extraction/mapping_{line,plane}_resolution (laser_mapping.hpp:661-662)          */
   float cell_resolution;                        /* m_pt_cell_resolution (1.0 => 0.5 m cells)                                               */
@@ -231,6 +249,9 @@ typedef struct {
   float maximum_search_range_corner, maximum_search_range_surface, maximum_in_fov_angle;   /* mapping/... (:691-695)                      */
   int   down_sample_replace;                    /* m_down_sample_replace (:277)                                                            */
   int   max_cells;                              /* hash-table sizing of each cell map (0 = 1 Mi cells)                                     */
+  int   matching_mode;                          /* mapping/matching_mode (:689): 0 = sliding window of the last maximum_history_size feature clouds
+                                                   (:518-531,1439-1478; what both shipped YAMLs select), 1 = cells in range and in the FOV (:471-516)   */
+  int   maximum_history_size;                   /* mapping/maximum_histroy_buffer (:687; YAML 400 / 200)                                   */
   ll_pipeline_cfg pipeline;                     /* feature-extraction glue (leaves, pieces)                                                */
   ll_reg_state reg;                             /* registration parameters; the poses in it are the initial pose                           */
 } ll_mapper_config;

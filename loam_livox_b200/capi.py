@@ -25,7 +25,7 @@ EXPORTS = [
     "ll_map_build_sharded", "ll_knn", "ll_reg_state_default", "ll_register", "ll_build_blocks", "ll_normal_equations", "ll_solve", "ll_transform",
     "ll_scan_to_pose", "ll_comm_local_handle", "ll_comm_connect", "ll_launch_count", "ll_cellmap_create", "ll_cellmap_release", "ll_cellmap_append",
     "ll_cellmap_assemble", "ll_cellmap_stats", "ll_voxel_downsample_dev", "ll_transform_dev", "ll_last_features_dev", "ll_mapper_config_default", "ll_mapper_create", "ll_mapper_release",
-    "ll_mapper_process_scan", "ll_mapper_pose", "ll_map_rebuild", "ll_debug_solver_cycles", "ll_state_snapshot_bytes", "ll_set_point_layout", "ll_format_pose_log", "ll_reg_state_yaml", "ll_cap_uniform", "ll_map_shard_info", "ll_shard_plan",
+    "ll_mapper_process_scan", "ll_mapper_pose", "ll_map_rebuild", "ll_debug_solver_cycles", "ll_state_snapshot_bytes", "ll_set_point_layout", "ll_format_pose_log", "ll_reg_state_yaml", "ll_cap_uniform", "ll_map_shard_info", "ll_shard_plan", "ll_align_cfg_default", "ll_scene_align",
 ]
 
 
@@ -65,7 +65,8 @@ class PointLayout(C.Structure):
 class MapperConfig(C.Structure):
     _fields_ = [("line_resolution", C.c_float), ("plane_resolution", C.c_float), ("cell_resolution", C.c_float), ("threshold_cell_revisit", C.c_int),
                 ("maximum_search_range_corner", C.c_float), ("maximum_search_range_surface", C.c_float), ("maximum_in_fov_angle", C.c_float),
-                ("down_sample_replace", C.c_int), ("max_cells", C.c_int), ("pipeline", PipelineCfg), ("reg", RegState)]
+                ("down_sample_replace", C.c_int), ("max_cells", C.c_int), ("matching_mode", C.c_int), ("maximum_history_size", C.c_int),
+                ("pipeline", PipelineCfg), ("reg", RegState)]
 
 
 class MapperStats(C.Structure):
@@ -76,6 +77,11 @@ class MapperStats(C.Structure):
 class ShardInfo(C.Structure):
     _fields_ = [("rank", C.c_int), ("world", C.c_int), ("cell_size", C.c_float), ("halo_corner", C.c_float), ("halo_surf", C.c_float), ("origin", C.c_float * 3),
                 ("dims", C.c_int * 3), ("kept_corner", C.c_longlong), ("kept_surf", C.c_longlong), ("total_corner", C.c_longlong), ("total_surf", C.c_longlong)]
+
+
+class AlignCfg(C.Structure):
+    _fields_ = [("line_res", C.c_float), ("plane_res", C.c_float), ("maximum_icp_iteration", C.c_int), ("maximum_residual_block", C.c_int),
+                ("accepted_threshold", C.c_float), ("rng_seed", C.c_int), ("t_init", C.c_double * 3)]
 
 
 class LoamLivoxError(RuntimeError):
@@ -113,6 +119,8 @@ def lib():
     L.ll_map_build_sharded.argtypes = [vp, vp, sz, vp, sz, ci, ci, ci, ci, cf, cf, cf, C.POINTER(vp)]
     L.ll_map_shard_info.argtypes = [vp, C.POINTER(ShardInfo), vp, sz]
     L.ll_shard_plan.argtypes = [vp, vp, ci, vp]
+    L.ll_align_cfg_default.argtypes = [C.POINTER(AlignCfg)]
+    L.ll_scene_align.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, ci, ci, C.POINTER(AlignCfg), C.POINTER(RegResult), C.POINTER(ci)]
     L.ll_map_release.argtypes = [vp]
     L.ll_map_size.argtypes = [vp, ci]
     L.ll_map_size.restype = sz

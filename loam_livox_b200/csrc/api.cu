@@ -92,6 +92,7 @@ void ll_ctx_destroy(ll_ctx* ctx) {
   ctx->scratch.release(); ctx->stage_in.release(); ctx->extract_buf.release(); ctx->feat_buf.release(); ctx->reg_buf.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->d_reg) cudaFree(ctx->d_reg);
+  if (ctx->d_sync) cudaFree(ctx->d_sync);
   if (ctx->comm_local) cudaFree(ctx->comm_local);
   for (int i = 0; i < 8; i++) if (ctx->comm_peers[i] && i != ctx->rank) cudaIpcCloseMemHandle(ctx->comm_peers[i]);
   for (int i = 0; i < 5 * 16 + 2; i++) if (ctx->evp[i]) cudaEventDestroy(ctx->evp[i]);
@@ -275,7 +276,8 @@ static int map_index(ll_ctx* ctx, ll_map* m, const void* corner, size_t nc, cons
   if (st == LL_OK) st = build_bucket_tree(ctx, d_in, (int)nc, &m->corner);
   if (st == LL_OK) st = upload_cloud(ctx, surf, ns, fmt, where, d_in);
   if (st == LL_OK) st = build_bucket_tree(ctx, d_in, (int)ns, &m->surf);
-  if (st == LL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = LL_ERR_CUDA;
+  // host inputs may be freed by the caller as soon as this returns; device inputs are consumed in stream order (the per-scan refresh never waits)
+  if (st == LL_OK && where == LL_HOST && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = LL_ERR_CUDA;
   return st;
 }
 static int map_build_common(ll_ctx* ctx, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where, ll_map** out) {
@@ -342,7 +344,7 @@ static KnnBlocksArgs knn_args(ll_ctx* ctx, const ll_map* map, const RegArrays& A
   return a;
 }
 static SolveArgs solve_args(ll_ctx* ctx, const RegArrays& A, int M, int mode, int max_iter) {
-  SolveArgs s; s.st = ctx->d_reg; s.feat = A.feat; s.blk_a = A.blk_a; s.blk_v = A.blk_v; s.l1 = A.l1; s.l1_sorted_unique = A.l1_unique; s.d_n_unique = A.n_unique;
+  SolveArgs s; s.st = ctx->d_reg; s.sync = ctx->d_sync; s.feat = A.feat; s.blk_a = A.blk_a; s.blk_v = A.blk_v; s.l1 = A.l1; s.l1_sorted_unique = A.l1_unique; s.d_n_unique = A.n_unique;
   s.partials = A.partials; s.M = M; s.max_iterations = max_iter; s.mode = mode; s.rank = ctx->rank; s.world = ctx->solve_world; s.comm_local = (double*)ctx->comm_local;
   for (int i = 0; i < 8; i++) s.comm_peer[i] = (double*)ctx->comm_peers[i];
   s.cap_check = 0; s.deblur = ctx->reg_deblur; s.prerun_iterations = 0; s.table = nullptr; s.table_mask = 0; s.uniq = nullptr; s.n_uniq = nullptr;

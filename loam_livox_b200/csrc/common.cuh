@@ -45,9 +45,9 @@ struct DevBuf {  // grow-only device allocation
 // (512 B = one coalesced warp load), with a 32-ary tree of axis-aligned boxes above them (a node record = its 32 children's
 // boxes, 1 KB).  Search is exact: a box gives a true lower bound of the fp32 distance.  lo[l] holds level l's node records;
 // hi[0] the base of the node array (top level first).
-#define LL_MAX_LEVELS 14
+#define LL_MAX_LEVELS 8
 struct BucketTree {
-  int n = 0;             // valid (finite) points
+  int n = 0;             // points given (the count of finite ones stays on the device)
   int n_pad = 0;         // padded to a multiple of 32
   int n_levels = 0;      // number of box levels (>= 1 when n > 0)
   int level_count[LL_MAX_LEVELS] = {0};   // boxes per level (unpadded)
@@ -56,7 +56,7 @@ struct BucketTree {
   float4* hi[LL_MAX_LEVELS] = {nullptr};
   float4* src = nullptr;                  // [n_src] the cloud as given to ll_map_build (x,y,z,intensity)
   int n_src = 0;
-  float bbox[6] = {0, 0, 0, 0, 0, 0};     // min xyz, max xyz of the finite points
+  float* d_bbox = nullptr;                // device: min xyz, max xyz of the finite points (6 floats inside `storage`)
   DevBuf storage;                          // one allocation backing all of the above
 };
 
@@ -118,6 +118,7 @@ struct ll_ctx {
   void* pinned = nullptr; size_t pinned_cap = 0;   // pinned host staging for small D2H/H2D control blocks
   ExtractState ex;
   RegDevState* d_reg = nullptr;   // device
+  struct SolveSync* d_sync = nullptr;   // device: exchange rows of the solver kernels (solve.cu)
   // multi-GPU
   int rank = 0, world = 1;
   cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_it[2] = {nullptr, nullptr}; DevBuf scratch2, scratch_fe;   // side stream of the per-scan front end; the front end's own scratch arenas (fixed once the scan size is

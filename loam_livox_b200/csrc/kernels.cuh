@@ -7,7 +7,7 @@ struct TreeView {
   const float4* src;                    // [n_src] the cloud in its original order
   const float4* nodes[LL_MAX_LEVELS];   // node records per level (6 float4 each); level 0's children are the 8-point buckets
   int n, n_levels;
-  float bbox[6];                        // map bounding box (min xyz, max xyz)
+  const float* bbox;                    // device: map bounding box (min xyz, max xyz)
 };
 TreeView make_view(const BucketTree& t);
 int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t);
@@ -42,6 +42,7 @@ struct FnSample { double x, value, gradient; int value_valid, gradient_valid; };
 struct LmState {
   int phase, iteration, max_iterations, num_invalid, done, termination, last_successful, reuse_diagonal;
   int ls_iters, n_valid, total_iterations, total_evaluations;
+  int pending, _pad;   // after lm_step: -1 nothing to start / 0 next iteration from the accepted point / 1 from the old point
   double x[7], x_norm, x_cost, g[6], H[21];
   double trial[7];
   double scaling[6], diagonal[6], radius, decrease_factor;
@@ -70,8 +71,20 @@ struct RegDevState {
   LmState lm;
 };
 
+// Grid-wide exchange area of the solver kernels (one per context, device memory, zeroed once at creation; see solve.cu):
+// one tagged 256-byte row per CTA and parity, the broadcast row of the sharded mode, the K10 histograms / candidate list, the generation base.
+#define LL_SYNC_ROWS 160
+struct SolveSync {
+  double rows[2][LL_SYNC_ROWS][32];   // [parity][cta]: 29 sums, [31] = generation tag (low 32 bits)
+  double bcast[2][32];                // world > 1: the all-reduced sums, from CTA 0 to the other CTAs of the rank
+  unsigned hist[6][2048]; unsigned list_cnt; unsigned _pad[63];   // K10 radix-select histograms + candidate counter (cleared together by every fused launch)
+  double list[64];
+  unsigned gen;                       // generation base of the next launch; grows monotonically over the life of the context
+};
+
 struct SolveArgs {
   RegDevState* st;
+  SolveSync* sync;
   const float4* feat;        // [M] scan-frame points
   const float4* blk_a;       // [M] (a.xyz, type)
   const double* blk_v;       // [M*3]

@@ -68,24 +68,28 @@ __device__ __forceinline__ unsigned long long spread21(unsigned v) {
   x = (x | x << 2) & 0x1249249249249249ull;
   return x;
 }
-// 63-bit Hilbert index (Skilling's transpose form, 21 bits per axis) on an ISOTROPIC grid (one scale for all axes):
-// consecutive runs along a Hilbert curve are connected blobs, so fixed-size buckets get tight, nearly cubic boxes.
-__global__ void hilbert_kernel(const float4* __restrict__ src, int n, const int* __restrict__ bbox, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+// Hilbert index (Skilling's transpose form, `bits` per axis, <= 21) on an ISOTROPIC grid (one scale for all axes): consecutive runs along a
+// Hilbert curve are connected blobs, so fixed-size buckets get tight, nearly cubic boxes.  The key only decides WHICH points share a bucket (the
+// boxes are computed from the points themselves, so the search is exact for any key): its width follows the map size (about 8 cells per bucket
+// side at the finest level), which is what bounds the number of radix passes of the sort below.
+template <typename KeyT>
+__global__ void hilbert_kernel(const float4* __restrict__ src, int n, const int* __restrict__ bbox, int bits, KeyT* __restrict__ keys, int* __restrict__ vals) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = src[i];
-  unsigned long long key = ~0ull;
+  unsigned long long key = 1ull << (3 * bits);   // non-finite points: one bit above every real key -> they sort to the end
   if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
     const float lo[3] = {ord2f(bbox[0]), ord2f(bbox[1]), ord2f(bbox[2])}, hi[3] = {ord2f(bbox[3]), ord2f(bbox[4]), ord2f(bbox[5])};
     const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
     const float c[3] = {p.x, p.y, p.z}; unsigned X[3];
+    const float scale = (float)(1u << bits), top = scale - 1.0f;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       float u = ext > 0.f ? (c[k] - lo[k]) / ext : 0.f;
       u = fminf(fmaxf(u, 0.f), 1.f);
-      X[k] = (unsigned)fminf(u * 2097152.0f, 2097151.0f);
+      X[k] = (unsigned)fminf(u * scale, top);
     }
-    for (unsigned Q = 1u << 20; Q > 1; Q >>= 1) {
+    for (unsigned Q = 1u << (bits - 1); Q > 1; Q >>= 1) {
       const unsigned P = Q - 1;
 #pragma unroll
       for (int k = 0; k < 3; k++) {
@@ -95,21 +99,24 @@ __global__ void hilbert_kernel(const float4* __restrict__ src, int n, const int*
     }
     X[1] ^= X[0]; X[2] ^= X[1];
     unsigned t = 0;
-    for (unsigned Q = 1u << 20; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+    for (unsigned Q = 1u << (bits - 1); Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
     X[0] ^= t; X[1] ^= t; X[2] ^= t;
-    key = (spread21(X[0]) << 2) | (spread21(X[1]) << 1) | spread21(X[2]);
+    key = (spread21(X[0]) << 2) | (spread21(X[1]) << 1) | spread21(X[2]);   // < 2^(3 bits)
   }
-  keys[i] = key; vals[i] = i;
+  keys[i] = (KeyT)key;
+  vals[i] = i;
 }
-__global__ void gather_kernel(const float4* __restrict__ src, const int* __restrict__ order, int n_valid, int n_pad, float4* __restrict__ pts) {
+// n_valid (= bbox[6], the number of finite points) is read on the device: the host never waits for it.
+__global__ void gather_kernel(const float4* __restrict__ src, const int* __restrict__ order, const int* __restrict__ bbox, int n_pad, float4* __restrict__ pts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pad) return;
+  const int n_valid = bbox[6];
   if (i < n_valid) { int j = order[i]; float4 p = src[j]; p.w = __int_as_float(j); pts[i] = p; }
   else pts[i] = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0x7fffffff));
 }
-// One thread per (node, child).  Level 0: the children are buckets of 8 points.  Level l > 0: the children are level l-1 nodes
-// (box = union of that node's 8 child boxes).  Missing children get the neutral box (+inf, -inf).
-__global__ void node_kernel(const float4* __restrict__ pts, int n_valid, const float4* __restrict__ child_nodes, int n_child, int n_nodes, float4* __restrict__ nodes) {
+// One thread per (node, child).  Level 0: the children are buckets of 32 points (pad points are +inf and do not count).  Level l > 0: the children
+// are level l-1 nodes (box = union of that node's child boxes).  Missing / empty children get the neutral box (+inf, -inf).
+__global__ void node_kernel(const float4* __restrict__ pts, const float4* __restrict__ child_nodes, int n_child, int n_nodes, float4* __restrict__ nodes) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = g / FANOUT, c = g % FANOUT;
   if (j >= n_nodes) return;
@@ -118,8 +125,8 @@ __global__ void node_kernel(const float4* __restrict__ pts, int n_valid, const f
   if (ci < n_child) {
     if (child_nodes == nullptr) {
       for (int k = 0; k < BUCKET; k++) {
-        const int pi = ci * BUCKET + k;
-        if (pi < n_valid) { const float4 p = pts[pi]; l0 = fminf(l0, p.x); l1 = fminf(l1, p.y); l2 = fminf(l2, p.z); h0 = fmaxf(h0, p.x); h1 = fmaxf(h1, p.y); h2 = fmaxf(h2, p.z); }
+        const float4 p = pts[ci * BUCKET + k];
+        if (p.x < INFINITY) { l0 = fminf(l0, p.x); l1 = fminf(l1, p.y); l2 = fminf(l2, p.z); h0 = fmaxf(h0, p.x); h1 = fmaxf(h1, p.y); h2 = fmaxf(h2, p.z); }
       }
     } else {
       const float4* r = child_nodes + (size_t)ci * NODE_F4;
@@ -132,55 +139,71 @@ __global__ void node_kernel(const float4* __restrict__ pts, int n_valid, const f
   float4* o = nodes + (size_t)j * NODE_F4;
   o[2 * c] = make_float4(l0, l1, l2, 0.f); o[2 * c + 1] = make_float4(h0, h1, h2, 0.f);
 }
+__global__ void bbox_publish_kernel(const int* __restrict__ bbox, float* __restrict__ out6) {   // decoded box for the query-sort kernel
+  if (threadIdx.x < 6) out6[threadIdx.x] = ord2f(bbox[threadIdx.x]);
+}
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// Everything is enqueued on the context's stream and nothing is read back: the layout is sized from n_src (the non-finite points -- there are
+// usually none -- only leave a few all-pad buckets with neutral boxes at the end), the count of finite points and the box stay on the device.
 int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t) {
   { DevBuf keep = t->storage; *t = BucketTree(); t->storage = keep; }   // re-indexing in place (ll_map_rebuild) reuses the allocation
   t->n_src = n_src;
   cudaStream_t s = ctx->stream;
+  // key width: lidar maps are surfaces, so a grid of 2^b cells per axis has ~4^b occupied cells; b = ceil(log2(n) / 2) - 1 keeps the occupied
+  // cells well below a bucket's 32 points (5M points: b = 11, 34 sorted bits = 5 radix passes instead of 8; 30k points: b = 7, 3 passes)
+  int lg = 0; while ((1ll << lg) < (long long)(n_src > 0 ? n_src : 1)) lg++;
+  int bits = (lg + 1) / 2 - 1; if (bits < 5) bits = 5; if (bits > 21) bits = 21;
+  const int key_bits = 3 * bits, sort_bits = key_bits + 1;   // one more bit: non-finite points get the key 2^key_bits and sort behind every real one
+  const bool k32 = sort_bits <= 32;
+  const size_t ksz = k32 ? 4 : 8;
   // scratch: bbox(8 ints) | keys | keys_out | vals | vals_out | cub temp
   size_t temp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, n_src > 0 ? n_src : 1, 0, 63, s);
-  size_t off_bbox = 0, off_k0 = align256(64), off_k1 = off_k0 + align256((size_t)n_src * 8), off_v0 = off_k1 + align256((size_t)n_src * 8),
+  if (k32) cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, n_src > 0 ? n_src : 1, 0, sort_bits, s);
+  else cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, n_src > 0 ? n_src : 1, 0, sort_bits, s);
+  size_t off_bbox = 0, off_k0 = align256(64), off_k1 = off_k0 + align256((size_t)n_src * ksz), off_v0 = off_k1 + align256((size_t)n_src * ksz),
          off_v1 = off_v0 + align256((size_t)n_src * 4), off_tmp = off_v1 + align256((size_t)n_src * 4);
   LL_CUDA(ctx, ctx->scratch.reserve(off_tmp + temp_bytes + 256));
   char* base = ctx->scratch.as<char>();
   int* bbox = (int*)(base + off_bbox);
-  unsigned long long* k0 = (unsigned long long*)(base + off_k0); unsigned long long* k1 = (unsigned long long*)(base + off_k1);
   int* v0 = (int*)(base + off_v0); int* v1 = (int*)(base + off_v1);
-  int n_valid = 0;
-  bbox_init_kernel<<<1, 32, 0, s>>>(bbox); ctx->launches++;
-  if (n_src > 0) {
-    int grid = min(ll_div_up(n_src, 256), ctx->num_sms * 8);
-    bbox_kernel<<<grid, 256, 0, s>>>(d_src, n_src, bbox); ctx->launches++;
-    hilbert_kernel<<<ll_div_up(n_src, 256), 256, 0, s>>>(d_src, n_src, bbox, k0, v0); ctx->launches++;
-    LL_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + off_tmp, temp_bytes, k0, k1, v0, v1, n_src, 0, 63, s)); ctx->launches += 8;
-    int hb[8];
-    LL_CUDA(ctx, cudaMemcpyAsync(hb, bbox, 7 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    LL_CUDA(ctx, cudaStreamSynchronize(s));
-    n_valid = hb[6];
-    for (int k = 0; k < 6; k++) { int v = hb[k]; v = v >= 0 ? v : v ^ 0x7fffffff; memcpy(&t->bbox[k], &v, 4); }
-  }
-  t->n = n_valid; t->n_pad = ll_div_up(n_valid > 0 ? n_valid : 1, BUCKET) * BUCKET;
+  t->n = n_src; t->n_pad = ll_div_up(n_src > 0 ? n_src : 1, BUCKET) * BUCKET;
   // level sizes: level 0 nodes have buckets as children; the top level has exactly one node
   int cnt = ll_div_up(t->n_pad / BUCKET, FANOUT); t->n_levels = 0;
   for (;;) { t->level_count[t->n_levels++] = cnt; if (cnt <= 1) break; if (t->n_levels == LL_MAX_LEVELS) { ctx->set_error("map too large for LL_MAX_LEVELS"); return LL_ERR_CAPACITY; } cnt = ll_div_up(cnt, FANOUT); }
   // node storage is laid out top level first
   size_t node_total = 0; for (int l = 0; l < t->n_levels; l++) node_total += (size_t)t->level_count[l];
-  size_t bytes = align256((size_t)t->n_pad * 16) + align256((size_t)n_src * 16) + align256(node_total * NODE_F4 * 16);
+  size_t bytes = align256((size_t)t->n_pad * 16) + align256((size_t)n_src * 16) + align256(node_total * NODE_F4 * 16) + 256;
   LL_CUDA(ctx, t->storage.reserve(bytes));
   char* p = t->storage.as<char>();
   t->pts = (float4*)p; p += align256((size_t)t->n_pad * 16);
   float4* nodes = (float4*)p; p += align256(node_total * NODE_F4 * 16);
   { size_t off = 0; for (int l = t->n_levels - 1; l >= 0; l--) { t->lo[l] = nodes + off * NODE_F4; off += (size_t)t->level_count[l]; } }
   t->hi[0] = nodes;   // base of the node array (top level first)
-  t->src = (float4*)p;
-  if (n_src > 0) LL_CUDA(ctx, cudaMemcpyAsync(t->src, d_src, (size_t)n_src * 16, cudaMemcpyDeviceToDevice, s));
-  gather_kernel<<<ll_div_up(t->n_pad, 256), 256, 0, s>>>(d_src, v1, n_valid, t->n_pad, t->pts); ctx->launches++;
+  t->src = (float4*)p; p += align256((size_t)n_src * 16);
+  t->d_bbox = (float*)p;
+  bbox_init_kernel<<<1, 32, 0, s>>>(bbox); ctx->launches++;
+  if (n_src > 0) {
+    int grid = min(ll_div_up(n_src, 256), ctx->num_sms * 8);
+    bbox_kernel<<<grid, 256, 0, s>>>(d_src, n_src, bbox); ctx->launches++;
+    if (k32) {
+      unsigned* k0 = (unsigned*)(base + off_k0); unsigned* k1 = (unsigned*)(base + off_k1);
+      hilbert_kernel<unsigned><<<ll_div_up(n_src, 256), 256, 0, s>>>(d_src, n_src, bbox, bits, k0, v0); ctx->launches++;
+      LL_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + off_tmp, temp_bytes, k0, k1, v0, v1, n_src, 0, sort_bits, s));
+    } else {
+      unsigned long long* k0 = (unsigned long long*)(base + off_k0); unsigned long long* k1 = (unsigned long long*)(base + off_k1);
+      hilbert_kernel<unsigned long long><<<ll_div_up(n_src, 256), 256, 0, s>>>(d_src, n_src, bbox, bits, k0, v0); ctx->launches++;
+      LL_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + off_tmp, temp_bytes, k0, k1, v0, v1, n_src, 0, sort_bits, s));
+    }
+    ctx->launches += 3 + (sort_bits + 7) / 8;
+    LL_CUDA(ctx, cudaMemcpyAsync(t->src, d_src, (size_t)n_src * 16, cudaMemcpyDeviceToDevice, s));
+  }
+  bbox_publish_kernel<<<1, 32, 0, s>>>(bbox, t->d_bbox); ctx->launches++;
+  gather_kernel<<<ll_div_up(t->n_pad, 256), 256, 0, s>>>(d_src, v1, bbox, t->n_pad, t->pts); ctx->launches++;
   for (int l = 0; l < t->n_levels; l++) {
     const int n_child = l == 0 ? t->n_pad / BUCKET : t->level_count[l - 1];
-    node_kernel<<<ll_div_up(t->level_count[l] * FANOUT, 128), 128, 0, s>>>(t->pts, n_valid, l == 0 ? nullptr : t->lo[l - 1], n_child, t->level_count[l], t->lo[l]); ctx->launches++;
+    node_kernel<<<ll_div_up(t->level_count[l] * FANOUT, 128), 128, 0, s>>>(t->pts, l == 0 ? nullptr : t->lo[l - 1], n_child, t->level_count[l], t->lo[l]); ctx->launches++;
   }
   LL_CUDA(ctx, cudaGetLastError());
   return LL_OK;
@@ -189,21 +212,21 @@ int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t
 TreeView make_view(const BucketTree& t) {
   TreeView v; v.pts = t.pts; v.src = t.src; v.n = t.n; v.n_levels = t.n_levels;
   for (int l = 0; l < LL_MAX_LEVELS; l++) v.nodes[l] = t.lo[l];
-  for (int k = 0; k < 6; k++) v.bbox[k] = t.bbox[k];
+  v.bbox = t.d_bbox;
   return v;
 }
 
 // ------------------------------------------------------------------------------------------------ search
-// LL_GROUP lanes per query (32: one warp per query).  A step of a query's best-first search pops one item from the group's stack
-// (shared memory) and handles it with all lanes at once: a NODE -> lane c tests child c's box (two coalesced 16-B loads per lane,
-// 1 KB per group) and the qualifying children are pushed far-to-near in one shot (ballot + popc); a BUCKET -> lane c takes
-// point c (one 16-B load, 512 B per group) and the candidates are merged into the group's top-5.  The top-5 and the stack pointer are
-// replicated in the lanes.  Exact: a box gives a true lower bound of the fp32 distance and (d2, index) is a total order.
-#define GROUP LL_GROUP
+// One warp per query.  Depth-first over the 32-ary box tree, nearest child first at every node: for the node being expanded at level l, lane c
+// holds the lower bound of child c (registers -> a 128-byte row of shared memory per level), a 32-bit mask says which children are still to
+// be visited, and "pick" = one REDUX.MIN over the bounds of the remaining children that can still beat the current 5th distance.  The bound is
+// tested when a child is PICKED, against the distance list as it is then -- nothing stale is ever expanded, and once the nearest remaining
+// child of a node fails the test the whole node is finished.  A bucket = 32 points, one per lane (one coalesced 512-byte load).
+// The 5 best (d2, index) pairs live in lanes 0..4, sorted; an insertion is a ballot + two SHFL.UP.  Exact: a box gives a true lower bound of the
+// fp32 distance, (d2, index) is a total order, and ties on d2 keep the smaller index, so the result does not depend on the visiting order.
 #define KNN_THREADS 256
-#define GROUPS_PER_CTA (KNN_THREADS / GROUP)
-#define STACK_CAP (LL_GROUP == 32 ? 160 : 64)
-#define ITEM_BUCKET 0x80000000u
+#define WARPS_PER_CTA (KNN_THREADS / 32)
+#define KNN_LEVELS LL_MAX_LEVELS   // 32^8 buckets: more than any map that fits the HBM
 
 __device__ __forceinline__ bool lex_less(float d, int id, float d2, int id2) { return d < d2 || (d == d2 && id < id2); }
 
@@ -221,148 +244,95 @@ __device__ __forceinline__ float box_lb(float lox, float loy, float loz, float h
   return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
 }
 
-struct Top5 { float d[LL_KNN]; int id[LL_KNN]; };
-
-__device__ __forceinline__ void top5_insert(Top5& t, float d, int id) {
-  t.d[4] = d; t.id[4] = id;
-#pragma unroll
-  for (int j = 4; j > 0; --j) {
-    if (lex_less(t.d[j], t.id[j], t.d[j - 1], t.id[j - 1])) {
-      float td = t.d[j]; t.d[j] = t.d[j - 1]; t.d[j - 1] = td;
-      int ti = t.id[j]; t.id[j] = t.id[j - 1]; t.id[j - 1] = ti;
-    }
-  }
+// The query's 5 best so far: lane j < 5 holds the j-th smallest (d, id); d5 / id5 = lane 4's entry, known to every lane.
+struct LaneTop { float d; int id; float d5; int id5; };
+__device__ __forceinline__ void top_init(LaneTop& t) { t.d = INFINITY; t.id = 0x7fffffff; t.d5 = INFINITY; t.id5 = 0x7fffffff; }
+// (md, mi) is warp-uniform and lex-less than the 5th entry.  An index that is already in the list is ignored (seeds are real points of the map).
+__device__ __forceinline__ void top_insert(LaneTop& t, float md, int mi, int lane) {
+  const bool mine = lane < LL_KNN;
+  if (__ballot_sync(FULL, mine && t.id == mi)) return;
+  const int pos = __popc(__ballot_sync(FULL, mine && !lex_less(md, mi, t.d, t.id)));   // entries that stay in front of the newcomer
+  const float ud = __shfl_up_sync(FULL, t.d, 1); const int ui = __shfl_up_sync(FULL, t.id, 1);
+  if (mine && lane >= pos) { t.d = lane == pos ? md : ud; t.id = lane == pos ? mi : ui; }
+  t.d5 = __shfl_sync(FULL, t.d, LL_KNN - 1); t.id5 = __shfl_sync(FULL, t.id, LL_KNN - 1);
 }
-
-struct GroupStack { unsigned item[STACK_CAP]; float lb[STACK_CAP]; };
-
-// Merge this step's candidates (one per lane, flag c) into the group's top-5.  Warp-collective.  A candidate whose index is already
-// in the list is ignored, so seeding the list with real points (below) can never create duplicates.
-__device__ __forceinline__ void merge_candidates(Top5& t, float d, int id, bool c) {
-  c = c && d < INFINITY && lex_less(d, id, t.d[4], t.id[4]) && id != t.id[0] && id != t.id[1] && id != t.id[2] && id != t.id[3];
+// Merge this step's candidates (one per lane, flag c): repeatedly take the smallest one that still beats the 5th entry (<= 5 rounds).
+__device__ __forceinline__ void top_merge(LaneTop& t, float d, int id, bool c, int lane) {
+  c = c && lex_less(d, id, t.d5, t.id5);   // NaN and +inf distances fail here
   while (__any_sync(FULL, c)) {
-    float md; int mi;   // group minimum of (d, id) among the remaining candidates
-    if (GROUP == 32) {   // whole-warp group: two REDUX instructions (non-negative floats order like their bit patterns)
-      const unsigned key = c ? __float_as_uint(d) : 0xffffffffu;
-      const unsigned mn = __reduce_min_sync(FULL, key);
-      mi = (int)__reduce_min_sync(FULL, (c && key == mn) ? (unsigned)id : 0x7fffffffu);
-      md = mn == 0xffffffffu ? INFINITY : __uint_as_float(mn);
-    } else {
-      md = c ? d : INFINITY; mi = c ? id : 0x7fffffff;
-#pragma unroll
-      for (int o = GROUP / 2; o > 0; o >>= 1) {
-        const float od = __shfl_xor_sync(FULL, md, o, GROUP); const int oi = __shfl_xor_sync(FULL, mi, o, GROUP);
-        if (lex_less(od, oi, md, mi)) { md = od; mi = oi; }
-      }
-    }
-    if (md < INFINITY && lex_less(md, mi, t.d[4], t.id[4])) top5_insert(t, md, mi);
-    if (c && id == mi && d == md) c = false;
-    c = c && lex_less(d, id, t.d[4], t.id[4]);
+    const unsigned key = c ? __float_as_uint(d) : 0xffffffffu;   // non-negative floats order like their bit patterns
+    const unsigned mn = __reduce_min_sync(FULL, key);
+    const int mi = (int)__reduce_min_sync(FULL, (c && key == mn) ? (unsigned)id : 0x7fffffffu);
+    top_insert(t, __uint_as_float(mn), mi, lane);
+    if (id == mi && key == mn) c = false;
+    c = c && lex_less(d, id, t.d5, t.id5);
   }
 }
 
-// All 32 lanes of the warp must call this together (width-GROUP shuffles); `active` is uniform inside a group.
-// seed_ids: the query's 5 neighbours of the previous ICP iteration (or null / -1): their distances to the moved query seed the
-// list, so the bound is tight from the first step.  Without seeds a greedy walk (child with the smallest farthest-corner distance)
-// reaches a bucket next to the query and its points seed the list.
-__device__ __forceinline__ void group_knn5(const TreeView& tv, GroupStack& st, bool active, float qx, float qy, float qz, Top5& t, const int* seed_ids) {
-  const int gl = threadIdx.x & (GROUP - 1);   // lane inside the group
-#pragma unroll
-  for (int j = 0; j < LL_KNN; j++) { t.d[j] = INFINITY; t.id[j] = 0x7fffffff; }
-  const bool go = active && tv.n > 0;
-  // ---- seeds
-  int sid = -1;
-  if (go && seed_ids && gl < LL_KNN) sid = seed_ids[gl];
-  const bool seeded = __shfl_sync(FULL, sid, (threadIdx.x & 31) & ~(GROUP - 1), 32) >= 0;   // group-uniform: lane 0 of the group has a seed
-  if (__any_sync(FULL, go && seeded)) {
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (sid >= 0) p = __ldg(tv.src + sid);
-    merge_candidates(t, sid >= 0 ? dist2_exact(qx, qy, qz, p.x, p.y, p.z) : INFINITY, sid, sid >= 0);
-  }
-  if (__any_sync(FULL, go && !seeded)) {
-    const bool walk = go && !seeded;
-    int idx = 0;
-    const int max_levels = __reduce_max_sync(FULL, tv.n_levels);   // corner / surface groups of one warp may use different trees
-    for (int lv = max_levels - 1; lv >= 0; lv--) {
-      float md = INFINITY;
-      if (walk && lv < tv.n_levels) {
-        const float4* r = tv.nodes[lv] + (size_t)idx * NODE_F4 + 2 * gl; const float4 A = __ldg(r), B = __ldg(r + 1);
-        if (A.x <= B.x) {   // a real child (the neutral box has lo = +inf > hi)
-          const float ex = fmaxf(fabsf(qx - A.x), fabsf(qx - B.x)), ey = fmaxf(fabsf(qy - A.y), fabsf(qy - B.y)), ez = fmaxf(fabsf(qz - A.z), fabsf(qz - B.z));
-          md = ex * ex + ey * ey + ez * ez;
-        }
-      }
-      float mm = md;
-#pragma unroll
-      for (int o = GROUP / 2; o > 0; o >>= 1) mm = fminf(mm, __shfl_xor_sync(FULL, mm, o, GROUP));
-      const unsigned gmask = (GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u)) << ((threadIdx.x & 31) & ~(GROUP - 1));
-      const unsigned who = __ballot_sync(FULL, walk && md == mm && md < INFINITY) & gmask;
-      if (walk && who) idx = idx * FANOUT + ((__ffs(who) - 1) & (GROUP - 1));
+struct WarpWalk { float lb[KNN_LEVELS][32]; };   // per warp: the child bounds of the node open at every level
+
+// All 32 lanes of the warp call this together; `active` is warp-uniform.
+// seed_ids: the query's 5 neighbours of the previous ICP iteration (or null / -1): their distances to the moved query seed the list, so the
+// bound is tight before the first box is opened.
+__device__ __forceinline__ void warp_knn5(const TreeView& tv, WarpWalk& ws, bool active, float qx, float qy, float qz, LaneTop& t, const int* seed_ids) {
+  const int lane = threadIdx.x & 31;
+  top_init(t);
+  if (!(active && tv.n > 0)) return;
+  if (seed_ids) {
+    int sid = -1;
+    if (lane < LL_KNN) sid = seed_ids[lane];
+    if (__any_sync(FULL, sid >= 0)) {
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sid >= 0) p = __ldg(tv.src + sid);
+      top_merge(t, sid >= 0 ? dist2_exact(qx, qy, qz, p.x, p.y, p.z) : INFINITY, sid, sid >= 0, lane);
     }
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (walk) p = __ldg(tv.pts + (size_t)idx * BUCKET + gl);
-    merge_candidates(t, walk ? dist2_exact(qx, qy, qz, p.x, p.y, p.z) : INFINITY, __float_as_int(p.w), walk);
   }
-  // ---- exact best-first search, pruned by the (already tight) 5th distance
-  int sp = 0;
-  if (go) { if (gl == 0) { st.item[0] = (unsigned)(tv.n_levels - 1) << 26; st.lb[0] = 0.f; } sp = 1; }
-  __syncwarp();
-  while (__any_sync(FULL, sp > 0)) {
-    // ---- pop (skip items that the shrinking bound has made useless)
-    bool have = false; unsigned item = 0;
-    while (sp > 0) { sp--; if (st.lb[sp] <= t.d[4]) { item = st.item[sp]; have = true; break; } }
-    const bool is_bucket = have && (item & ITEM_BUCKET);
-    const bool is_node = have && !is_bucket;
-    const int lv = (int)((item >> 26) & 31u);
-    const int idx = (int)(is_bucket ? (item & 0x7fffffffu) : (item & 0x03ffffffu));
-    // ---- one batch of loads per step: child box (2 x 16 B) or point (16 B)
-    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
-    if (is_node) { const float4* r = tv.nodes[lv] + (size_t)idx * NODE_F4 + 2 * gl; A = __ldg(r); B = __ldg(r + 1); }
-    else if (is_bucket) A = __ldg(tv.pts + (size_t)idx * BUCKET + gl);
-    __syncwarp();   // stack reads above are complete before anyone pushes below
-    if (__any_sync(FULL, is_node)) {
-      const float lb = is_node ? box_lb(A.x, A.y, A.z, B.x, B.y, B.z, qx, qy, qz) : INFINITY;
-      const bool q = is_node && lb < INFINITY && lb <= t.d[4];
-      // push every qualifying child in one shot; the nearest one goes on top of the stack (it is popped next), the others in lane order
-      const unsigned wq = __ballot_sync(FULL, q);
-      const unsigned gmask = (GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u)) << ((threadIdx.x & 31) & ~(GROUP - 1));
-      const unsigned gq = wq & gmask;
-      const int nq = __popc(gq);
-      float mlb = q ? lb : INFINITY;
-#pragma unroll
-      for (int o = GROUP / 2; o > 0; o >>= 1) mlb = fminf(mlb, __shfl_xor_sync(FULL, mlb, o, GROUP));
-      const unsigned near = __ballot_sync(FULL, q && lb == mlb) & gmask;
-      const int near_lane = __ffs(near) - 1;                       // warp lane of the nearest qualifying child (or -1)
-      const int me = threadIdx.x & 31;
-      if (q) {
-        const unsigned below = gq & ((1u << me) - 1u);
-        int pos = __popc(below); if (near_lane >= 0 && near_lane < me) pos--;   // rank among the non-nearest
-        if (me == near_lane) pos = nq - 1;
-        st.item[sp + pos] = (lv == 0 ? ITEM_BUCKET : ((unsigned)(lv - 1) << 26)) | (unsigned)(idx * FANOUT + gl); st.lb[sp + pos] = lb;
-      }
-      if (is_node) sp += nq;
+  const int top = tv.n_levels - 1;
+  int l = top, idx = 0;          // the node open at level l is node `idx` of that level
+  unsigned remv = 0;             // lane k keeps the mask of the children still to visit of the node open at level k
+  bool open_node = true;
+  for (;;) {
+    if (open_node) {             // expand node idx of level l: one box per lane (2 x 16-byte loads, 1 KB per node)
+      const float4* r = tv.nodes[l] + (size_t)idx * NODE_F4 + 2 * lane;
+      const float4 A = __ldg(r), B = __ldg(r + 1);
+      const float lb = box_lb(A.x, A.y, A.z, B.x, B.y, B.z, qx, qy, qz);   // a missing child has the neutral box (+inf, -inf): lb = +inf
+      ws.lb[l][lane] = lb;
+      const unsigned m = __ballot_sync(FULL, lb <= t.d5 && lb < INFINITY);
+      if (lane == l) remv = m;
+      open_node = false;   // (every lane only ever reads back its own slot of the row: no synchronisation needed)
     }
-    if (__any_sync(FULL, is_bucket)) merge_candidates(t, is_bucket ? dist2_exact(qx, qy, qz, A.x, A.y, A.z) : INFINITY, __float_as_int(A.w), is_bucket);
-    __syncwarp();   // pushes are visible before the next pop
+    // pick the nearest remaining child of the node open at level l that can still hold a neighbour
+    const float lb = ws.lb[l][lane];
+    const unsigned rem = __shfl_sync(FULL, remv, l);
+    const bool ok = ((rem >> lane) & 1u) && lb <= t.d5;
+    const unsigned key = ok ? __float_as_uint(lb) : 0xffffffffu;
+    const unsigned mn = __reduce_min_sync(FULL, key);
+    if (mn == 0xffffffffu) {     // nothing left here: back to the parent (whose bounds are still in its row)
+      if (l == top) break;
+      l++; idx >>= 5; continue;
+    }
+    const unsigned who = __ballot_sync(FULL, key == mn);
+    const int c = __ffs(who) - 1;
+    const unsigned okm = __ballot_sync(FULL, ok);
+    if (lane == l) remv = okm & ~(1u << c);   // (okm is a subset of rem) the children that failed the test now can never pass it later
+    const int child = idx * FANOUT + c;
+    if (l == 0) {                // a bucket: one point per lane
+      const float4 P = __ldg(tv.pts + (size_t)child * BUCKET + lane);
+      top_merge(t, dist2_exact(qx, qy, qz, P.x, P.y, P.z), __float_as_int(P.w), true, lane);   // pad points are +inf: never candidates
+    } else { l--; idx = child; open_node = true; }
   }
 }
 
 // Parity hook (ll_knn): world-frame queries in caller order.
 __global__ void __launch_bounds__(KNN_THREADS) knn_query_kernel(TreeView tv, const float4* __restrict__ q, int nq, int* __restrict__ idx5, float* __restrict__ d5) {
-  __shared__ GroupStack stacks[GROUPS_PER_CTA];
-  const int g = blockIdx.x * GROUPS_PER_CTA + (threadIdx.x / GROUP), gl = threadIdx.x & (GROUP - 1);
+  __shared__ WarpWalk walks[WARPS_PER_CTA];
+  const int g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const bool have = g < nq;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f); if (have) p = __ldg(&q[g]);
   const bool active = have && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
-  Top5 t; group_knn5(tv, stacks[threadIdx.x / GROUP], active, p.x, p.y, p.z, t, nullptr);
-  if (have && gl < LL_KNN) {
-    float d = t.d[0]; int id = t.id[0];
-#pragma unroll
-    for (int j = 1; j < LL_KNN; j++) if (gl == j) { d = t.d[j]; id = t.id[j]; }
-    idx5[g * LL_KNN + gl] = (id == 0x7fffffff) ? -1 : id; d5[g * LL_KNN + gl] = d;
-  }
+  LaneTop t; warp_knn5(tv, walks[threadIdx.x >> 5], active, p.x, p.y, p.z, t, nullptr);
+  if (have && lane < LL_KNN) { idx5[g * LL_KNN + lane] = (t.id == 0x7fffffff) ? -1 : t.id; d5[g * LL_KNN + lane] = t.d; }
 }
-
 
 // Spatial sort key of a feature at the current pose: class bit (corner/surface) | 21-bit Hilbert index (7 bits per axis) inside the tree's box.
 // Neighbouring queries then sit in the same warp / CTA, walk the same tree nodes and buckets, and hit them in L1.
@@ -374,7 +344,7 @@ __global__ void query_key_kernel(KnnBlocksArgs a, unsigned* __restrict__ keys, i
   const float4 f = __ldg(&a.feat[i]);
   double wx, wy, wz; qrot_d(a.pose, (double)f.x, (double)f.y, (double)f.z, wx, wy, wz);
   const float c[3] = {(float)(wx + a.pose[4]), (float)(wy + a.pose[5]), (float)(wz + a.pose[6])};
-  const float* bb = is_corner ? a.corner.bbox : a.surf.bbox;
+  const float* bb = is_corner ? a.corner.bbox : a.surf.bbox;   // device memory: the box never visits the host
   const float ext = fmaxf(fmaxf(bb[3] - bb[0], bb[4] - bb[1]), bb[5] - bb[2]);
   unsigned X[3]; bool ok = true;
 #pragma unroll
@@ -395,23 +365,15 @@ __global__ void query_key_kernel(KnnBlocksArgs a, unsigned* __restrict__ keys, i
   keys[i] = (is_corner ? 0u : 0x200000u) | h; vals[i] = i;
 }
 
-// Gates + functor constructors (K7) for one feature whose 5 nearest neighbours are in `t`; writes the residual-block slot `w`.
-__device__ __forceinline__ void emit_block(const KnnBlocksArgs& a, const TreeView& tv, bool is_corner, bool active, int w, const Top5& t) {
+// Gates + functor constructors (K7) for one feature whose 5 nearest neighbours are id[0..4] (d4 = the 5th squared distance); lane 0 writes slot `w`.
+__device__ __forceinline__ void emit_block(const KnnBlocksArgs& a, const TreeView& tv, bool is_corner, bool active, int w, int id0, int id1, int id2, int id4, float d4) {
   int type = 0; double ax = 0, ay = 0, az = 0, vx = 0, vy = 0, vz = 0;
   if (active) {
-    if (a.seed_ids) {
-#pragma unroll
-      for (int k = 0; k < LL_KNN; k++) a.seed_ids[(size_t)w * LL_KNN + k] = (t.id[k] == 0x7fffffff) ? -1 : t.id[k];
-    }
-    if (a.knn_d) {
-#pragma unroll
-      for (int k = 0; k < LL_KNN; k++) a.knn_d[w * LL_KNN + k] = t.d[k];
-    }
-    const bool found5 = t.id[4] != 0x7fffffff;
+    const bool found5 = id4 != 0x7fffffff;
     if (is_corner) {
-      if (found5 && (double)t.d[4] < a.max_dis_line) {
+      if (found5 && (double)d4 < a.max_dis_line) {
         if (a.icp_line) {
-          const float4 p1 = __ldg(&tv.src[t.id[0]]), p2 = __ldg(&tv.src[t.id[1]]);
+          const float4 p1 = __ldg(&tv.src[id0]), p2 = __ldg(&tv.src[id1]);
           double d0 = (double)p1.x - (double)p2.x, d1 = (double)p1.y - (double)p2.y, d2 = (double)p1.z - (double)p2.z;
           double dn = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
           if (!(dn < 0.0001)) {
@@ -424,9 +386,9 @@ __device__ __forceinline__ void emit_block(const KnnBlocksArgs& a, const TreeVie
         }
       }
     } else {
-      if (found5 && (double)t.d[4] < a.max_dis_plane) {
+      if (found5 && (double)d4 < a.max_dis_plane) {
         if (a.icp_plane) {
-          const float4 pa = __ldg(&tv.src[t.id[0]]), pb = __ldg(&tv.src[t.id[2]]), pc = __ldg(&tv.src[t.id[4]]);
+          const float4 pa = __ldg(&tv.src[id0]), pb = __ldg(&tv.src[id2]), pc = __ldg(&tv.src[id4]);
           double b0 = (double)pb.x - (double)pa.x, b1 = (double)pb.y - (double)pa.y, b2 = (double)pb.z - (double)pa.z;
           double nb = sqrt(b0 * b0 + b1 * b1 + b2 * b2); b0 = b0 / nb; b1 = b1 / nb; b2 = b2 / nb;
           double c0 = (double)pc.x - (double)pa.x, c1 = (double)pc.y - (double)pa.y, c2 = (double)pc.z - (double)pa.z;
@@ -448,9 +410,9 @@ __device__ __forceinline__ void emit_block(const KnnBlocksArgs& a, const TreeVie
 // type 0 invalid / 1 line / 2 plane, blk_v[slot*3..] = unit line direction or (un-normalised) plane normal, in fp64.
 __global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a) {
   if (a.st->icp_done) return;   // launched ahead of the termination test by the host: the ICP loop has already ended
-  __shared__ GroupStack stacks[GROUPS_PER_CTA];
-  const int j = blockIdx.x * GROUPS_PER_CTA + (threadIdx.x / GROUP);
-  const int gl = threadIdx.x & (GROUP - 1);
+  __shared__ WarpWalk walks[WARPS_PER_CTA];
+  const int j = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   const int M = a.n_corner + a.n_surf;
   const bool have = j < M;
   const int w = have ? (a.perm ? a.perm[j] : j) : 0;      // original feature index
@@ -488,16 +450,21 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a
   { const int ncls = is_corner ? a.n_corner : a.n_surf;
     if (have && ncls > 2 * a.cap) skipped = ll_cap_uniform_f(a.rng_seed, a.st->icp_iter, is_corner ? 0 : 1, is_corner ? w : w - a.n_corner) * (float)ncls > (float)(2 * a.cap); }
   const bool active = have && owned && finite_in && !skipped;
-  Top5 t;
-  group_knn5(tv, stacks[threadIdx.x / GROUP], active, qx, qy, qz, t, (a.seed_ids && have) ? a.seed_ids + (size_t)w * LL_KNN : nullptr);
-
-  if (!have || gl != 0) return;
-  emit_block(a, tv, is_corner, active, w, t);
+  LaneTop t;
+  warp_knn5(tv, walks[threadIdx.x >> 5], active, qx, qy, qz, t, (a.seed_ids && have) ? a.seed_ids + (size_t)w * LL_KNN : nullptr);
+  if (!have) return;
+  if (active && lane < LL_KNN) {   // the neighbours seed the next ICP iteration's search (5 lanes, one 20-byte row)
+    if (a.seed_ids) a.seed_ids[(size_t)w * LL_KNN + lane] = (t.id == 0x7fffffff) ? -1 : t.id;
+    if (a.knn_d) a.knn_d[(size_t)w * LL_KNN + lane] = t.d;
+  }
+  const int id0 = __shfl_sync(FULL, t.id, 0), id1 = __shfl_sync(FULL, t.id, 1), id2 = __shfl_sync(FULL, t.id, 2);
+  if (lane != 0) return;
+  emit_block(a, tv, is_corner, active, w, id0, id1, id2, t.id5, t.d5);
 }
 
 int launch_knn_query(ll_ctx* ctx, const BucketTree& t, const float4* d_q, int nq, int* d_idx, float* d_d) {
   if (nq == 0) return LL_OK;
-  knn_query_kernel<<<ll_div_up(nq, GROUPS_PER_CTA), KNN_THREADS, 0, ctx->stream>>>(make_view(t), d_q, nq, d_idx, d_d); ctx->launches++;
+  knn_query_kernel<<<ll_div_up(nq, WARPS_PER_CTA), KNN_THREADS, 0, ctx->stream>>>(make_view(t), d_q, nq, d_idx, d_d); ctx->launches++;
   LL_CUDA(ctx, cudaGetLastError());
   return LL_OK;
 }
@@ -518,7 +485,7 @@ int launch_query_sort(ll_ctx* ctx, const KnnBlocksArgs& a, int* d_perm) {
 int launch_knn_blocks(ll_ctx* ctx, const KnnBlocksArgs& a) {
   int M = a.n_corner + a.n_surf;
   if (M == 0) return LL_OK;
-  knn_blocks_kernel<<<ll_div_up(M, GROUPS_PER_CTA), KNN_THREADS, 0, ctx->stream>>>(a);
+  knn_blocks_kernel<<<ll_div_up(M, WARPS_PER_CTA), KNN_THREADS, 0, ctx->stream>>>(a);
   ctx->launches++;
   LL_CUDA(ctx, cudaGetLastError());
   return LL_OK;

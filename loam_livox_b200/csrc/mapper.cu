@@ -1,8 +1,10 @@
-// Streaming odometry driver: Laser_mapping::process_new_scan + update_buff_for_matching in matching_mode 1, with everything resident on
-// the device (the cell maps, the match-map snapshot and its index, the features).
+// Streaming odometry driver: Laser_mapping::process_new_scan + update_buff_for_matching (matching_mode 0 = sliding window of the last
+// maximum_histroy_buffer feature clouds, the mode both shipped YAMLs select; matching_mode 1 = cells in range and in the FOV), with everything
+// resident on the device (the history window, the cell maps, the match-map snapshot and its index, the features).
 //
-// Restates, on the reference side (ROS I/O, threads, mutexes, history buffers of mode 0 and loop closure left out):
+// Restates, on the reference side (ROS I/O, threads, mutexes and loop closure left out):
 //   Laser_mapping::process_new_scan                /root/reference/source/laser_mapping.hpp:1316-1521
+//   history window push / pop                      /root/reference/source/laser_mapping.hpp:1439-1487 (mode 0 concatenation :518-531)
 //   Laser_mapping::update_buff_for_matching        /root/reference/source/laser_mapping.hpp:460-566 (mode 1 branch :471-516, whole-map VoxelGrid :533-537,
 //                                                                                                  KdTreeFLANN build :544-545)
 //   Laser_mapping::init_pointcloud_registration    /root/reference/source/laser_mapping.hpp:1266-1297
@@ -22,8 +24,41 @@ int ll_cellmap_assemble(ll_ctx*, ll_cellmap*, const double*, const double*, floa
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// m_laser_cloud_{corner,surface}_history (std::list<PointCloud>, :1446-1478) as ONE flat device array: the clouds of the window lie one after the
+// other in push order, so the concatenation of mode 0 (:518-531) is the live range itself.  Two arenas, ping-pong: when the tail reaches the end of
+// one, the live range is copied to the start of the other (no allocation per scan in steady state).
+struct HistoryWindow {
+  DevBuf buf[2]; int cur = 0;
+  std::vector<std::pair<size_t, size_t>> segs;   // (offset, count) in points, oldest first
+  size_t tail = 0;                               // first free point of buf[cur]
+  size_t head() const { return segs.empty() ? tail : segs.front().first; }
+  size_t live() const { return tail - head(); }
+  const float4* data() const { return (const float4*)buf[cur].p + head(); }
+  int push(ll_ctx* ctx, const float4* d_pts, size_t n) {
+    cudaStream_t s = ctx->stream;
+    const size_t cap = buf[cur].cap / 16;
+    if (tail + n > cap) {   // slide: live range + the new cloud into the other arena
+      const size_t need = live() + n;
+      DevBuf& o = buf[cur ^ 1];
+      LL_CUDA(ctx, cudaStreamSynchronize(s));   // (the other arena may be reallocated; nothing may still read it)
+      LL_CUDA(ctx, o.reserve((need + need / 2 + 1024) * 16));
+      const size_t h = head(), lv = live();
+      if (lv) LL_CUDA(ctx, cudaMemcpyAsync(o.p, (const float4*)buf[cur].p + h, lv * 16, cudaMemcpyDeviceToDevice, s));
+      for (auto& sg : segs) sg.first -= h;
+      cur ^= 1; tail = lv;
+    }
+    if (n) LL_CUDA(ctx, cudaMemcpyAsync((float4*)buf[cur].p + tail, d_pts, n * 16, cudaMemcpyDeviceToDevice, s));
+    segs.emplace_back(tail, n); tail += n;
+    return LL_OK;
+  }
+  void pop_front() { if (!segs.empty()) segs.erase(segs.begin()); }
+  void release() { buf[0].release(); buf[1].release(); segs.clear(); tail = 0; }
+};
+
 struct ll_mapper {
   ll_ctx* ctx = nullptr;
+  HistoryWindow his_corner, his_surf;
+  double last_his_add_q[4] = {1, 0, 0, 0}, last_his_add_t[3] = {0, 0, 0};   // m_last_his_add_q / _t (uninitialised members in the reference: defined as identity / 0)
   ll_mapper_config cfg;
   ll_cellmap* cells_corner = nullptr; ll_cellmap* cells_surf = nullptr;
   ll_map* match_map = nullptr;
@@ -45,6 +80,7 @@ void ll_mapper_config_default(ll_mapper_config* c) {
   c->cell_resolution = 1.0f; c->threshold_cell_revisit = 2000;      // laser_mapping.hpp:272, performance_precision.yaml
   c->maximum_search_range_corner = 100.f; c->maximum_search_range_surface = 100.f; c->maximum_in_fov_angle = 45.f;   // :691-695
   c->down_sample_replace = 1;                                        // :277
+  c->matching_mode = 0; c->maximum_history_size = 400;               // mapping/matching_mode, mapping/maximum_histroy_buffer (performance_precision.yaml:28-29)
   c->pipeline.pieces = 3; c->pipeline.use_piece = 0; c->pipeline.whole_frame = 1;
   c->pipeline.extractor_leaf_corner = 0.1f; c->pipeline.extractor_leaf_surf = 0.2f; c->pipeline.mapping_leaf_corner = 0.1f; c->pipeline.mapping_leaf_surf = 0.4f;
   ll_reg_state_default(&c->reg);
@@ -67,7 +103,7 @@ void ll_mapper_release(ll_mapper* m) {
   cudaSetDevice(m->ctx->device);
   ll_cellmap_release(m->cells_corner); ll_cellmap_release(m->cells_surf);
   if (m->match_map) ll_map_release(m->match_map);
-  m->work.release(); m->snap.release(); delete m;
+  m->work.release(); m->snap.release(); m->his_corner.release(); m->his_surf.release(); delete m;
 }
 int ll_mapper_pose(const ll_mapper* m, double q_wxyz[4], double t[3], int* frame_index) {
   if (!m) return LL_ERR_INVALID;
@@ -100,10 +136,14 @@ int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int
   // ---- update_buff_for_matching (mode 1): snapshot of the cells in range and in the FOV, whole-map VoxelGrid, index
   if (m->map_dirty) {
     size_t mc = 0, ms = 0; const ll_point* d_mc = nullptr; const ll_point* d_ms = nullptr; int fov_c = 0, fov_s = 0;
+    if (m->cfg.matching_mode == 0) {   // :518-531: the concatenation of the history window (the live range of the flat array)
+      mc = m->his_corner.live(); ms = m->his_surf.live(); d_mc = (const ll_point*)m->his_corner.data(); d_ms = (const ll_point*)m->his_surf.data();
+    } else {
     LL_TRY(ll_cellmap_assemble(ctx, m->cells_corner, m->q_w_curr, m->t_w_curr, m->cfg.maximum_search_range_corner, m->cfg.maximum_in_fov_angle, m->cfg.line_resolution,
                                m->cfg.down_sample_replace, nullptr, 0, &mc, &fov_c, &d_mc));
     LL_TRY(ll_cellmap_assemble(ctx, m->cells_surf, m->q_w_curr, m->t_w_curr, m->cfg.maximum_search_range_surface, m->cfg.maximum_in_fov_angle, m->cfg.plane_resolution,
                                m->cfg.down_sample_replace, nullptr, 0, &ms, &fov_s, &d_ms));
+    }
     LL_CUDA(ctx, m->snap.reserve(align256((mc + 1) * 16) + align256((ms + 1) * 16) + 256));
     float4* s0 = m->snap.as<float4>(); float4* s1 = (float4*)((char*)s0 + align256((mc + 1) * 16)); int* d_sc = (int*)((char*)s1 + align256((ms + 1) * 16));
     int hc[2] = {0, 0};
@@ -148,6 +188,22 @@ int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int
   if (ns > 0) { LL_TRY(launch_transform(ctx, d_pose, A.feat + nc, ns, w3)); LL_TRY(launch_voxel_grid(ctx, w3, ns, nullptr, m->cfg.plane_resolution, w1, d_cnt + 1)); } else LL_CUDA(ctx, cudaMemsetAsync(d_cnt + 1, 0, 4, s));
   LL_CUDA(ctx, cudaMemcpyAsync(hc, d_cnt, 8, cudaMemcpyDeviceToHost, s));
   LL_CUDA(ctx, cudaStreamSynchronize(s));
+  // history window (:1439-1478): r_diff / t_diff compare the pose adopted from the PREVIOUS scan (m_q_w_curr is only overwritten at :1498) with the
+  // pose of the last addition; history_add_t_step = history_add_angle_step = 0 (:83-84)
+  {
+    const double* q = m->q_w_curr; const double* lq = m->last_his_add_q;
+    double dot = fabs(q[0] * lq[0] + q[1] * lq[1] + q[2] * lq[2] + q[3] * lq[3]); if (dot > 1.0) dot = 1.0;
+    const double r_diff = 2.0 * acos(dot) * 57.3;
+    double t2 = 0; for (int k = 0; k < 3; k++) t2 += (m->t_w_curr[k] - m->last_his_add_t[k]) * (m->t_w_curr[k] - m->last_his_add_t[k]);
+    const double t_diff = sqrt(t2);
+    if ((int)m->his_corner.segs.size() < m->cfg.maximum_history_size || t_diff > 0.0 || r_diff > 0.0 * 57.3) {
+      for (int k = 0; k < 4; k++) m->last_his_add_q[k] = m->q_w_curr[k]; for (int k = 0; k < 3; k++) m->last_his_add_t[k] = m->t_w_curr[k];
+      LL_TRY(m->his_corner.push(ctx, w0, (size_t)hc[0]));
+      LL_TRY(m->his_surf.push(ctx, w1, (size_t)hc[1]));
+    }
+    if ((int)m->his_corner.segs.size() > m->cfg.maximum_history_size) m->his_corner.pop_front();
+    if ((int)m->his_surf.segs.size() > m->cfg.maximum_history_size) m->his_surf.pop_front();
+  }
   LL_TRY(ll_cellmap_append(ctx, m->cells_corner, w0, (size_t)hc[0], LL_FMT_XYZI16, LL_DEVICE));
   LL_TRY(ll_cellmap_append(ctx, m->cells_surf, w1, (size_t)hc[1], LL_FMT_XYZI16, LL_DEVICE));
   m->map_dirty = true;                                                           // m_if_mapping_updated_* (:1490-1491)

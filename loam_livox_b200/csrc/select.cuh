@@ -29,6 +29,21 @@ __device__ __forceinline__ void l1_set_insert(unsigned long long* __restrict__ t
   __syncthreads();
 }
 
+// Bit pattern of a non-negative double as an order-preserving key (-0.0 == 0.0 in a std::set).
+__device__ __forceinline__ unsigned long long l1_key(double v) { return (unsigned long long)__double_as_longlong(v == 0.0 ? 0.0 : v); }
+// Insert without compaction: true when this call created the entry, i.e. the caller is the (only) representative of a distinct value.
+__device__ __forceinline__ bool l1_set_insert_flag(unsigned long long* __restrict__ table, unsigned table_mask, double v, bool valid) {
+  if (!(valid && v < INFINITY)) return false;   // +inf = invalid slot, NaN never compares
+  const unsigned long long key = l1_key(v);
+  unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) & table_mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(&table[h], L1_EMPTY, key);
+    if (prev == L1_EMPTY) return true;
+    if (prev == key) return false;
+    h = (h + 1) & table_mask;
+  }
+}
+
 // Block-collective (NT threads): the k-th smallest (k = min(floor(ratio n), n-1)) of uniq[0..n) — distinct non-negative doubles, whose bit patterns
 // order like the values.  11-bit digits from the top; as soon as the bin holding the k-th element has <= 1024 members they are gathered and ranked
 // directly, which for a scan's L1 norms happens after two passes.  Returns the value to every thread.  n >= 1.

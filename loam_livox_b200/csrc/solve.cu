@@ -21,7 +21,7 @@
 
 #define FULL 0xffffffffu
 #define NSUM 29          // 21 JtJ (upper, row-major) + 6 Jtr + cost + valid-block count
-#define SOLVE_THREADS 512
+#define SOLVE_THREADS 256
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -168,37 +168,73 @@ __device__ double lm_gmax(const LmState& L, double bound) {
 __device__ void lm_finish(LmState& L, int termination) {
   L.done = 1; L.termination = termination; L.final_cost = fmin(L.initial_cost, L.min_iter_cost);
 }
-// Starts LM iterations until one needs an evaluation (sets L.trial, phase = 1) or the solve terminates.
-__device__ void lm_next_iteration(LmState& L, double bound) {
+// LevenbergMarquardtStrategy::ComputeStep + the trial point of one LM iteration as a PURE function of its inputs, so that it can be evaluated
+// ahead of the accept / reject decision for both outcomes (lm_hypothesis below).  One copy of the code (noinline): the speculative evaluation and
+// the in-line one round identically.
+struct StepIn { double H[21], g[6], x[7], scaling[6], diagonal[6], radius; int reuse_diagonal; };
+struct StepOut { double delta[6], trial[7], diagonal[6], model_cost_change, gd, dmax; int valid; };
+__device__ __noinline__ void compute_step(const StepIn& I, double bound, StepOut& O) {
+  for (int c = 0; c < 6; c++) { if (I.reuse_diagonal) O.diagonal[c] = I.diagonal[c]; else { double d = I.H[hidx(c, c)] * I.scaling[c] * I.scaling[c]; O.diagonal[c] = fmin(fmax(d, 1e-6), 1e32); } }
+  double A[6][6], rhs[6], Hs[6][6];
+  for (int i = 0; i < 6; i++) { rhs[i] = I.g[i] * I.scaling[i]; for (int j = i; j < 6; j++) { double v = I.H[hidx(i, j)] * I.scaling[i] * I.scaling[j]; Hs[i][j] = v; Hs[j][i] = v; } }
+  for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) A[i][j] = Hs[i][j];
+  for (int c = 0; c < 6; c++) { double d = sqrt(O.diagonal[c] / I.radius); A[c][c] += d * d; }
+  double step[6]; const bool solved = d_chol6(A, rhs, step);
+  O.valid = 0; O.model_cost_change = 0; O.gd = 0; O.dmax = 0;
+  if (solved) {
+    for (int c = 0; c < 6; c++) step[c] = -step[c];
+    // model_cost_change = -(J s)'(f + J s / 2) = -(s' J'f) - s' J'J s / 2
+    double sg = 0, shs = 0; for (int i = 0; i < 6; i++) { sg += step[i] * rhs[i]; double r = 0; for (int j = 0; j < 6; j++) r += Hs[i][j] * step[j]; shs += step[i] * r; }
+    O.model_cost_change = -sg - 0.5 * shs; O.valid = O.model_cost_change > 0.0 ? 1 : 0;
+  }
+  if (!O.valid) return;
+  for (int c = 0; c < 6; c++) { O.delta[c] = step[c] * I.scaling[c]; O.gd += I.g[c] * O.delta[c]; O.dmax = fmax(O.dmax, fabs(O.delta[c])); }
+  d_plus(I.x, O.delta, bound, O.trial);
+}
+__device__ __forceinline__ double radius_after_success(double radius, double rel) {   // HandleSuccessfulStep
+  const double c1 = 2.0 * rel - 1.0; radius = radius / fmax(1.0 / 3.0, 1.0 - c1 * c1 * c1); return fmin(1e16, radius);
+}
+// Inputs of the NEXT iteration's ComputeStep under hypothesis h, built from the state BEFORE the evaluation `sums` is digested:
+// h = 0: the candidate is accepted (or this is iteration zero): x <- trial, H, g <- sums, radius grows, diagonal recomputed;
+// h = 1: the candidate is rejected: x, H, g stay, radius shrinks, diagonal reused.
+__device__ void lm_hypothesis(const LmState& L, const double* sums, int h, StepIn& I) {
+  if (L.phase == 0 || h == 0) {
+    for (int i = 0; i < 21; i++) I.H[i] = sums[i]; for (int i = 0; i < 6; i++) I.g[i] = sums[21 + i]; for (int k = 0; k < 7; k++) I.x[k] = L.trial[k];
+    if (L.phase == 0) { for (int c = 0; c < 6; c++) I.scaling[c] = 1.0 / (1.0 + sqrt(I.H[hidx(c, c)])); I.radius = 1e4; }
+    else { for (int c = 0; c < 6; c++) I.scaling[c] = L.scaling[c]; I.radius = radius_after_success(L.radius, (L.x_cost - sums[27]) / L.model_cost_change); }
+    for (int c = 0; c < 6; c++) I.diagonal[c] = 0.0; I.reuse_diagonal = 0;
+  } else {
+    for (int i = 0; i < 21; i++) I.H[i] = L.H[i]; for (int i = 0; i < 6; i++) I.g[i] = L.g[i]; for (int k = 0; k < 7; k++) I.x[k] = L.x[k];
+    for (int c = 0; c < 6; c++) { I.scaling[c] = L.scaling[c]; I.diagonal[c] = L.diagonal[c]; }
+    I.radius = L.radius / L.decrease_factor; I.reuse_diagonal = 1;
+  }
+}
+// Starts LM iterations until one needs an evaluation (sets L.trial, phase = 1) or the solve terminates.  `pre`: the ComputeStep of the first
+// iteration started here, already evaluated for exactly the state L is in (see lm_hypothesis), or null.
+__device__ void lm_next_iteration(LmState& L, double bound, const StepOut* pre) {
   for (;;) {
     if (L.iteration >= L.max_iterations) { lm_finish(L, 0); return; }
     if (L.last_successful && L.last_gmax <= LM_GTOL) { lm_finish(L, 1); return; }
     if (L.radius <= 1e-32) { lm_finish(L, 5); return; }
     L.iteration++; L.total_iterations++;
-    // LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system
-    if (!L.reuse_diagonal) for (int c = 0; c < 6; c++) { double d = L.H[hidx(c, c)] * L.scaling[c] * L.scaling[c]; L.diagonal[c] = fmin(fmax(d, 1e-6), 1e32); }
-    double A[6][6], rhs[6], Hs[6][6];
-    for (int i = 0; i < 6; i++) { rhs[i] = L.g[i] * L.scaling[i]; for (int j = i; j < 6; j++) { double v = L.H[hidx(i, j)] * L.scaling[i] * L.scaling[j]; Hs[i][j] = v; Hs[j][i] = v; } }
-    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) A[i][j] = Hs[i][j];
-    for (int c = 0; c < 6; c++) { double d = sqrt(L.diagonal[c] / L.radius); A[c][c] += d * d; }
-    double step[6]; bool solved = d_chol6(A, rhs, step);
-    L.reuse_diagonal = 1;
-    bool valid = false;
-    if (solved) {
-      for (int c = 0; c < 6; c++) step[c] = -step[c];
-      // model_cost_change = -(J s)'(f + J s / 2) = -(s' J'f) - s' J'J s / 2
-      double sg = 0, shs = 0; for (int i = 0; i < 6; i++) { sg += step[i] * rhs[i]; double r = 0; for (int j = 0; j < 6; j++) r += Hs[i][j] * step[j]; shs += step[i] * r; }
-      L.model_cost_change = -sg - 0.5 * shs; valid = L.model_cost_change > 0.0;
+    StepOut tmp; const StepOut* so = pre; pre = nullptr;
+    if (!so) {
+      StepIn in; for (int i = 0; i < 21; i++) in.H[i] = L.H[i]; for (int i = 0; i < 6; i++) { in.g[i] = L.g[i]; in.scaling[i] = L.scaling[i]; in.diagonal[i] = L.diagonal[i]; }
+      for (int k = 0; k < 7; k++) in.x[k] = L.x[k]; in.radius = L.radius; in.reuse_diagonal = L.reuse_diagonal;
+      compute_step(in, bound, tmp); so = &tmp;
     }
-    if (!valid) {  // HandleInvalidStep
+    for (int c = 0; c < 6; c++) L.diagonal[c] = so->diagonal[c];
+    L.reuse_diagonal = 1;
+    if (!so->valid) {  // HandleInvalidStep
       if (++L.num_invalid >= 5) { lm_finish(L, 4); return; }
       L.radius = L.radius / L.decrease_factor; L.decrease_factor *= 2.0; L.reuse_diagonal = 1; L.last_successful = 0; continue;
     }
     L.num_invalid = 0;
-    L.gd = 0; L.dmax = 0;
-    for (int c = 0; c < 6; c++) { L.delta[c] = step[c] * L.scaling[c]; L.gd += L.g[c] * L.delta[c]; L.dmax = fmax(L.dmax, fabs(L.delta[c])); }
+    L.model_cost_change = so->model_cost_change; L.gd = so->gd; L.dmax = so->dmax;
+    for (int c = 0; c < 6; c++) L.delta[c] = so->delta[c];
+    for (int k = 0; k < 7; k++) L.trial[k] = so->trial[k];
     L.ls_iters = 0; L.prev.value_valid = 0; L.prev.gradient_valid = 0; L.ls_alpha = 1.0;
-    d_plus(L.x, L.delta, bound, L.trial); L.phase = 1; return;
+    L.phase = 1; return;
   }
 }
 // Candidate point L.trial evaluated: cost + sums (normal equations at the candidate).
@@ -214,19 +250,22 @@ __device__ void lm_accept_test(LmState& L, const double* sums, double bound) {
     double n = 0; for (int k = 0; k < 7; k++) n += L.x[k] * L.x[k]; L.x_norm = sqrt(n);
     L.x_cost = cand_cost; for (int i = 0; i < 21; i++) L.H[i] = sums[i]; for (int i = 0; i < 6; i++) L.g[i] = sums[21 + i];
     L.last_gmax = lm_gmax(L, bound); L.last_successful = 1;
-    { const double c1 = 2.0 * rel - 1.0; L.radius = L.radius / fmax(1.0 / 3.0, 1.0 - c1 * c1 * c1); } L.radius = fmin(1e16, L.radius);
+    L.radius = radius_after_success(L.radius, rel);
     L.decrease_factor = 2.0; L.reuse_diagonal = 0;
     L.min_iter_cost = fmin(L.min_iter_cost, L.x_cost);
     if (L.x_cost < L.minimum_cost) { L.minimum_cost = L.x_cost; for (int k = 0; k < 7; k++) L.x_best[k] = L.x[k]; }
+    L.pending = 0;
   } else {  // HandleUnsuccessfulStep
     L.radius = L.radius / L.decrease_factor; L.decrease_factor *= 2.0; L.reuse_diagonal = 1; L.last_successful = 0;
     L.min_iter_cost = fmin(L.min_iter_cost, cand_cost);
+    L.pending = 1;
   }
-  lm_next_iteration(L, bound);
 }
-// One evaluation finished; sums = normal equations at L.trial.
+// One evaluation finished; sums = normal equations at L.trial.  Digests it up to the point where the next LM iteration would start: L.pending = 0 / 1
+// (next iteration from the accepted / the old point: the caller finishes with lm_next_iteration and the matching pre-computed step) or -1 (the solve
+// ended, or the line search goes on and L.trial is its next sample).
 __device__ __noinline__ void lm_step(LmState& L, const double* sums, double bound) {
-  L.total_evaluations++;
+  L.total_evaluations++; L.pending = -1;
   if (L.phase == 0) {  // IterationZero
     for (int k = 0; k < 7; k++) { L.x[k] = L.trial[k]; L.x_best[k] = L.trial[k]; }
     double n = 0; for (int k = 0; k < 7; k++) n += L.x[k] * L.x[k]; L.x_norm = sqrt(n);
@@ -237,7 +276,7 @@ __device__ __noinline__ void lm_step(LmState& L, const double* sums, double boun
     L.last_gmax = lm_gmax(L, bound); L.last_successful = 1; L.iteration = 0; L.radius = 1e4; L.decrease_factor = 2.0; L.reuse_diagonal = 0; L.num_invalid = 0;
     if (L.n_valid == 0) { lm_finish(L, -1); return; }
     if (!isfinite(L.x_cost)) { lm_finish(L, 4); return; }
-    lm_next_iteration(L, bound); return;
+    L.pending = 0; return;
   }
   if (L.phase == 1) {  // projected Armijo line search sample at ls_alpha (ArmijoLineSearch::DoSearch, CUBIC interpolation)
     double gt = 0; for (int c = 0; c < 6; c++) gt += sums[21 + c] * L.delta[c];
@@ -433,43 +472,60 @@ __device__ __forceinline__ SmemSlots carve(unsigned char* base, int cap, bool mb
 #define SLOT_BYTES 64
 #define SLOT_BYTES_MB 56
 
-// Plain grid barrier on the same counter / generation pair the evaluation loop uses (cooperative launch: all CTAs are resident).
-__device__ __forceinline__ void grid_barrier(RegDevState* st, unsigned& gen, bool master, int tid) {
+// ------------------------------------------------------------------------------------------------ grid-wide exchange without a master
+// Every CTA owns one 256-byte row per parity in SolveSync: 29 sums + a generation tag.  An exchange = every CTA writes its row and tags it with
+// the generation (release), every CTA waits until all rows carry that tag (thread t polls row t: one L2 round trip, no atomics, nobody is special)
+// and reduces the rows itself in fixed order -- bit-identical sums everywhere, so every CTA advances its own copy of the solver state and there is
+// no publish step.  Rows are double-buffered by generation parity: a CTA can be at most one exchange ahead of the slowest one.  Generations grow
+// monotonically over the life of the context (SolveSync::gen is never reset), so a stale tag can never match.
+__device__ __forceinline__ double* sync_row(SolveSync* Y, unsigned gen, int cta) { return Y->rows[gen & 1u][cta]; }
+__device__ __forceinline__ void sync_arrive(SolveSync* Y, unsigned gen) {   // called by one thread after the CTA's row (if any) is written and fenced
   __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    atomicAdd(&st->bar_count, 1u);
-    if (master) { while (ld_acquire_u32(&st->bar_count) != gridDim.x) {} st->bar_count = 0; __threadfence(); st_release_u32(&st->bar_gen, gen + 1); }
-    else { while (ld_acquire_u32(&st->bar_gen) != gen + 1) {} }
-  }
-  gen++;
+  st_release_u32((unsigned*)(sync_row(Y, gen, blockIdx.x) + 31), gen);
+}
+__device__ __forceinline__ void sync_wait_all(SolveSync* Y, unsigned gen) {   // CTA-collective
+  if (threadIdx.x < gridDim.x) { const unsigned* f = (const unsigned*)(sync_row(Y, gen, threadIdx.x) + 31); while (ld_acquire_u32(f) != gen) {} }
   __syncthreads();
 }
+// plain barrier (no payload)
+__device__ __forceinline__ void grid_sync(SolveSync* Y, unsigned& gen) {
+  gen++;
+  __syncthreads();
+  if (threadIdx.x == 0) sync_arrive(Y, gen);
+  sync_wait_all(Y, gen);
+}
+
+// K10 (compute_inlier_residual_threshold, :153-161) spread over the grid: see the fused section of the kernel.
+#define K10_PASSES 6
+struct K10Smem { unsigned hist[2048]; unsigned warp_sum[SOLVE_THREADS / 32 + 1]; unsigned long long prefix, mask; int k, cnt_bin, n_distinct, done; int scratch[40]; double result; };
 
 template <bool MB>
-__global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a, int tiles_per_cta, int tile) {
+__global__ void __launch_bounds__(SOLVE_THREADS, 2) lm_solve_kernel(SolveArgs a, int tiles_per_cta, int tile) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ EvalConst E;
   __shared__ double s_red[SOLVE_THREADS / 32][NSUM + 1];
   __shared__ double s_sum[32];
-  __shared__ int s_flag;
-  __shared__ LmState s_lm;   // used by CTA 0 only: the solver state never leaves the chip during a solve
-  __shared__ SelectSmem s_sel;   // mode 4 (fused) only
+  __shared__ LmState s_lm;     // EVERY CTA keeps its own copy of the solver state and advances it identically
+  __shared__ StepOut s_pre[2]; // the next iteration's ComputeStep under both outcomes of the accept test, evaluated by warp 1 while warp 0 decides
+  __shared__ K10Smem s_k10;    // mode 4 (fused) only
   RegDevState* st = a.st;
+  SolveSync* Y = a.sync;
   if ((a.mode == 4 || a.mode <= 1) && *((volatile int*)&st->icp_done)) return;   // speculative launch after the ICP loop ended (uniform over the grid)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cap = tiles_per_cta * SOLVE_THREADS;
   const SmemSlots S = carve(s_dyn, cap, MB);
+  const bool master = blockIdx.x == 0;   // the CTA that writes results back to RegDevState and talks to the peers (nothing waits for it otherwise)
+  unsigned gen = *((volatile unsigned*)&Y->gen);   // uniform over the grid: written by the previous launch's CTA 0 at its very end
 
   const long long t_k0 = clock64();
   // mode 4 = one whole ICP iteration's solver work in ONE launch: solve #1 (prerun iterations) -> L1 norms -> std::set de-duplication + order
-  // statistic (K10) -> drop outliers from the staged blocks -> solve #2 -> pose.  The hash set is cleared here; the first evaluation barrier
-  // orders the clear before any insert.
+  // statistic (K10) -> drop outliers from the staged blocks -> solve #2 -> pose.  The hash set and the histograms are cleared here; the first
+  // exchange orders the clear before any insert.
   const bool fused = a.mode == 4;
   int cur_mode = fused ? 0 : a.mode;
   if (fused) {
     for (unsigned idx = blockIdx.x * SOLVE_THREADS + threadIdx.x; idx <= a.table_mask; idx += gridDim.x * SOLVE_THREADS) a.table[idx] = L1_EMPTY;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *a.n_uniq = 0;
+    for (unsigned idx = blockIdx.x * SOLVE_THREADS + threadIdx.x; idx < K10_PASSES * 2048u + 64u; idx += gridDim.x * SOLVE_THREADS) ((unsigned*)Y->hist)[idx] = 0u;   // hist + list_cnt + pad
   }
   // ---- stage this CTA's residual blocks
   double thr = 0;
@@ -479,7 +535,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
     int k = (int)(st->inlier_ratio * (double)nu);
     double rt = nu > 0 ? a.l1_sorted_unique[k < nu ? k : nu - 1] : 0.0;
     thr = fmax(st->inliner_dis, rt);
-    if (blockIdx.x == 0 && tid == 0) st->inlier_threshold = thr;
+    if (master && tid == 0) st->inlier_threshold = thr;
   }
   // Residual-block cap, drop rule (:434-458): with M blocks and M > cap, block i leaves the problem when rand_i > (float)cap / (float)M.
   float cap_keep = 2.0f; int cap_iter = 0, cap_seed = 0;
@@ -512,24 +568,20 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
     }
     S.type[li] = type;
   }
-  // ---- iteration zero trial point: Plus(x, 0), the projection of the start point onto the bounds (TrustRegionMinimizer::IterationZero).
-  // Every CTA computes the same value; CTA 0 (the master) owns the solver state in its shared memory for the whole solve.
-  unsigned gen = ld_acquire_u32(&st->bar_gen);
-  const bool master = blockIdx.x == 0;
+  const double bound = st->bound;
+  double x_start[7]; for (int k = 0; k < 7; k++) x_start[k] = st->x[k];   // read before anybody can write it (CTA 0 does, at the end of a solve)
   for (int ph = 0; ph < (fused ? 2 : 1); ph++) {
+  // ---- iteration zero trial point: Plus(x, 0), the projection of the start point onto the bounds (TrustRegionMinimizer::IterationZero).
   if (tid == 0) {
-    double x0[7], z[6] = {0, 0, 0, 0, 0, 0}, tr[7];
-    for (int k = 0; k < 7; k++) x0[k] = ((const volatile double*)st->x)[k];   // phase 2 of the fused mode starts from the master's result
-    d_plus(x0, z, st->bound, tr);
+    double z[6] = {0, 0, 0, 0, 0, 0}, tr[7];
+    if (ph == 1) for (int k = 0; k < 7; k++) x_start[k] = s_lm.x_best[k];   // phase 2 of the fused mode starts from solve #1's result
+    d_plus(x_start, z, bound, tr);
     if (ph == 0) setup_static(E, st);
     setup_trial<MB>(E, tr);
-    s_flag = 0;
-    if (master) {
-      LmState& L = s_lm;
-      L.phase = 0; L.iteration = 0; L.max_iterations = (fused && ph == 0) ? a.prerun_iterations : a.max_iterations; L.num_invalid = 0; L.done = 0; L.termination = 0; L.last_successful = 1; L.reuse_diagonal = 0;
-      L.ls_iters = 0; L.n_valid = 0; L.total_iterations = 0; L.total_evaluations = 0;
-      for (int k = 0; k < 7; k++) L.trial[k] = tr[k];
-    }
+    LmState& L = s_lm;
+    L.phase = 0; L.iteration = 0; L.max_iterations = (fused && ph == 0) ? a.prerun_iterations : a.max_iterations; L.num_invalid = 0; L.done = 0; L.termination = 0; L.last_successful = 1; L.reuse_diagonal = 0;
+    L.ls_iters = 0; L.n_valid = 0; L.total_iterations = 0; L.total_evaluations = 0; L.pending = -1;
+    for (int k = 0; k < 7; k++) { L.trial[k] = tr[k]; L.x_best[k] = tr[k]; }
   }
   __syncthreads();
 
@@ -579,30 +631,30 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
       }
     } else if (lane < NSUM) s_red[warp][lane] = 0.0;
     __syncthreads();
-    if (tid < NSUM) {
-      double v = 0; for (int wq = 0; wq < SOLVE_THREADS / 32; wq++) v += s_red[wq][tid];
-      a.partials[(size_t)blockIdx.x * 32 + tid] = v;
+    // ---- exchange: this CTA's 29 sums into its row, tag, wait for every row, reduce all rows in fixed order (every CTA does, identically)
+    gen++;
+    if (warp == 0) {
+      if (lane < NSUM) { double v = 0; for (int wq = 0; wq < SOLVE_THREADS / 32; wq++) v += s_red[wq][lane]; sync_row(Y, gen, blockIdx.x)[lane] = v; }
+      __syncwarp();
+      if (lane == 0) sync_arrive(Y, gen);
     }
-    __threadfence();
-    __syncthreads();
-    // ---- grid barrier: every CTA arrives; the master waits for all of them, reduces the grid in fixed order and advances the solver
     const long long t_e1 = clock64();
-    long long t_e2 = 0, t_e3 = 0;
-    if (tid == 0) atomicAdd(&st->bar_count, 1u);
-    if (master) {
-      if (tid == 0) { while (ld_acquire_u32(&st->bar_count) != gridDim.x) {} st->bar_count = 0; t_e2 = clock64(); }
-      __syncthreads();
-      __threadfence();
-      const int val = tid & 31, grp = tid >> 5;   // 16 groups x 32 values
+    sync_wait_all(Y, gen);
+    const long long t_e2 = clock64();
+    {
+      const int val = tid & 31, grp = tid >> 5;   // (SOLVE_THREADS / 32) groups x 32 values
       double v = 0;
-      if (val < NSUM) for (int b = grp; b < (int)gridDim.x; b += SOLVE_THREADS / 32) v += __ldcg(&a.partials[(size_t)b * 32 + val]);
+      if (val < NSUM) for (int b = grp; b < (int)gridDim.x; b += SOLVE_THREADS / 32) v += __ldcg(&sync_row(Y, gen, b)[val]);
       if (val < NSUM) s_red[grp][val] = v;
       __syncthreads();
       if (tid < NSUM) { double t = 0; for (int g = 0; g < SOLVE_THREADS / 32; g++) t += s_red[g][tid]; s_sum[tid] = t; }
       __syncthreads();
-      if (a.world > 1 && warp == 0) {
-        // fused all-reduce over NVLink peer memory: every rank writes its 29 sums into slot [rank] of every peer's staging
-        // buffer (double-buffered by generation parity), then sums the slots in rank order -> bit-identical on all ranks.
+    }
+    if (a.world > 1) {
+      // fused all-reduce over NVLink peer memory (CTA 0 of every rank): every rank writes its 29 sums into slot [rank] of every peer's staging
+      // buffer (double-buffered by generation parity), then sums the slots in rank order -> bit-identical on all ranks; the result goes to the
+      // other CTAs of this rank through one more tagged row.
+      if (master && warp == 0) {
         unsigned* cgen = (unsigned*)((char*)a.comm_local + LL_COMM_CTRL_OFF);   // monotonic over the life of the context
         const unsigned g1 = *cgen + 1; const int par = g1 & 1;
         for (int p = 0; p < a.world; p++) {
@@ -616,72 +668,74 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
         __syncwarp();
         double t = 0;
         if (lane < NSUM) for (int p = 0; p < a.world; p++) t += *((volatile double*)(a.comm_local + ((size_t)par * 8 + p) * 64 + lane));
-        if (lane < NSUM) s_sum[lane] = t;
+        if (lane < NSUM) Y->bcast[gen & 1u][lane] = t;
         if (lane == 0) *cgen = g1;
+        __syncwarp();
+        if (lane == 0) { __threadfence(); st_release_u32((unsigned*)&Y->bcast[gen & 1u][31], gen); }
       }
+      if (tid == 0) { const unsigned* f = (const unsigned*)&Y->bcast[gen & 1u][31]; while (ld_acquire_u32(f) != gen) {} }
       __syncthreads();
-      if (tid == 0) {
-        t_e3 = clock64();
-        LmState& L = s_lm;
-        if (cur_mode == 3) { for (int i = 0; i < 21; i++) L.H[i] = s_sum[i]; for (int i = 0; i < 6; i++) L.g[i] = s_sum[21 + i]; L.x_cost = s_sum[27]; L.n_valid = (int)(s_sum[28] + 0.5); L.done = 1; }
-        else lm_step(L, s_sum, st->bound);
-        const long long t_e4 = clock64();
-        // publish the next trial point (or the result)
-        st->lm.done = L.done;
-        if (!L.done) { for (int k = 0; k < 7; k++) st->lm.trial[k] = L.trial[k]; }
-        else {
-          st->lm = L;   // whole solver state (parity hooks / host diagnostics read it)
-          if (cur_mode != 3) {
-            for (int k = 0; k < 7; k++) st->x[k] = L.x_best[k];
-            st->total_lm_iterations += L.iteration; st->total_evaluations += L.total_evaluations;
-          }
-          if (cur_mode == 1) {   // :514-531 pose composition + ICP termination test
-            double qi[4] = {L.x_best[3], L.x_best[0], L.x_best[1], L.x_best[2]}, ti[3] = {L.x_best[4], L.x_best[5], L.x_best[6]};
-            const double* ql = st->pose_last; double tcur[3], qcur[4];
-            d_qrot(ql, ti, tcur); for (int k = 0; k < 3; k++) tcur[k] += st->pose_last[4 + k];
-            d_qmul(ql, qi, qcur);
-            for (int k = 0; k < 4; k++) st->pose_curr[k] = qcur[k]; for (int k = 0; k < 3; k++) st->pose_curr[4 + k] = tcur[k];
-            st->angular_diff = (double)((float)d_angdist(qcur, ql)) * 57.3;
-            double td = 0; for (int k = 0; k < 3; k++) td += (tcur[k] - st->pose_last[4 + k]) * (tcur[k] - st->pose_last[4 + k]); st->t_diff = sqrt(td);
-            if (MB) {   // compute_interpolatation_rodrigue (:607-620): Eigen::AngleAxisd(q_incre), used by the next iteration's pointAssociateToMap
-              double n = sqrt(qi[1] * qi[1] + qi[2] * qi[2] + qi[3] * qi[3]), ax[3], ang;
-              if (n != 0.0) { ang = 2.0 * atan2(n, fabs(qi[0])); if (qi[0] < 0) n = -n; ax[0] = qi[1] / n; ax[1] = qi[2] / n; ax[2] = qi[3] / n; }
-              else { ang = 0; ax[0] = 1; ax[1] = 0; ax[2] = 0; }
-              const double an = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]); for (int k = 0; k < 3; k++) ax[k] /= an;
-              double* H = st->interp_hat; for (int k = 0; k < 9; k++) H[k] = 0;
-              H[1] = -ax[2]; H[3] = ax[2]; H[2] = ax[1]; H[6] = -ax[1]; H[5] = -ax[0]; H[7] = ax[0];
-              for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double t = 0; for (int k = 0; k < 3; k++) t += H[i * 3 + k] * H[k * 3 + j]; st->interp_hat_sq[i * 3 + j] = t; }
-              st->interp_theta = ang;
-            }
-            if (L.termination == -1) st->icp_done = 1;   // no residual block: the host reports the error; iterations launched ahead must not run
-            st->final_cost = L.final_cost; st->initial_cost = L.initial_cost; st->num_residual_blocks = L.n_valid;
-            double dt = 0; for (int k = 0; k < 3; k++) dt += (st->t_last_opt[k] - ti[k]) * (st->t_last_opt[k] - ti[k]);
-            if (d_angdist(st->q_last_opt, qi) < 57.3 * st->min_icp_R && sqrt(dt) < st->min_icp_T) st->icp_done = 1;
-            else { for (int k = 0; k < 4; k++) st->q_last_opt[k] = qi[k]; for (int k = 0; k < 3; k++) st->t_last_opt[k] = ti[k]; }
-            st->icp_iter++;
-          }
-        }
-        { const long long t_e5 = clock64(); st->prof[0] += t_e1 - t_e0; st->prof[1] += t_e2 - t_e1; st->prof[2] += t_e3 - t_e2; st->prof[3] += t_e4 - t_e3; st->prof[4] += t_e5 - t_e4; st->prof[5] += 1; }
-        __threadfence();
-        st_release_u32(&st->bar_gen, gen + 1);
-      }
+      if (tid < NSUM) s_sum[tid] = __ldcg(&Y->bcast[gen & 1u][tid]);
+      __syncthreads();
+    }
+    const long long t_e3 = clock64();
+    // ---- advance the solver: warp 1 evaluates the next iteration's ComputeStep under both outcomes while warp 0 digests the evaluation
+    if (cur_mode == 3) {
+      if (tid == 0) { LmState& L = s_lm; for (int i = 0; i < 21; i++) L.H[i] = s_sum[i]; for (int i = 0; i < 6; i++) L.g[i] = s_sum[21 + i]; L.x_cost = s_sum[27]; L.n_valid = (int)(s_sum[28] + 0.5); L.done = 1; }
     } else {
-      if (tid == 0) { while (ld_acquire_u32(&st->bar_gen) != gen + 1) {} }
+      StepIn in;
+      if (warp == 1 && lane < 2) lm_hypothesis(s_lm, s_sum, lane, in);   // a private copy of the state BEFORE warp 0 touches it
+      __syncthreads();
+      const long long t_h0 = clock64();
+      if (warp == 1 && lane < 2) { compute_step(in, bound, s_pre[lane]); if (master && lane == 0) st->prof[13] += clock64() - t_h0; }   // Cholesky + model cost + Plus: the long pole of an LM step ...
+      else if (tid == 0) { lm_step(s_lm, s_sum, bound); if (master) st->prof[14] += clock64() - t_h0; }   // ... next to the accept test, the bookkeeping and the gradient test's Plus
+      __syncthreads();
+      if (master && tid == 0) st->prof[15] += clock64() - t_h0;
+      if (tid == 0 && s_lm.pending >= 0) lm_next_iteration(s_lm, bound, &s_pre[s_lm.pending]);
     }
-    gen++;
+    if (tid == 0 && !s_lm.done) setup_trial<MB>(E, s_lm.trial);
     __syncthreads();
-    // ---- everyone picks up the next trial point (or the final x)
-    if (tid == 0) {
-      const volatile LmState* L = &st->lm;
-      s_flag = L->done;
-      double tr[7];
-      if (L->done) for (int k = 0; k < 7; k++) tr[k] = ((const volatile double*)st->x)[k];
-      else for (int k = 0; k < 7; k++) tr[k] = L->trial[k];
-      setup_trial<MB>(E, tr);
-    }
-    __syncthreads();
-    if (s_flag) break;
+    if (master && tid == 0) { const long long t_e4 = clock64(); st->prof[0] += t_e1 - t_e0; st->prof[1] += t_e2 - t_e1; st->prof[2] += t_e3 - t_e2; st->prof[3] += t_e4 - t_e3; st->prof[5] += 1; }
+    if (s_lm.done) break;
   }
+  // ---- the solve has ended (on every CTA, with the same state)
+  if (tid == 0) {
+    LmState& L = s_lm;
+    setup_trial<MB>(E, L.x_best);   // the epilogue (L1 norms) evaluates at the solution
+    if (master) {
+      st->lm = L;   // whole solver state (parity hooks / host diagnostics read it)
+      if (cur_mode != 3) {
+        for (int k = 0; k < 7; k++) st->x[k] = L.x_best[k];
+        st->total_lm_iterations += L.iteration; st->total_evaluations += L.total_evaluations;
+      }
+      if (cur_mode == 1) {   // :514-531 pose composition + ICP termination test
+        double qi[4] = {L.x_best[3], L.x_best[0], L.x_best[1], L.x_best[2]}, ti[3] = {L.x_best[4], L.x_best[5], L.x_best[6]};
+        const double* ql = st->pose_last; double tcur[3], qcur[4];
+        d_qrot(ql, ti, tcur); for (int k = 0; k < 3; k++) tcur[k] += st->pose_last[4 + k];
+        d_qmul(ql, qi, qcur);
+        for (int k = 0; k < 4; k++) st->pose_curr[k] = qcur[k]; for (int k = 0; k < 3; k++) st->pose_curr[4 + k] = tcur[k];
+        st->angular_diff = (double)((float)d_angdist(qcur, ql)) * 57.3;
+        double td = 0; for (int k = 0; k < 3; k++) td += (tcur[k] - st->pose_last[4 + k]) * (tcur[k] - st->pose_last[4 + k]); st->t_diff = sqrt(td);
+        if (MB) {   // compute_interpolatation_rodrigue (:607-620): Eigen::AngleAxisd(q_incre), used by the next iteration's pointAssociateToMap
+          double n = sqrt(qi[1] * qi[1] + qi[2] * qi[2] + qi[3] * qi[3]), ax[3], ang;
+          if (n != 0.0) { ang = 2.0 * atan2(n, fabs(qi[0])); if (qi[0] < 0) n = -n; ax[0] = qi[1] / n; ax[1] = qi[2] / n; ax[2] = qi[3] / n; }
+          else { ang = 0; ax[0] = 1; ax[1] = 0; ax[2] = 0; }
+          const double an = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]); for (int k = 0; k < 3; k++) ax[k] /= an;
+          double* H = st->interp_hat; for (int k = 0; k < 9; k++) H[k] = 0;
+          H[1] = -ax[2]; H[3] = ax[2]; H[2] = ax[1]; H[6] = -ax[1]; H[5] = -ax[0]; H[7] = ax[0];
+          for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double t = 0; for (int k = 0; k < 3; k++) t += H[i * 3 + k] * H[k * 3 + j]; st->interp_hat_sq[i * 3 + j] = t; }
+          st->interp_theta = ang;
+        }
+        if (L.termination == -1) st->icp_done = 1;   // no residual block: the host reports the error; iterations launched ahead must not run
+        st->final_cost = L.final_cost; st->initial_cost = L.initial_cost; st->num_residual_blocks = L.n_valid;
+        double dt = 0; for (int k = 0; k < 3; k++) dt += (st->t_last_opt[k] - ti[k]) * (st->t_last_opt[k] - ti[k]);
+        if (d_angdist(st->q_last_opt, qi) < 57.3 * st->min_icp_R && sqrt(dt) < st->min_icp_T) st->icp_done = 1;
+        else { for (int k = 0; k < 4; k++) st->q_last_opt[k] = qi[k]; for (int k = 0; k < 3; k++) st->t_last_opt[k] = ti[k]; }
+        st->icp_iter++;
+      }
+    }
+  }
+  __syncthreads();
   // ---- epilogue of solve #1: loss-corrected L1 norm of every block at the solution (problem.Evaluate, :476-481)
   const long long t_p0 = clock64();
   if (cur_mode == 0) {
@@ -690,7 +744,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
       double my_l1 = INFINITY;
       if (i < a.M && tid < tile) {
         double l1 = INFINITY;
-        Slot s; s.type = S.type[li];
+        Slot s; s.type = S.type[li] & 0xff;
         if (s.type != 0) {
           double r[3];
           if (MB) {
@@ -711,43 +765,113 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) lm_solve_kernel(SolveArgs a,
           l1 = fabs(sc * r[0]) + fabs(sc * r[1]) + fabs(sc * r[2]);
         }
         a.l1[i] = l1;
-        if (fused) my_l1 = l1;
+        my_l1 = l1;
       }
-      if (fused) l1_set_insert(a.table, a.table_mask, a.uniq, a.n_uniq, my_l1, my_l1 < INFINITY, (int*)s_sel.warp_sum);   // CTA-collective: every thread calls it
+      // std::set de-duplication: the thread whose insert created the entry represents the value from here on (bit 8 of its slot's type)
+      if (fused && l1_set_insert_flag(a.table, a.table_mask, my_l1, my_l1 < INFINITY)) S.type[li] |= 0x100;
     }
   }
   if (fused && ph == 0) {
+    // ---- K10 over the whole grid (:153-161): the element of rank floor(ratio * n) among the DISTINCT L1 norms.  Radix select on the bit patterns
+    // (non-negative doubles order like their bits), 11-bit digits from the exponent down: per pass every CTA histograms the distinct values it
+    // represents (shared memory), adds its non-empty bins to the global histogram, one exchange, and every CTA finds the bin of the wanted rank in
+    // the same histogram.  When that bin holds <= 64 values they are collected and ranked directly.
     const long long q0 = clock64();
-    grid_barrier(st, gen, master, tid);                      // every rank's distinct L1 norms are in uniq[0 .. *n_uniq)
-    const long long q1 = clock64();
-    if (master) {
-      const int nu = *((volatile int*)a.n_uniq);
-      double rt = 0.0;
-      if (nu > 0) rt = block_select<SOLVE_THREADS>(a.uniq, nu, st->inlier_ratio, s_sel);
-      if (tid == 0) { st->inlier_threshold = fmax(st->inliner_dis, rt); st->n_unique = nu; }   // :484-485
+    if (tid == 0) { s_k10.prefix = 0ull; s_k10.mask = 0ull; s_k10.k = -1; s_k10.done = 0; s_k10.result = 0.0; }
+    __syncthreads();
+    for (int pass = 0; pass < K10_PASSES && !s_k10.done; pass++) {
+      const int shift = pass < 5 ? 52 - 11 * pass : 0; const unsigned dmask = pass < 5 ? 2047u : 255u;   // bits 62..52, 51..41, 40..30, 29..19, 18..8, 7..0
+      for (int b = tid; b < 2048; b += SOLVE_THREADS) s_k10.hist[b] = 0u;
+      __syncthreads();
+      const unsigned long long prefix = s_k10.prefix, himask = s_k10.mask;
+      for (int k = 0; k < tiles_per_cta; k++) {
+        const int i = (blockIdx.x + gridDim.x * k) * tile + tid, li = k * SOLVE_THREADS + tid;
+        if (i < a.M && tid < tile && (S.type[li] & 0x100)) {
+          const unsigned long long key = l1_key(a.l1[i]);
+          if ((key & himask) == prefix) atomicAdd(&s_k10.hist[(unsigned)(key >> shift) & dmask], 1u);
+        }
+      }
+      __syncthreads();
+      unsigned* gh = Y->hist[pass];
+      for (int b = tid; b < 2048; b += SOLVE_THREADS) { const unsigned c = s_k10.hist[b]; if (c) atomicAdd(&gh[b], c); }
+      grid_sync(Y, gen);
+      // every CTA: exclusive scan of the global histogram, find the bin that holds rank k
+      constexpr int BPT = 2048 / SOLVE_THREADS;
+      unsigned h[BPT], run = 0;
+#pragma unroll
+      for (int b = 0; b < BPT; b++) { h[b] = __ldcg(&gh[tid * BPT + b]); run += h[b]; }
+      unsigned incl = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+      if (lane == 31) s_k10.warp_sum[warp] = incl;
+      __syncthreads();
+      if (tid == 0) { unsigned t = 0; for (int w = 0; w < SOLVE_THREADS / 32; w++) { const unsigned c = s_k10.warp_sum[w]; s_k10.warp_sum[w] = t; t += c; } s_k10.warp_sum[SOLVE_THREADS / 32] = t; }
+      __syncthreads();
+      if (pass == 0 && tid == 0) {
+        const int n = (int)s_k10.warp_sum[SOLVE_THREADS / 32]; s_k10.n_distinct = n;
+        int k = (int)(st->inlier_ratio * (double)n); if (k > n - 1) k = n - 1; s_k10.k = k;
+        if (n == 0) s_k10.done = 1;   // no block at all: the solve reported termination -1 already
+      }
+      __syncthreads();
+      if (!s_k10.done) {
+        const unsigned excl = s_k10.warp_sum[warp] + incl - run; const unsigned k = (unsigned)s_k10.k;
+        __syncthreads();
+        if (k >= excl && k < excl + run) {   // exactly one thread
+          unsigned below = excl; int j = 0;
+#pragma unroll
+          for (int b = 0; b < BPT; b++) { if (k >= below + h[b] && j == b) { below += h[b]; j = b + 1; } }
+          const int jj = j < BPT ? j : BPT - 1;
+          s_k10.k = (int)(k - below); s_k10.cnt_bin = (int)h[jj];
+          s_k10.prefix = prefix | ((unsigned long long)(tid * BPT + jj) << shift);
+          s_k10.mask = himask | ((unsigned long long)dmask << shift);
+        }
+        __syncthreads();
+        if (s_k10.cnt_bin <= 64 || pass == K10_PASSES - 1) {
+          // collect the members of the bin (<= 64 distinct values, or all equal in their 63 bits: then any of them is the answer) and rank them
+          const unsigned long long pf = s_k10.prefix, hm = s_k10.mask;
+          for (int kk = 0; kk < tiles_per_cta; kk++) {
+            const int i = (blockIdx.x + gridDim.x * kk) * tile + tid, li = kk * SOLVE_THREADS + tid;
+            if (i < a.M && tid < tile && (S.type[li] & 0x100)) {
+              const double v = a.l1[i];
+              if ((l1_key(v) & hm) == pf) { const unsigned slot = atomicAdd(&Y->list_cnt, 1u); if (slot < 64u) Y->list[slot] = v; }
+            }
+          }
+          grid_sync(Y, gen);
+          if (tid == 0) {
+            const int m = min((int)*((volatile unsigned*)&Y->list_cnt), 64); const int want = s_k10.k; double res = 0.0;
+            for (int e = 0; e < m; e++) { const double mine = __ldcg(&Y->list[e]); int rank = 0; for (int q = 0; q < m; q++) rank += (__ldcg(&Y->list[q]) < mine) ? 1 : 0; if (rank == want) res = mine; }
+            s_k10.result = res; s_k10.done = 1;
+          }
+          __syncthreads();
+        }
+      }
     }
-    const long long q2 = clock64();
-    grid_barrier(st, gen, master, tid);
+    const double thr2 = fmax(st->inliner_dis, s_k10.n_distinct > 0 ? s_k10.result : 0.0);   // :484-485
+    if (master && tid == 0) { st->inlier_threshold = thr2; st->n_unique = s_k10.n_distinct; }
     const long long q3 = clock64();
-    const double thr2 = *((volatile double*)&st->inlier_threshold);
     for (int k = 0; k < tiles_per_cta; k++) {                // :487-499: blocks above the threshold leave the problem
       const int i = (blockIdx.x + gridDim.x * k) * tile + tid, li = k * SOLVE_THREADS + tid;
-      if (i < a.M && tid < tile && S.type[li] != 0 && a.l1[i] > thr2) S.type[li] = 0;
+      if (i < a.M && tid < tile) { const int t = S.type[li] & 0xff; S.type[li] = (t != 0 && a.l1[i] > thr2) ? 0 : t; }
     }
     cur_mode = 1;
     __syncthreads();
-    if (master && tid == 0) { const long long q4 = clock64(); st->prof[8] += q0 - t_p0; st->prof[9] += q1 - q0; st->prof[10] += q2 - q1; st->prof[11] += q3 - q2; st->prof[12] += q4 - q3; }
+    if (master && tid == 0) { const long long q4 = clock64(); st->prof[8] += q0 - t_p0; st->prof[10] += q3 - q0; st->prof[12] += q4 - q3; }
   }
   if (master && tid == 0) st->prof[7] += clock64() - t_p0;
   }   // phase
+  // hand the generation base to the next launch (stream-ordered): every CTA ended with the same `gen`
+  if (master && tid == 0) *((volatile unsigned*)&Y->gen) = gen;
 }
 
-#define SOLVE_MAX_SMEM (200 * 1024)
+#define SOLVE_MAX_SMEM (100 * 1024)   // two CTAs per SM (another context's solver, or the next launch) fit next to each other
 int solve_max_slots(ll_ctx* ctx) { return ctx->num_sms * ((SOLVE_MAX_SMEM / SLOT_BYTES) / SOLVE_THREADS) * SOLVE_THREADS; }
 
 int solve_prepare(ll_ctx* ctx) {
   LL_CUDA(ctx, cudaFuncSetAttribute((void*)lm_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_MAX_SMEM));
   LL_CUDA(ctx, cudaFuncSetAttribute((void*)lm_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_MAX_SMEM));
+  if (!ctx->d_sync) {
+    void* p = nullptr; LL_CUDA(ctx, cudaMalloc(&p, sizeof(SolveSync))); LL_CUDA(ctx, cudaMemset(p, 0, sizeof(SolveSync))); ctx->d_sync = (SolveSync*)p;
+  }
   return LL_OK;
 }
 int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
@@ -756,14 +880,14 @@ int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
   const int M1 = a.M > 0 ? a.M : 1;
   int tile = ((ll_div_up(M1, ctx->num_sms) + 31) / 32) * 32; if (tile > SOLVE_THREADS) tile = SOLVE_THREADS;
   const int tiles = ll_div_up(M1, tile);
-  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms; if (grid > LL_SYNC_ROWS) grid = LL_SYNC_ROWS;
   int tiles_per_cta = ll_div_up(tiles, grid);
   const int mb = a.deblur ? 1 : 0;
   const size_t smem = (size_t)tiles_per_cta * SOLVE_THREADS * (mb ? SLOT_BYTES_MB : SLOT_BYTES);
   if (smem > SOLVE_MAX_SMEM) { ctx->set_error("too many residual-block slots for the shared-memory-resident solver"); return LL_ERR_CAPACITY; }
   void* fn = mb ? (void*)lm_solve_kernel<true> : (void*)lm_solve_kernel<false>;
-  SolveArgs args = a; void* kargs[] = {&args, &tiles_per_cta, &tile};
-  LL_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SOLVE_THREADS), kargs, smem, ctx->stream));   // (an ordinary launch is not faster: measured)
+  SolveArgs args = a; args.sync = ctx->d_sync; void* kargs[] = {&args, &tiles_per_cta, &tile};
+  LL_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SOLVE_THREADS), kargs, smem, ctx->stream));   // co-residency of the whole grid is what the exchanges rely on
   ctx->launches++;
   return LL_OK;
 }

@@ -263,6 +263,32 @@ def scan_to_pose(ctx: Context, match_map: Map, raw, stamp, pipeline: capi.Pipeli
     return res, nc.value, ns.value
 
 
+class Scene_alignment:
+    """Mirror of Scene_alignment::find_tranfrom_of_two_mappings from the point where the four feature clouds exist
+    (/root/reference/source/scene_alignment.hpp:269-353): coarse-to-fine registration of keyframe b's features onto keyframe a's."""
+
+    def __init__(self, ctx: Context, line_res: float = 0.4, plane_res: float = 0.4, **kw):
+        self.ctx = ctx
+        self.cfg = capi.AlignCfg()
+        ctx._lib.ll_align_cfg_default(C.byref(self.cfg))
+        self.cfg.line_res, self.cfg.plane_res = line_res, plane_res
+        for k, v in kw.items():
+            setattr(self.cfg, k, v)
+
+    def find_tranfrom_of_two_mappings(self, source_line, source_plane, target_line, target_plane, t_init=(0.0, 0.0, 0.0)):
+        sl, fmt = _pts(source_line)
+        sp, _ = _pts(source_plane)
+        tl, _ = _pts(target_line)
+        tp, _ = _pts(target_plane)
+        self.cfg.t_init[:] = list(t_init)
+        res, runs = capi.RegResult(), C.c_int()
+        self.ctx.check(self.ctx._lib.ll_scene_align(self.ctx.h, sl.ctypes.data, sl.shape[0], sp.ctypes.data, sp.shape[0], tl.ctypes.data, tl.shape[0], tp.ctypes.data, tp.shape[0],
+                                                    fmt, capi.LL_HOST, C.byref(self.cfg), C.byref(res), C.byref(runs)))
+        self.m_q_w_curr, self.m_t_w_curr = np.array(res.q_w_curr), np.array(res.t_w_curr)
+        self.scales_run = runs.value
+        return res
+
+
 class Points_cloud_map:
     """Device-resident voxel-cell map as the matching path uses it (Points_cloud_map<float>, /root/reference/source/cell_map_keyframe.hpp:264;
     append_cloud :619, find_cells_in_radius :761; the consumer is update_buff_for_matching, /root/reference/source/laser_mapping.hpp:471-516)."""

@@ -302,6 +302,36 @@ def plus(x, delta, bound=0.3):
     return out
 
 
+def scene_align(source_line, source_plane, target_line, target_plane, t_init=(0.0, 0.0, 0.0), line_res=0.4, plane_res=0.4, maximum_icp_iteration=10,
+                maximum_residual_block=5000, accepted_threshold=0.2, rng_seed=0, threads=1):
+    """Scene_alignment::find_tranfrom_of_two_mappings (/root/reference/source/scene_alignment.hpp:269-353; object set-up :233-243) from the point where
+    the four feature clouds exist.  One persistent Point_cloud_registration: increment and pose carry over between the three scales."""
+    p = default_params(icp_line=0, icp_plane=1, max_final_cost=20000.0, para_max_speed=1000.0, para_max_angular_rate=360 * 57.3, inliner_dis=0.2,
+                       current_frame_index=10000000, mapping_init_accumulate_frames=100, icp_max_iterations=maximum_icp_iteration, cere_max_iterations=50,
+                       cere_prerun_times=2, maximum_allow_residual_block=maximum_residual_block, rng_seed=rng_seed, num_threads=threads,
+                       t_w_curr=list(t_init), para_buffer_incremental=[0, 0, 0, 1] + list(t_init))
+    res, runs = None, 0
+    for scale in (8, 4, 0):
+        lr, pr = max(line_res * scale, line_res), plane_res * scale
+        if pr < plane_res:
+            pr = plane_res
+            p.icp_max_iterations = maximum_icp_iteration * 2
+        sl, sp = voxel_grid(source_line, np.float32(lr)), voxel_grid(source_plane, np.float32(pr))
+        tl, tp = voxel_grid(target_line, np.float32(lr)), voxel_grid(target_plane, np.float32(pr))
+        runs += 1
+        if sl.shape[0] == 0 or sp.shape[0] == 0:
+            continue
+        st, r = register(sl, KdTree(sl), sp, KdTree(sp), tl, tp, p)
+        if st < 0:
+            raise RuntimeError(f"oracle registration failed ({st})")
+        res = r
+        p.q_w_curr[:] = list(r.q_w_curr); p.t_w_curr[:] = list(r.t_w_curr)
+        p.para_buffer_incremental[:] = [r.q_w_incre[1], r.q_w_incre[2], r.q_w_incre[3], r.q_w_incre[0]] + list(r.t_w_incre)
+        if r.registered and r.inlier_threshold > np.float32(accepted_threshold) * 2:
+            break
+    return res, runs
+
+
 class CellMap:
     """Points_cloud_map<float> as the matching path uses it (append_cloud, cells-in-radius + FOV + per-cell VoxelGrid)."""
 
@@ -335,12 +365,12 @@ class CellMap:
 
 
 class Mapper:
-    """Laser_mapping::process_new_scan + update_buff_for_matching (matching_mode 1) glued from the oracle pieces above, single-threaded
+    """Laser_mapping::process_new_scan + update_buff_for_matching (matching_mode 0: history window; 1: cell map) glued from the oracle pieces above, single-threaded
     (/root/reference/source/laser_mapping.hpp:1316-1521, :460-566, :1266-1297).  The background refresh of the match map is run at the start
     of the next scan with the pose the previous scan ended with, which is what the reference does with maximum_parallel_thread = 1."""
 
     def __init__(self, params=None, line_resolution=0.1, plane_resolution=0.4, cell_resolution=1.0, revisit_threshold=2000, search_range=100.0,
-                 fov_angle=45.0, replace=True, extractor_leaf_corner=0.1, extractor_leaf_surf=0.2, threads=1):
+                 fov_angle=45.0, replace=True, extractor_leaf_corner=0.1, extractor_leaf_surf=0.2, threads=1, matching_mode=0, maximum_history_size=400):
         self.params = params if params is not None else default_params()
         self.line_resolution, self.plane_resolution = line_resolution, plane_resolution
         self.search_range, self.fov_angle, self.replace = search_range, fov_angle, replace
@@ -349,6 +379,9 @@ class Mapper:
         self.ex = Extractor()
         self.q = np.array(list(self.params.q_w_curr), np.float64)
         self.t = np.array(list(self.params.t_w_curr), np.float64)
+        self.matching_mode, self.maximum_history_size = matching_mode, maximum_history_size
+        self.his_corner, self.his_surf = [], []                      # m_laser_cloud_{corner,surface}_history (:1446-1478)
+        self.last_his_add_q, self.last_his_add_t = np.array([1.0, 0, 0, 0]), np.zeros(3)   # uninitialised in the reference: defined as identity / 0
         self.frame_index = 0
         self.last_time_stamp = 0.0
         self.dirty = False
@@ -369,8 +402,13 @@ class Mapper:
         frame_index_for_reg = self.frame_index
         self.frame_index += 1
         if self.dirty:
-            mc, fc = self.cells_corner.assemble(self.q, self.t, self.search_range, self.fov_angle, self.line_resolution, self.replace)
-            ms, fs = self.cells_surf.assemble(self.q, self.t, self.search_range, self.fov_angle, self.plane_resolution, self.replace)
+            if self.matching_mode == 0:      # :518-531: concatenation of the history window
+                z = np.zeros((0, 4), np.float32)
+                mc, fc = (np.concatenate(self.his_corner) if self.his_corner else z), 0
+                ms, fs = (np.concatenate(self.his_surf) if self.his_surf else z), 0
+            else:
+                mc, fc = self.cells_corner.assemble(self.q, self.t, self.search_range, self.fov_angle, self.line_resolution, self.replace)
+                ms, fs = self.cells_surf.assemble(self.q, self.t, self.search_range, self.fov_angle, self.plane_resolution, self.replace)
             self.map_c, self.map_s = voxel_grid(mc, self.line_resolution), voxel_grid(ms, self.plane_resolution)
             self.tree_c = KdTree(self.map_c) if self.map_c.shape[0] else None
             self.tree_s = KdTree(self.map_s) if self.map_s.shape[0] else None
@@ -395,6 +433,16 @@ class Mapper:
         t = np.array(list(res.t_w_curr)) if res is not None else self.t
         wc = voxel_grid(transform(c, q, t), self.line_resolution) if c.shape[0] else c
         ws = voxel_grid(transform(s, q, t), self.plane_resolution) if s.shape[0] else s
+        # :1439-1478: r_diff / t_diff use the pose adopted from the PREVIOUS scan (m_q_w_curr is overwritten only at :1498); steps are 0 (:83-84)
+        r_diff = 2.0 * np.arccos(min(1.0, abs(float(np.dot(self.q, self.last_his_add_q))))) * 57.3
+        t_diff = float(np.linalg.norm(self.t - self.last_his_add_t))
+        if len(self.his_corner) < self.maximum_history_size or t_diff > 0.0 or r_diff > 0.0:
+            self.last_his_add_q, self.last_his_add_t = self.q.copy(), self.t.copy()
+            self.his_corner.append(wc); self.his_surf.append(ws)
+        if len(self.his_corner) > self.maximum_history_size:
+            self.his_corner.pop(0)
+        if len(self.his_surf) > self.maximum_history_size:
+            self.his_surf.pop(0)
         self.cells_corner.append_cloud(wc)
         self.cells_surf.append_cloud(ws)
         self.last.update(appended_corner=wc.shape[0], appended_surf=ws.shape[0])

@@ -19,4 +19,4 @@ for rep in range(3):
         if rep == 2:
             n = o[5]
             us = o / 1965.0
-            print(f"scan {k}: icp {res.icp_iterations} evals {int(n)} solve_ms {res.gpu_ms_solve_all:.3f} | per eval us: eval {us[0]/n:.2f} wait {us[1]/n:.2f} reduce {us[2]/n:.2f} lm {us[3]/n:.2f} publish {us[4]/n:.2f} | per launch us: staging {us[6]/res.icp_iterations:.2f} L1+K10+tail {us[7]/res.icp_iterations:.2f} | K10 per launch us: l1+insert {us[8]/res.icp_iterations:.2f} bar {us[9]/res.icp_iterations:.2f} select {us[10]/res.icp_iterations:.2f} bar {us[11]/res.icp_iterations:.2f} drop {us[12]/res.icp_iterations:.2f} | total accounted {us[:5].sum()/1e3 + (us[6]+us[7])/1e3:.3f} ms")
+            print(f"scan {k}: icp {res.icp_iterations} evals {int(n)} solve_ms {res.gpu_ms_solve_all:.3f} | per eval us: eval {us[0]/n:.2f} wait {us[1]/n:.2f} reduce {us[2]/n:.2f} lm {us[3]/n:.2f} publish {us[4]/n:.2f} | per launch us: staging {us[6]/res.icp_iterations:.2f} L1+K10+tail {us[7]/res.icp_iterations:.2f} | K10 per launch us: l1+insert {us[8]/res.icp_iterations:.2f} bar {us[9]/res.icp_iterations:.2f} select {us[10]/res.icp_iterations:.2f} bar {us[11]/res.icp_iterations:.2f} drop {us[12]/res.icp_iterations:.2f} | LM step per eval us: compute_step (warp 1) {us[13]/n:.2f} lm_step (warp 0) {us[14]/n:.2f} both+sync {us[15]/n:.2f} | total accounted {us[:5].sum()/1e3 + (us[6]+us[7])/1e3:.3f} ms")

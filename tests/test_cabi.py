@@ -59,3 +59,20 @@ def test_pose_log_format_matches_reference_printf():
     want = "--------------------\n" + "Curr_Q = %f,%f,%f,%f\r\n" % (0.9, 0.1, -0.2, 0.3) + "Curr_T = %f,%f,%f\r\n" % (1.5, -2.25, 0.125) + \
            "Incre_Q = %f,%f,%f,%f\r\n" % (1.0, 0.001, 0.002, -0.003) + "Incre_T = %f,%f,%f\r\n" % (0.01, 0.02, -0.03) + "Cost=%f,blk_size = %d \r\n" % (12.3456789, 4321)
     assert format_pose_log(r) == want
+
+
+def test_cpp_mirror_compiles_links_and_runs(tmp_path):
+    """include/loamlivox_b200.hpp (the reference's class names over the C-ABI) is compiled with g++, linked against the product library and run;
+    on a box without a GPU the program must stop at ll_ctx_create with LL_ERR_CUDA (no fallback), on a GPU box it runs a tiny extraction."""
+    import os
+    import subprocess
+    from loam_livox_b200 import capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "mirror_smoke")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "mirror_smoke.cpp"), "-o", exe,
+           "-L", libdir, "-lloamlivox_b200", "-L", "/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)

@@ -385,14 +385,16 @@ def test_cellmap_revisit_parity(ctx, oracle):
 
 
 @pytest.mark.gpu
-def test_streaming_mapper_parity(ctx, oracle):
-    """Config C3 in small: the device mapper against the oracle's process_new_scan loop, scan by scan (pose within 1e-4 m / 1e-4 rad)."""
+@pytest.mark.parametrize("mode,window", [(0, 400), (0, 3), (1, 400)])
+def test_streaming_mapper_parity(ctx, oracle, mode, window):
+    """Config C3 in small: the device mapper against the oracle's process_new_scan loop, scan by scan (pose within 1e-4 m / 1e-4 rad), in
+    matching_mode 0 (history window, the shipped YAMLs' mode; window = 3 exercises the pop at :1468-1478) and 1 (cell map)."""
     from loam_livox_b200 import capi
     from loam_livox_b200.registration import Laser_mapping
     poses = S.trajectory(n_scans=9, n_static=4, speed=1.0)
     reg = capi.default_reg_state(mapping_init_accumulate_frames=3)
-    gm = Laser_mapping(ctx, reg=reg)
-    om = oracle.Mapper(oracle.default_params(mapping_init_accumulate_frames=3, num_threads=4), threads=4)
+    gm = Laser_mapping(ctx, reg=reg, matching_mode=mode, maximum_history_size=window)
+    om = oracle.Mapper(oracle.default_params(mapping_init_accumulate_frames=3, num_threads=4), threads=4, matching_mode=mode, maximum_history_size=window)
     for k, pose in enumerate(poses):
         raw = S.make_scan(24000, pose, seed=S.SEED + k)
         res, stats = gm.process_new_scan(raw, 100.0 + 0.1 * k)
@@ -413,14 +415,15 @@ def test_streaming_mapper_parity(ctx, oracle):
 
 
 @pytest.mark.gpu
-def test_streaming_mapper_long_sequence(ctx, oracle):
-    """60 scans with yaw motion: the cell maps grow, get down-sampled-and-replaced on every refresh, and the two implementations must stay
-    together (pose 1e-4, identical feature / map / append counts) all the way."""
+@pytest.mark.parametrize("mode,window", [(0, 20), (1, 400)])
+def test_streaming_mapper_long_sequence(ctx, oracle, mode, window):
+    """60 scans with yaw motion: the history window slides (mode 0: 20 clouds, the arenas ping-pong) / the cell maps grow and get down-sampled-and-
+    replaced on every refresh (mode 1), and the two implementations must stay together (pose 1e-4, identical feature / map / append counts)."""
     from loam_livox_b200 import capi
     from loam_livox_b200.registration import Laser_mapping
     poses = S.trajectory(n_scans=60, n_static=4, speed=2.0, yaw_rate_deg=20.0)
-    gm = Laser_mapping(ctx, reg=capi.default_reg_state(mapping_init_accumulate_frames=3))
-    om = oracle.Mapper(oracle.default_params(mapping_init_accumulate_frames=3, num_threads=4), threads=4)
+    gm = Laser_mapping(ctx, reg=capi.default_reg_state(mapping_init_accumulate_frames=3), matching_mode=mode, maximum_history_size=window)
+    om = oracle.Mapper(oracle.default_params(mapping_init_accumulate_frames=3, num_threads=4), threads=4, matching_mode=mode, maximum_history_size=window)
     worst = 0.0
     for k, pose in enumerate(poses):
         raw = S.make_scan(16000, pose, seed=S.SEED + 100 + k)
@@ -615,6 +618,26 @@ def test_two_contexts_on_two_host_threads_share_one_map(oracle):
     m.release()
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.gpu
+def test_scene_alignment_parity(ctx, oracle):
+    """N4: ll_scene_align against the oracle's restatement of Scene_alignment::find_tranfrom_of_two_mappings -- same number of scales, same ICP
+    iteration / block counts at the last scale (the residual cap of 5000 binds: same counter-based draws), same transform."""
+    from test_oracle import _two_keyframes
+    from loam_livox_b200.registration import Scene_alignment
+    al, ap, bl, bp, q, t = _two_keyframes()
+    sa = Scene_alignment(ctx, rng_seed=4)
+    r = sa.find_tranfrom_of_two_mappings(al, ap, bl, bp)
+    ores, oruns = oracle.scene_align(al, ap, bl, bp, rng_seed=4, threads=8)
+    assert sa.scales_run == oruns == 3
+    assert (r.status, r.registered, r.icp_iterations, r.corner_used, r.surf_used, r.num_residual_blocks) == \
+           (ores.status, ores.registered, ores.icp_iterations, ores.corner_used, ores.surf_used, ores.num_residual_blocks)
+    dt = np.linalg.norm(np.array(r.t_w_curr) - np.array(ores.t_w_curr))
+    da = S.quat_angle(np.array(r.q_w_curr), np.array(ores.q_w_curr))
+    assert dt < 1e-6 and da < 1e-6, (dt, da)
+    assert abs(r.inlier_threshold - ores.inlier_threshold) <= 1e-6 * abs(ores.inlier_threshold)
+    assert np.linalg.norm(np.array(r.t_w_curr) - t) < 0.05 and S.quat_angle(np.array(r.q_w_curr), q) < 0.01
 
 
 # ---------------------------------------------------------------------------------------------- N3: PointCloud2 payload in

@@ -354,3 +354,26 @@ def test_converged_solution_is_a_stationary_point_of_the_huber_objective(oracle)
     for _ in range(50):
         d = rng.normal(0, 1e-4, 6)
         assert oracle.evaluate(b, guess.q, guess.t, oracle.plus(x, d, bound=10.0))[0] >= cost0 * (1 - 1e-9)
+
+
+# ---------------------------------------------------------------------------------------------- N4: scene alignment (loop-closure reuse of the registration)
+def _two_keyframes(seed=0, n_line=4000, n_plane=40000):
+    """Line / plane feature clouds of the same scene seen as two keyframes: b = a's scene (another sample) moved by the inverse of (q, t)."""
+    al, ap = S.make_map(n_line, n_plane, seed=S.SEED + 50 + seed)
+    bl, bp = S.make_map(n_line, n_plane, seed=S.SEED + 60 + seed)
+    q = S.quat_from_euler(0.02, -0.015, 0.06)
+    t = np.array([0.35, -0.25, 0.1])
+    R = S.quat_to_mat(q)
+    for c in (bl, bp):
+        c[:, :3] = ((c[:, :3].astype(np.float64) - t) @ R).astype(np.float32)    # p_b = R^T (p_a - t)  <=>  p_a = R p_b + t
+    return al, ap, bl, bp, q, t
+
+
+def test_scene_alignment_recovers_the_transform_between_two_keyframes(oracle):
+    """Scene_alignment::find_tranfrom_of_two_mappings (scene_alignment.hpp:269-353): three coarse-to-fine registrations with ICP_LINE = 0 on one
+    persistent registration object bring keyframe b onto keyframe a."""
+    al, ap, bl, bp, q, t = _two_keyframes()
+    res, runs = oracle.scene_align(al, ap, bl, bp, threads=4)
+    assert runs == 3 and res.registered == 1 and res.status == 1
+    assert np.linalg.norm(np.array(res.t_w_curr) - t) < 0.05 and S.quat_angle(np.array(res.q_w_curr), q) < 0.01
+    assert res.corner_used == 0 and 3000 < res.num_residual_blocks <= 5000 * 1.3      # ICP_LINE = 0: corners add no residual blocks (:256); the cap of 5000 binds

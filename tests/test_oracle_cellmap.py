@@ -75,11 +75,16 @@ def test_cellmap_assemble_matches_per_cell_voxelgrid(oracle):
     assert np.array_equal(out1, ref) and n_after < 20000 and np.array_equal(out2, out1)
 
 
-def test_streaming_mapper_tracks_trajectory(oracle):
-    """Oracle end to end on a short C3 sequence: poses relative to the first scan within a few centimetres of ground truth."""
+import pytest
+
+
+@pytest.mark.parametrize("mode,window", [(1, 400), (0, 400), (0, 3)])
+def test_streaming_mapper_tracks_trajectory(oracle, mode, window):
+    """Oracle end to end on a short C3 sequence: poses relative to the first scan within a few centimetres of ground truth, in matching_mode 1
+    (cell map) and 0 (history window of the last `window` feature clouds, laser_mapping.hpp:518-531,1439-1478)."""
     poses = S.trajectory(n_scans=9, n_static=4, speed=1.0)
     p = oracle.default_params(mapping_init_accumulate_frames=3, num_threads=4)
-    mp = oracle.Mapper(p, threads=4)
+    mp = oracle.Mapper(p, threads=4, matching_mode=mode, maximum_history_size=window)
     R0, t0 = poses[0].R(), poses[0].t
     errs = []
     for k, pose in enumerate(poses):
@@ -97,3 +102,4 @@ def test_streaming_mapper_tracks_trajectory(oracle):
     assert mp.frame_index == 9
     assert max(errs) < 0.05, errs
     assert mp.cells_surf.cells() > 100 and mp.cells_corner.cells() > 10
+    assert len(mp.his_surf) == min(9, window) and len(mp.his_corner) == min(9, window)
