@@ -224,6 +224,12 @@ typedef struct {
 int ll_scan_to_pose(ll_ctx* ctx, const ll_map* map, const void* raw, size_t n, int fmt, int where, double stamp,
                     const ll_pipeline_cfg* pc, const ll_reg_state* in, ll_reg_result* out, int* n_corner_used, int* n_surf_used);
 
+/* Multi-head frames (Mid-100 = three Mid-40 heads, launch/rosbag_mid100.launch:6): ONE extractor handles the heads in turn and the per-piece feature
+ * clouds of the heads are summed before the VoxelGrids (laser_feature_extractor.hpp:303-380, 339-389); then as ll_scan_to_pose.  raws / ns / stamps have n_heads
+ * entries (<= 8); the context's max_scan_points must cover the whole frame.  A head whose frame has <= 5 petals contributes nothing (:287). */
+int ll_frame_to_pose(ll_ctx* ctx, const ll_map* map, int n_heads, const void* const* raws, const size_t* ns, int fmt, int where, const double* stamps,
+                     const ll_pipeline_cfg* pc, const ll_reg_state* in, ll_reg_result* out, int* n_corner_used, int* n_surf_used);
+
 /* ---- a14: device-resident voxel-cell map (matching_mode 1) ---------------------------------------------- */
 /* Replaces Points_cloud_map<float> as the matching path uses it (cell_map_keyframe.hpp:476-1000): `resolution` is what
  * Laser_mapping passes to set_resolution (1.0 => 0.5 m cells, :674-679), `revisit_threshold` = m_minimum_revisit_threshold
@@ -273,6 +279,10 @@ int  ll_mapper_pose(const ll_mapper* mapper, double q_wxyz[4], double t[3], int*
 enum { LL_I_NONE = 0, LL_I_FLOAT32 = 7, LL_I_UINT8 = 2, LL_I_UINT16 = 4 };   /* = sensor_msgs/PointField datatype codes (0: no intensity field -> 0.0) */
 typedef struct { int point_step, offset_x, offset_y, offset_z, offset_intensity, intensity_datatype; } ll_point_layout;
 int  ll_set_point_layout(ll_ctx* ctx, const ll_point_layout* layout);
+/* The output side (pcl::toROSMsg, laser_feature_extractor.hpp:367-384): the feature cloud of the last registration on this context (which = 0 corners,
+ * 1 surfaces; what the feature node publishes on /pc2_corners, /pc2_surface) packed on the device into PointCloud2 records of the layout above.
+ * out_host may be NULL to query *n_points first. */
+int  ll_features_to_pointcloud2(ll_ctx* ctx, int which, void* out_host, size_t cap_bytes, size_t* n_points);
 /* One accepted scan in the format of the reference's poses.log (laser_mapping.hpp:1506-1511; the Ceres BriefReport line is not reproduced).
  * Returns the number of characters written (excluding the terminating 0), or -1 when cap is too small. */
 int  ll_format_pose_log(const ll_reg_result* r, char* buf, size_t cap);

@@ -97,6 +97,7 @@ class Point_cloud_registration {
   double m_minimum_icp_R_diff = 0.01, m_minimum_icp_T_diff = 0.01, m_inliner_dis = 0.02, m_inlier_ratio = 0.80;
   double m_maximum_dis_plane_for_match = 50.0, m_maximum_dis_line_for_match = 2.0;
   int ICP_PLANE = 1, ICP_LINE = 1, m_maximum_allow_residual_block = 100000;
+  int m_rand_seed = 0;   // stands in for m_rand_float's std::random_device seed (tools_random.hpp:18-25): same seed, same dropped residual blocks
   std::array<double, 4> m_q_w_last{{1, 0, 0, 0}}, m_q_w_curr{{1, 0, 0, 0}}, m_q_w_incre{{1, 0, 0, 0}};
   std::array<double, 3> m_t_w_last{{0, 0, 0}}, m_t_w_curr{{0, 0, 0}}, m_t_w_incre{{0, 0, 0}};
   double m_inlier_threshold = 0;
@@ -109,7 +110,7 @@ class Point_cloud_registration {
     ll_reg_state s; ll_reg_state_default(&s);
     s.if_motion_deblur = m_if_motion_deblur; s.current_frame_index = m_current_frame_index; s.mapping_init_accumulate_frames = m_mapping_init_accumulate_frames;
     s.icp_max_iterations = m_para_icp_max_iterations; s.cere_max_iterations = m_para_cere_max_iterations; s.cere_prerun_times = m_para_cere_prerun_times;
-    s.icp_plane = ICP_PLANE; s.icp_line = ICP_LINE; s.maximum_allow_residual_block = m_maximum_allow_residual_block;
+    s.icp_plane = ICP_PLANE; s.icp_line = ICP_LINE; s.maximum_allow_residual_block = m_maximum_allow_residual_block; s.rng_seed = m_rand_seed;
     s.para_max_angular_rate = m_para_max_angular_rate; s.para_max_speed = m_para_max_speed; s.max_final_cost = m_max_final_cost;
     s.minimum_pt_time_stamp = m_minimum_pt_time_stamp; s.maximum_pt_time_stamp = m_maximum_pt_time_stamp;
     s.minimum_icp_R_diff = m_minimum_icp_R_diff; s.minimum_icp_T_diff = m_minimum_icp_T_diff; s.inliner_dis = m_inliner_dis; s.inlier_ratio = m_inlier_ratio;
@@ -131,6 +132,32 @@ class Point_cloud_registration {
     std::vector<ll_point> out(pc_in.size());
     ctx_.check(ll_transform(ctx_.get(), m_q_w_curr.data(), m_t_w_curr.data(), pc_in.data(), pc_in.size(), LL_FMT_PCL32, LL_HOST, out.data()));
     pt_out = to_cloud(out); return (unsigned int)pc_in.size();
+  }
+ private:
+  Context& ctx_;
+};
+
+// ---- Scene_alignment::find_tranfrom_of_two_mappings (scene_alignment.hpp:269-353) from the four feature clouds on ------------------------
+class Scene_alignment {
+ public:
+  float m_line_res = 0.4f, m_plane_res = 0.4f, m_accepted_threshold = 0.2f;
+  int m_para_scene_alignments_maximum_residual_block = 5000, m_maximum_icp_iteration = 10, m_rand_seed = 0;
+  std::array<double, 4> m_q_w_curr{{1, 0, 0, 0}};   // m_pc_reg.m_q_w_curr / m_t_w_curr after the call: keyframe b into keyframe a
+  std::array<double, 3> m_t_w_curr{{0, 0, 0}};
+  ll_reg_result m_last{}; int m_scales_run = 0;
+  explicit Scene_alignment(Context& ctx) : ctx_(ctx) {}
+  // returns m_pc_reg.m_inlier_threshold (the loop-closure score; the reference truncates it to int at :390)
+  double find_tranfrom_of_two_mappings(const PointCloud& source_line, const PointCloud& source_plane, const PointCloud& target_line, const PointCloud& target_plane,
+                                       const std::array<double, 3>& center_a_minus_center_b) {
+    ll_align_cfg c; ll_align_cfg_default(&c);
+    c.line_res = m_line_res; c.plane_res = m_plane_res; c.accepted_threshold = m_accepted_threshold; c.maximum_icp_iteration = m_maximum_icp_iteration;
+    c.maximum_residual_block = m_para_scene_alignments_maximum_residual_block; c.rng_seed = m_rand_seed;
+    for (int k = 0; k < 3; k++) c.t_init[k] = center_a_minus_center_b[k];
+    ctx_.check(ll_scene_align(ctx_.get(), source_line.data(), source_line.size(), source_plane.data(), source_plane.size(), target_line.data(), target_line.size(),
+                              target_plane.data(), target_plane.size(), LL_FMT_PCL32, LL_HOST, &c, &m_last, &m_scales_run));
+    for (int k = 0; k < 4; k++) m_q_w_curr[k] = m_last.q_w_curr[k];
+    for (int k = 0; k < 3; k++) m_t_w_curr[k] = m_last.t_w_curr[k];
+    return m_last.inlier_threshold;
   }
  private:
   Context& ctx_;
@@ -160,7 +187,7 @@ class Points_cloud_map {
   Context& ctx_; ll_cellmap* map_ = nullptr;
 };
 
-// ---- Laser_mapping::process_new_scan with everything on the device (laser_mapping.hpp:1316-1521 + :460-566 mode 1) ----
+// ---- Laser_mapping::process_new_scan with everything on the device (laser_mapping.hpp:1316-1521 + :460-566, matching_mode 0 and 1) ----
 class Laser_mapping {
  public:
   explicit Laser_mapping(Context& ctx, const ll_mapper_config* cfg = nullptr) : ctx_(ctx) {

@@ -71,6 +71,8 @@ int ll_ctx_create(const ll_config* cfg, int device, ll_ctx** out) {
   cudaDeviceProp prop; ok(cudaGetDeviceProperties(&prop, device)); ctx->num_sms = prop.multiProcessorCount;
   ok(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ok(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  ok(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
+  ok(cudaEventCreateWithFlags(&ctx->ev_fork3, cudaEventDisableTiming)); ok(cudaEventCreateWithFlags(&ctx->ev_join3, cudaEventDisableTiming));
   ok(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); ok(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   ok(cudaEventCreateWithFlags(&ctx->ev_it[0], cudaEventDisableTiming)); ok(cudaEventCreateWithFlags(&ctx->ev_it[1], cudaEventDisableTiming));
   ok(cudaEventCreate(&ctx->ev0)); ok(cudaEventCreate(&ctx->ev1)); ok(cudaEventCreate(&ctx->ev2)); ok(cudaEventCreate(&ctx->ev3));
@@ -84,7 +86,8 @@ int ll_ctx_create(const ll_config* cfg, int device, ll_ctx** out) {
 void ll_ctx_destroy(ll_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  if (ctx->stream) cudaStreamSynchronize(ctx->stream); if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream); if (ctx->stream2) cudaStreamSynchronize(ctx->stream2); if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
+  ctx->scratch3.release(); if (ctx->stream3) cudaStreamDestroy(ctx->stream3); if (ctx->ev_fork3) cudaEventDestroy(ctx->ev_fork3); if (ctx->ev_join3) cudaEventDestroy(ctx->ev_join3);
   if (ctx->fg.exec) cudaGraphExecDestroy(ctx->fg.exec);
   ctx->scratch2.release(); ctx->scratch_fe.release(); if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork); if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -542,6 +545,24 @@ int ll_set_point_layout(ll_ctx* ctx, const ll_point_layout* L) {
   ctx->layout = *L;
   return LL_OK;
 }
+// pcl::toROSMsg for the feature clouds the feature node publishes (laser_feature_extractor.hpp:367-384): the features of the last ll_scan_to_pose /
+// ll_register / ll_frame_to_pose on this context (which = 0 corners, 1 surfaces; scan frame) as PointCloud2 records in the layout of ll_set_point_layout.
+int ll_features_to_pointcloud2(ll_ctx* ctx, int which, void* out_host, size_t cap_bytes, size_t* n_points) {
+  if (!ctx || !n_points || (which != 0 && which != 1)) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  RegArrays A; LL_TRY(reg_arrays(ctx, 0, &A));
+  const int n = which == 0 ? ctx->last_nc : ctx->last_ns;
+  const float4* src = which == 0 ? A.feat : A.feat + ctx->last_nc;
+  *n_points = (size_t)n;
+  const size_t bytes = (size_t)n * (size_t)ctx->layout.point_step;
+  if (!out_host || n == 0) return LL_OK;
+  if (cap_bytes < bytes) { ctx->set_error("output buffer smaller than n * point_step"); return LL_ERR_CAPACITY; }
+  LL_CUDA(ctx, ctx->stage_in.reserve(bytes));
+  LL_TRY(launch_pack_strided(ctx, src, n, ctx->stage_in.as<unsigned char>()));
+  LL_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->stage_in.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  LL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return LL_OK;
+}
 int ll_format_pose_log(const ll_reg_result* r, char* buf, size_t cap) {
   if (!r || !buf) return -1;
   const int n = snprintf(buf, cap, "--------------------\nCurr_Q = %f,%f,%f,%f\r\nCurr_T = %f,%f,%f\r\nIncre_Q = %f,%f,%f,%f\r\nIncre_T = %f,%f,%f\r\nCost=%f,blk_size = %d \r\n",
@@ -570,7 +591,14 @@ int ll_debug_solver_cycles(ll_ctx* ctx, long long out8[16]) {
 // Everything of the front end that is enqueued on the device, in the order the reference runs it; counts land in pinned memory.
 static int front_end_enqueue(ll_ctx* ctx, const ll_pipeline_cfg* pc, const RegArrays& A, int ncap) {
   cudaStream_t s = ctx->stream;
-  LL_TRY(extract_enqueue(ctx));
+  const bool petals_aside = pc->whole_frame && ctx->ex.n >= 5;   // nothing downstream of get_features reads the petal bookkeeping then
+  if (petals_aside) {
+    LL_TRY(launch_extract_points(ctx, ctx->ex.n));
+    LL_CUDA(ctx, cudaEventRecord(ctx->ev_fork3, s));
+    LL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork3, 0));
+    LL_TRY(launch_extract_petals(ctx, ctx->ex.n, ctx->stream3, ctx->scratch3));
+    LL_CUDA(ctx, cudaEventRecord(ctx->ev_join3, ctx->stream3));
+  } else LL_TRY(extract_enqueue(ctx));
   const float* d_bounds = nullptr;
   if (!pc->whole_frame) { LL_TRY(launch_piece_bounds(ctx, pc->pieces, A.bounds)); d_bounds = A.bounds + 2 * pc->use_piece; }
   LL_TRY(launch_get_features(ctx, d_bounds, 0.f, 1.f, A.tmp_a, A.tmp_b, nullptr, A.counts));
@@ -584,6 +612,7 @@ static int front_end_enqueue(ll_ctx* ctx, const ll_pipeline_cfg* pc, const RegAr
   LL_TRY(launch_voxel_grid(ctx, A.tmp_b, ncap, cnt + 1, pc->extractor_leaf_surf, A.tmp_c, cnt + 6));
   LL_TRY(launch_voxel_grid(ctx, A.tmp_c, ncap, cnt + 6, pc->mapping_leaf_surf, A.tmp_b, cnt + 7));
   LL_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+  if (petals_aside) LL_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join3, 0));
   int* h = (int*)ctx->pinned + 8192;
   LL_CUDA(ctx, cudaMemcpyAsync(h, cnt, 12 * sizeof(int), cudaMemcpyDeviceToHost, s));   // [10], [11]: min / max time stamp of the full cloud
   LL_CUDA(ctx, cudaMemcpyAsync(h + 12, ctx->ex.d_meta, 12, cudaMemcpyDeviceToHost, s));
@@ -598,7 +627,7 @@ int scan_front_end(ll_ctx* ctx, const void* raw, size_t n, int fmt, int where, d
   struct ScratchSwap { ll_ctx* c; ScratchSwap(ll_ctx* c_) : c(c_) { DevBuf t = c->scratch; c->scratch = c->scratch_fe; c->scratch_fe = t; }
                        ~ScratchSwap() { DevBuf t = c->scratch; c->scratch = c->scratch_fe; c->scratch_fe = t; } } swap_guard(ctx);
   ll_ctx::FrontGraph& g = ctx->fg;
-  void* bufs[5] = {ctx->extract_buf.p, ctx->reg_buf.p, ctx->scratch.p, ctx->scratch2.p, (void*)(size_t)ctx->scratch.cap};
+  void* bufs[6] = {ctx->extract_buf.p, ctx->reg_buf.p, ctx->scratch.p, ctx->scratch2.p, (void*)(size_t)ctx->scratch.cap, ctx->scratch3.p};
   const bool same = g.n == n && memcmp(&g.pc, pc, sizeof(*pc)) == 0 && memcmp(g.bufs, bufs, sizeof(bufs)) == 0;
   if (same && g.exec) {
     LL_CUDA(ctx, cudaGraphLaunch(g.exec, s));
@@ -611,7 +640,7 @@ int scan_front_end(ll_ctx* ctx, const void* raw, size_t n, int fmt, int where, d
     LL_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
     const int st = front_end_enqueue(ctx, pc, A, ncap);
     const cudaError_t ce = cudaStreamEndCapture(s, &graph);
-    void* after[5] = {ctx->extract_buf.p, ctx->reg_buf.p, ctx->scratch.p, ctx->scratch2.p, (void*)(size_t)ctx->scratch.cap};
+    void* after[6] = {ctx->extract_buf.p, ctx->reg_buf.p, ctx->scratch.p, ctx->scratch2.p, (void*)(size_t)ctx->scratch.cap, ctx->scratch3.p};
     if (st != LL_OK || ce != cudaSuccess || memcmp(after, bufs, sizeof(bufs)) != 0) {   // should not happen: fall back to eager launches
       if (graph) cudaGraphDestroy(graph);
       cudaGetLastError(); g.warm = false; g.n = 0;
@@ -625,7 +654,7 @@ int scan_front_end(ll_ctx* ctx, const void* raw, size_t n, int fmt, int where, d
   } else {
     if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     LL_TRY(front_end_enqueue(ctx, pc, A, ncap));
-    void* after[5] = {ctx->extract_buf.p, ctx->reg_buf.p, ctx->scratch.p, ctx->scratch2.p, (void*)(size_t)ctx->scratch.cap};
+    void* after[6] = {ctx->extract_buf.p, ctx->reg_buf.p, ctx->scratch.p, ctx->scratch2.p, (void*)(size_t)ctx->scratch.cap, ctx->scratch3.p};
     g.n = n; g.pc = *pc; memcpy(g.bufs, after, sizeof(after)); g.warm = true;
   }
   LL_CUDA(ctx, cudaStreamSynchronize(s));
@@ -651,6 +680,45 @@ extern "C" int ll_scan_to_pose(ll_ctx* ctx, const ll_map* map, const void* raw, 
   if (n_corner_used) *n_corner_used = nc; if (n_surf_used) *n_surf_used = ns;
   if (dropped) { memset(out, 0, sizeof(*out)); out->status = 1; ctx->set_error("frame dropped: <= 5 petals"); return LL_OK; }
   return register_device(ctx, map, A, nc, ns, in, out);
+}
+
+// Multi-head frame (Mid-100: three Mid-40 heads, launch/rosbag_mid100.launch): Laser_feature::laserCloudHandler runs ONE Livox_laser object over
+// the heads in turn and sums their per-piece feature clouds before the VoxelGrids (laser_feature_extractor.hpp:303-380); the mapping node then sees
+// one merged feature pair (laser_mapping.hpp:1367-1405).  Heads whose frame has <= 5 petals contribute nothing (:287).
+extern "C" int ll_frame_to_pose(ll_ctx* ctx, const ll_map* map, int n_heads, const void* const* raws, const size_t* ns, int fmt, int where, const double* stamps,
+                     const ll_pipeline_cfg* pc, const ll_reg_state* in, ll_reg_result* out, int* n_corner_used, int* n_surf_used) {
+  if (!ctx || !map || !pc || !in || !out || !raws || !ns || !stamps || n_heads < 1 || n_heads > 8) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  size_t total = 0; for (int h = 0; h < n_heads; h++) total += ns[h];
+  if ((int)total > ctx->cfg.max_scan_points) { ctx->set_error("frame (all heads) larger than max_scan_points"); return LL_ERR_CAPACITY; }
+  RegArrays A; LL_TRY(reg_arrays(ctx, 0, &A));
+  int acc_c = 0, acc_s = 0;
+  int* hc = (int*)ctx->pinned + 8192;
+  for (int h = 0; h < n_heads; h++) {
+    LL_TRY(extract_prepare(ctx, raws[h], ns[h], fmt, where, stamps[h]));
+    LL_TRY(extract_enqueue(ctx));
+    const float* d_bounds = nullptr;
+    if (!pc->whole_frame) { LL_TRY(launch_piece_bounds(ctx, pc->pieces, A.bounds)); d_bounds = A.bounds + 2 * pc->use_piece; }
+    LL_TRY(launch_get_features(ctx, d_bounds, 0.f, 1.f, A.tmp_a + acc_c, A.tmp_b + acc_s, nullptr, A.counts));
+    LL_CUDA(ctx, cudaMemcpyAsync(hc, A.counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    LL_CUDA(ctx, cudaMemcpyAsync(hc + 4, ctx->ex.d_meta, 12, cudaMemcpyDeviceToHost, s));
+    LL_CUDA(ctx, cudaStreamSynchronize(s));
+    if (ns[h] >= 5 && (hc[5] > 5 || pc->whole_frame)) { acc_c += hc[0]; acc_s += hc[1]; }   // hc[5] = meta[1] = laserCloudScans.size()
+  }
+  int* cnt = A.counts;   // [4..7] VoxelGrid outputs
+  LL_TRY(launch_voxel_grid(ctx, A.tmp_a, acc_c, nullptr, pc->extractor_leaf_corner, A.tmp_d, cnt + 4));
+  LL_TRY(launch_voxel_grid(ctx, A.tmp_d, acc_c > 0 ? acc_c : 0, cnt + 4, pc->mapping_leaf_corner, A.tmp_a, cnt + 5));
+  LL_TRY(launch_voxel_grid(ctx, A.tmp_b, acc_s, nullptr, pc->extractor_leaf_surf, A.tmp_c, cnt + 6));
+  LL_TRY(launch_voxel_grid(ctx, A.tmp_c, acc_s > 0 ? acc_s : 0, cnt + 6, pc->mapping_leaf_surf, A.tmp_b, cnt + 7));
+  LL_CUDA(ctx, cudaMemcpyAsync(hc, cnt, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  LL_CUDA(ctx, cudaStreamSynchronize(s));
+  const int nc = hc[5], nsf = hc[7];
+  if (n_corner_used) *n_corner_used = nc; if (n_surf_used) *n_surf_used = nsf;
+  if (nc + nsf > ctx->cfg.max_features) { ctx->set_error("more features than max_features"); return LL_ERR_CAPACITY; }
+  LL_CUDA(ctx, cudaMemcpyAsync(A.feat, A.tmp_a, (size_t)nc * 16, cudaMemcpyDeviceToDevice, s));
+  LL_CUDA(ctx, cudaMemcpyAsync(A.feat + nc, A.tmp_b, (size_t)nsf * 16, cudaMemcpyDeviceToDevice, s));
+  return register_device(ctx, map, A, nc, nsf, in, out);
 }
 
 extern "C" {

@@ -38,6 +38,27 @@ __global__ void repack_strided_kernel(const unsigned char* __restrict__ src, int
   dst[i] = make_float4(load_f32_le(r + L.offset_x), load_f32_le(r + L.offset_y), load_f32_le(r + L.offset_z), it);
 }
 
+// The other direction (pcl::toROSMsg, laser_feature_extractor.hpp:367-384): 16-byte points -> records of a sensor_msgs/PointCloud2 payload.
+// Bytes of a record that belong to no field are zeroed.
+__device__ __forceinline__ void store_f32_le(unsigned char* p, float f) { const unsigned v = __float_as_uint(f); p[0] = v & 255; p[1] = (v >> 8) & 255; p[2] = (v >> 16) & 255; p[3] = v >> 24; }
+__global__ void pack_strided_kernel(const float4* __restrict__ src, int n, ll_point_layout L, unsigned char* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned char* r = dst + (size_t)i * L.point_step;
+  for (int b = 0; b < L.point_step; b++) r[b] = 0;
+  const float4 p = src[i];
+  store_f32_le(r + L.offset_x, p.x); store_f32_le(r + L.offset_y, p.y); store_f32_le(r + L.offset_z, p.z);
+  if (L.intensity_datatype == LL_I_FLOAT32) store_f32_le(r + L.offset_intensity, p.w);
+  else if (L.intensity_datatype == LL_I_UINT8) r[L.offset_intensity] = (unsigned char)fminf(fmaxf(p.w, 0.f), 255.f);
+  else if (L.intensity_datatype == LL_I_UINT16) { const unsigned v = (unsigned)fminf(fmaxf(p.w, 0.f), 65535.f); r[L.offset_intensity] = v & 255; r[L.offset_intensity + 1] = v >> 8; }
+}
+int launch_pack_strided(ll_ctx* ctx, const float4* d_src, int n, unsigned char* d_dst) {
+  if (n == 0) return LL_OK;
+  pack_strided_kernel<<<ll_div_up(n, 256), 256, 0, ctx->stream>>>(d_src, n, ctx->layout, d_dst); ctx->launches++;
+  LL_CUDA(ctx, cudaGetLastError());
+  return LL_OK;
+}
+
 int upload_cloud(ll_ctx* ctx, const void* src, size_t n, int fmt, int where, float4* d_dst) {
   if (n == 0) return LL_OK;
   cudaStream_t s = ctx->stream;
@@ -91,16 +112,18 @@ struct VgMeta {
   int n_in;
   int min_b[3]; int mul[3];
   float inv;
+  int ticket;           // blocks of vg_minmax_setup_kernel that have finished (the last one does the set-up and resets it)
 };
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
-__global__ void vg_init_kernel(VgMeta* m, int n_host, const int* d_n) {
-  for (int k = 0; k < 3; k++) { m->mn[k] = f2ord(INFINITY); m->mx[k] = f2ord(-INFINITY); }
-  m->n_finite = 0; m->passthrough = 0; m->n_in = d_n ? min(*d_n, n_host) : n_host;
-}
-__global__ void vg_minmax_kernel(const float4* __restrict__ in, VgMeta* m) {
-  const int n = m->n_in;
+// Min / max over the finite points, then -- by the last block to finish -- the grid set-up of VoxelGrid::applyFilter (one launch instead of
+// init + minmax + setup; `m` is cleared by a memset node: mins are kept as the bitwise complement of their order-preserving key, so that
+// "all zero" is the neutral element of the atomicMax that reduces both the mins and the maxs).
+__device__ __forceinline__ unsigned f2key(float f) { return (unsigned)f2ord(f) ^ 0x80000000u; }     // unsigned order == float order
+__device__ __forceinline__ float key2f(unsigned k) { return ord2f((int)(k ^ 0x80000000u)); }
+__global__ void vg_minmax_setup_kernel(const float4* __restrict__ in, VgMeta* m, int n_host, const int* __restrict__ d_n, float leaf) {
+  const int n = d_n ? min(*d_n, n_host) : n_host;
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}; int cnt = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = in[i];
@@ -117,14 +140,22 @@ __global__ void vg_minmax_kernel(const float4* __restrict__ in, VgMeta* m) {
   }
   if ((threadIdx.x & 31) == 0 && cnt > 0) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) { atomicMin(&m->mn[k], f2ord(lo[k])); atomicMax(&m->mx[k], f2ord(hi[k])); }
+    for (int k = 0; k < 3; k++) { atomicMax((unsigned*)&m->mn[k], ~f2key(lo[k])); atomicMax((unsigned*)&m->mx[k], f2key(hi[k])); }
     atomicAdd(&m->n_finite, cnt);
   }
-}
-__global__ void vg_setup_kernel(VgMeta* m, float leaf) {
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = (atomicAdd(&m->ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  // ---- set-up (the last block sees every block's contribution)
+  volatile VgMeta* v = m;
+  m->n_in = n; m->passthrough = 0; m->ticket = 0;
   const float inv = 1.0f / leaf; m->inv = inv;
-  if (m->n_finite == 0) { for (int k = 0; k < 3; k++) { m->min_b[k] = 0; m->mul[k] = 0; } return; }
-  float mn[3], mx[3]; for (int k = 0; k < 3; k++) { mn[k] = ord2f(m->mn[k]); mx[k] = ord2f(m->mx[k]); }
+  if (v->n_finite == 0) { for (int k = 0; k < 3; k++) { m->min_b[k] = 0; m->mul[k] = 0; } return; }
+  float mn[3], mx[3]; for (int k = 0; k < 3; k++) { mn[k] = key2f(~(unsigned)v->mn[k]); mx[k] = key2f((unsigned)v->mx[k]); }
   long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1, dz = (long long)((mx[2] - mn[2]) * inv) + 1;
   if (dx * dy * dz > 2147483647LL) { m->passthrough = 1; return; }
   int div_b[3];
@@ -147,12 +178,11 @@ __global__ void vg_keys_kernel(const float4* __restrict__ in, const VgMeta* __re
   }
   keys[i] = key; vals[i] = i;
 }
-__global__ void vg_heads_kernel(const unsigned* __restrict__ keys, int n_cap, unsigned char* __restrict__ flags) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_cap) return;
-  unsigned k = keys[i];
-  flags[i] = (k != 0xffffffffu && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
-}
+// First element of every run of equal (valid) keys in the sorted key array: the predicate of the stream compaction that lists the voxels.
+struct VgHead {
+  const unsigned* keys;
+  __device__ __forceinline__ bool operator()(int i) const { const unsigned k = keys[i]; return k != 0xffffffffu && (i == 0 || keys[i - 1] != k); }
+};
 // One thread per voxel: sequential float sum in ascending input index (radix sort is stable), like CentroidPoint<PointXYZI>.
 __global__ void vg_centroid_kernel(const float4* __restrict__ in, const VgMeta* __restrict__ m, const int* __restrict__ vals, const int* __restrict__ seg_start,
                                    const int* __restrict__ d_num_seg, int n_cap, float4* __restrict__ out, int* __restrict__ d_n_out) {
@@ -181,25 +211,23 @@ int launch_voxel_grid_on(ll_ctx* ctx, cudaStream_t s, DevBuf& scratch, const flo
   if (n_cap <= 0) { LL_CUDA(ctx, cudaMemsetAsync(d_n_out, 0, sizeof(int), s)); return LL_OK; }
   size_t sort_bytes = 0, sel_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, n_cap, 0, 32, s);
-  cub::DeviceSelect::Flagged(nullptr, sel_bytes, cub::CountingInputIterator<int>(0), (unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, n_cap, s);
+  cub::DeviceSelect::If(nullptr, sel_bytes, cub::CountingInputIterator<int>(0), (int*)nullptr, (int*)nullptr, n_cap, VgHead{nullptr}, s);
   size_t tmp_bytes = sort_bytes > sel_bytes ? sort_bytes : sel_bytes;
   size_t o_meta = 0, o_k0 = align256(sizeof(VgMeta) + 16), o_k1 = o_k0 + align256((size_t)n_cap * 4), o_v0 = o_k1 + align256((size_t)n_cap * 4), o_v1 = o_v0 + align256((size_t)n_cap * 4),
-         o_fl = o_v1 + align256((size_t)n_cap * 4), o_seg = o_fl + align256((size_t)n_cap), o_tmp = o_seg + align256((size_t)n_cap * 4);
+         o_seg = o_v1 + align256((size_t)n_cap * 4), o_tmp = o_seg + align256((size_t)n_cap * 4);
   LL_CUDA(ctx, scratch.reserve(o_tmp + tmp_bytes + 256));
   char* base = scratch.as<char>();
   VgMeta* meta = (VgMeta*)(base + o_meta); int* d_num_seg = (int*)(base + o_meta + sizeof(VgMeta));
   unsigned* k0 = (unsigned*)(base + o_k0); unsigned* k1 = (unsigned*)(base + o_k1); int* v0 = (int*)(base + o_v0); int* v1 = (int*)(base + o_v1);
-  unsigned char* flags = (unsigned char*)(base + o_fl); int* seg = (int*)(base + o_seg);
+  int* seg = (int*)(base + o_seg);
   const int blocks = ll_div_up(n_cap, 256);
-  vg_init_kernel<<<1, 1, 0, s>>>(meta, n_cap, d_n_in);
-  vg_minmax_kernel<<<min(blocks, ctx->num_sms * 8), 256, 0, s>>>(d_in, meta);
-  vg_setup_kernel<<<1, 1, 0, s>>>(meta, leaf);
+  LL_CUDA(ctx, cudaMemsetAsync(meta, 0, sizeof(VgMeta), s));
+  vg_minmax_setup_kernel<<<min(blocks, ctx->num_sms * 2), 256, 0, s>>>(d_in, meta, n_cap, d_n_in, leaf);
   vg_keys_kernel<<<blocks, 256, 0, s>>>(d_in, meta, n_cap, k0, v0);
   LL_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + o_tmp, sort_bytes, k0, k1, v0, v1, n_cap, 0, 32, s));
-  vg_heads_kernel<<<blocks, 256, 0, s>>>(k1, n_cap, flags);
-  LL_CUDA(ctx, cub::DeviceSelect::Flagged(base + o_tmp, sel_bytes, cub::CountingInputIterator<int>(0), flags, seg, d_num_seg, n_cap, s));
+  LL_CUDA(ctx, cub::DeviceSelect::If(base + o_tmp, sel_bytes, cub::CountingInputIterator<int>(0), seg, d_num_seg, n_cap, VgHead{k1}, s));
   vg_centroid_kernel<<<blocks, 256, 0, s>>>(d_in, meta, v1, seg, d_num_seg, n_cap, d_out, d_n_out);
-  ctx->launches += 12;
+  ctx->launches += 11;   // minmax+setup, keys, radix sort (histogram, scan, 4 onesweep passes), select (init, sweep), centroid
   LL_CUDA(ctx, cudaGetLastError());
   return LL_OK;
 }

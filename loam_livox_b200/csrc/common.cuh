@@ -121,11 +121,12 @@ struct ll_ctx {
   struct SolveSync* d_sync = nullptr;   // device: exchange rows of the solver kernels (solve.cu)
   // multi-GPU
   int rank = 0, world = 1;
+  cudaStream_t stream3 = nullptr; cudaEvent_t ev_fork3 = nullptr, ev_join3 = nullptr; DevBuf scratch3;   // second side stream: the petal bookkeeping of the extractor (whole_frame front end)
   cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_it[2] = {nullptr, nullptr}; DevBuf scratch2, scratch_fe;   // side stream of the per-scan front end; the front end's own scratch arenas (fixed once the scan size is
                                  // known: the captured graph must never see them reallocated by the map refresh or the registration)
   // The per-scan front end (extract + get_features + 4 VoxelGrids + count read-back) replayed as ONE CUDA graph: ~60 launches whose
   // enqueue cost on the host (CUB dispatch included) was longer than their execution.  Re-captured when the shape or any buffer changes.
-  struct FrontGraph { cudaGraphExec_t exec = nullptr; size_t n = 0; ll_pipeline_cfg pc; void* bufs[5] = {nullptr}; bool warm = false; uint64_t launches = 0; } fg;
+  struct FrontGraph { cudaGraphExec_t exec = nullptr; size_t n = 0; ll_pipeline_cfg pc; void* bufs[6] = {nullptr}; bool warm = false; uint64_t launches = 0; } fg;
   int reg_deblur = 0;                      // if_motion_deblur of the registration whose blocks are on the device
   int solve_world = 1;                     // world size the solver kernels all-reduce over (1 unless the map in use is sharded)
   void* comm_local = nullptr;              // this rank's staging slot (device memory, IPC-exported)

@@ -259,24 +259,42 @@ int extract_reserve(ll_ctx* ctx, int n) {
   return LL_OK;
 }
 
-int launch_extract(ll_ctx* ctx, int n) {
-  ExtractState& e = ctx->ex; cudaStream_t s = ctx->stream;
+static ExtractParams extract_params(ll_ctx* ctx, int n) {
+  ExtractState& e = ctx->ex;
   ExtractParams P; P.n = n; P.dt = ctx->cfg.time_interval_pts; P.d_current_time = e.d_time;
   P.min_dis_sq = ctx->cfg.livox_min_dis * ctx->cfg.livox_min_dis; P.min_sigma = ctx->cfg.livox_min_sigma;
   P.max_edge_polar = (float)std::pow(std::tan(ctx->cfg.max_fov_deg / 57.3) * 1, 2);
   P.thr_corner = ctx->cfg.corner_curvature; P.thr_surface = ctx->cfg.surface_curvature; P.min_view_angle = ctx->cfg.minimum_view_angle;
+  return P;
+}
+// K1 + K2: the per-point part of projection_scan_3d_2d and compute_features (everything get_features needs)
+int launch_extract_points(ll_ctx* ctx, int n) {
+  ExtractState& e = ctx->ex; cudaStream_t s = ctx->stream;
+  const ExtractParams P = extract_params(ctx, n);
   const int blocks = ll_div_up(n, 256);
-  size_t sel_bytes = 0;
-  cub::DeviceSelect::Flagged(nullptr, sel_bytes, cub::CountingInputIterator<int>(0), (unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, n, s);
-  LL_CUDA(ctx, ctx->scratch.reserve(sel_bytes + (size_t)(n + 1) * 4 + 512));
-  float* seg_angle = (float*)((char*)ctx->scratch.p + align256(sel_bytes));
   ex_point_kernel<<<blocks, 256, 0, s>>>(e.raw, P, e.time_stamp, e.polar_dis_sq2, e.depth_sq2, e.self_mask);
   ex_feature_kernel<<<blocks, 256, 0, s>>>(e.raw, P, e.polar_dis_sq2, e.depth_sq2, e.self_mask, e.pt_type, e.pt_label, e.curvature, e.view_angle, (signed char*)e.polar_dir, e.cand);
-  LL_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->scratch.p, sel_bytes, cub::CountingInputIterator<int>(0), e.cand, e.cand_idx, e.d_num_cand, n, s));
-  ex_petal_kernel<<<1, 32, 0, s>>>(e.raw, n, e.polar_dis_sq2, e.pt_type, e.cand, e.cand_idx, e.d_num_cand, e.split_idx, seg_angle, e.scan_first, e.scan_last, e.d_meta);
-  ctx->launches += 5;
+  ctx->launches += 2;
   LL_CUDA(ctx, cudaGetLastError());
   return LL_OK;
+}
+// The petal bookkeeping (split indices with the 50-point hysteresis, petal angles, first / last surviving point per petal: :529-604, split_laser_scan).
+// Only the piece bounds and the "<= 5 petals" test read its results, so with whole_frame = 1 the front end runs it on a side stream.
+int launch_extract_petals(ll_ctx* ctx, int n, cudaStream_t s, DevBuf& scratch) {
+  ExtractState& e = ctx->ex;
+  size_t sel_bytes = 0;
+  cub::DeviceSelect::Flagged(nullptr, sel_bytes, cub::CountingInputIterator<int>(0), (unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, n, s);
+  LL_CUDA(ctx, scratch.reserve(sel_bytes + (size_t)(n + 1) * 4 + 512));
+  float* seg_angle = (float*)((char*)scratch.p + align256(sel_bytes));
+  LL_CUDA(ctx, cub::DeviceSelect::Flagged(scratch.p, sel_bytes, cub::CountingInputIterator<int>(0), e.cand, e.cand_idx, e.d_num_cand, n, s));
+  ex_petal_kernel<<<1, 32, 0, s>>>(e.raw, n, e.polar_dis_sq2, e.pt_type, e.cand, e.cand_idx, e.d_num_cand, e.split_idx, seg_angle, e.scan_first, e.scan_last, e.d_meta);
+  ctx->launches += 3;
+  LL_CUDA(ctx, cudaGetLastError());
+  return LL_OK;
+}
+int launch_extract(ll_ctx* ctx, int n) {
+  LL_TRY(launch_extract_points(ctx, n));
+  return launch_extract_petals(ctx, n, ctx->stream, ctx->scratch);
 }
 
 int launch_piece_bounds(ll_ctx* ctx, int pieces, float* d_start_end) {

@@ -123,6 +123,7 @@ int solve_max_slots(ll_ctx* ctx);
 // ---------------------------------------------------------------------------------------------- clouds (cloud.cu)
 int upload_cloud(ll_ctx* ctx, const void* src, size_t n, int fmt, int where, float4* d_dst);   // async on ctx->stream
 int launch_transform(ll_ctx* ctx, const double* d_pose7, const float4* d_in, int n, float4* d_out);
+int launch_pack_strided(ll_ctx* ctx, const float4* d_src, int n, unsigned char* d_dst);   // 16-byte points -> PointCloud2 records (ctx->layout)
 // VoxelGrid on device: d_in [n] -> d_out [<= n], *d_n_out on device. n given by host, or by device count d_n_in (may be null).
 struct VoxelTemps { DevBuf* buf; };
 int launch_inlier_select(ll_ctx* ctx, const double* d_l1, int M, double ratio, double* d_sorted, double* d_unique, int* d_n_unique);
@@ -132,6 +133,8 @@ int launch_voxel_grid_on(ll_ctx* ctx, cudaStream_t s, DevBuf& scratch, const flo
 // ---------------------------------------------------------------------------------------------- extractor (extract.cu)
 int extract_reserve(ll_ctx* ctx, int n);
 int launch_extract(ll_ctx* ctx, int n);   // current_time is read from ctx->ex.d_time
+int launch_extract_points(ll_ctx* ctx, int n);
+int launch_extract_petals(ll_ctx* ctx, int n, cudaStream_t s, DevBuf& scratch);
 int launch_get_features(ll_ctx* ctx, const float* d_bounds /*min_blur,max_blur on device*/, float min_blur, float max_blur,
                         float4* d_corners, float4* d_surf, float4* d_full, int* d_counts /*3*/);
 int launch_piece_bounds(ll_ctx* ctx, int pieces, float* d_start_end /* 2*pieces */);

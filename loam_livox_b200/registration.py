@@ -51,6 +51,7 @@ class Context:
         """Record layout of LL_FMT_STRIDED inputs (a sensor_msgs/PointCloud2 payload: what pcl::fromROSMsg resolves by field name)."""
         L = capi.PointLayout(point_step, offset_x, offset_y, offset_z, offset_intensity, intensity_datatype)
         self.check(self._lib.ll_set_point_layout(self.h, C.byref(L)))
+        self._layout_step = point_step
 
     def launches(self) -> int:
         return int(self._lib.ll_launch_count(self.h))
@@ -261,6 +262,36 @@ def scan_to_pose(ctx: Context, match_map: Map, raw, stamp, pipeline: capi.Pipeli
     nc, ns = C.c_int(), C.c_int()
     ctx.check(ctx._lib.ll_scan_to_pose(ctx.h, match_map.h, ptr, n, fmt, where, float(stamp), C.byref(pipeline), C.byref(state), C.byref(res), C.byref(nc), C.byref(ns)))
     return res, nc.value, ns.value
+
+
+def frame_to_pose(ctx: Context, match_map: Map, heads, stamps, pipeline: capi.PipelineCfg, state: capi.RegState, where=capi.LL_HOST, ns=None, fmt=None):
+    """Multi-head frame (Mid-100: three Mid-40 heads): one extractor over the heads in turn, feature clouds summed, VoxelGrids, registration
+    (ll_frame_to_pose; laser_feature_extractor.hpp:303-380).  heads: list of [n,4] arrays (LL_HOST) or of device pointers (LL_DEVICE, with ns)."""
+    k = len(heads)
+    if where == capi.LL_HOST:
+        arrs = [_pts(h) for h in heads]
+        fmt = arrs[0][1]
+        ptrs = (C.c_void_p * k)(*[a.ctypes.data for a, _ in arrs])
+        sizes = (C.c_size_t * k)(*[a.shape[0] for a, _ in arrs])
+    else:
+        ptrs = (C.c_void_p * k)(*[int(h) for h in heads])
+        sizes = (C.c_size_t * k)(*[int(n) for n in ns])
+    st = (C.c_double * k)(*[float(t) for t in stamps])
+    res = capi.RegResult()
+    nc, nsf = C.c_int(), C.c_int()
+    ctx.check(ctx._lib.ll_frame_to_pose(ctx.h, match_map.h, k, ptrs, sizes, fmt, where, st, C.byref(pipeline), C.byref(state), C.byref(res), C.byref(nc), C.byref(nsf)))
+    return res, nc.value, nsf.value
+
+
+def features_to_pointcloud2(ctx: Context, which: int) -> bytes:
+    """pcl::toROSMsg of the last registration's corner (0) / surface (1) features, in the layout of Context.set_point_layout (ll_features_to_pointcloud2)."""
+    n = C.c_size_t()
+    ctx.check(ctx._lib.ll_features_to_pointcloud2(ctx.h, which, None, 0, C.byref(n)))
+    step = ctx._layout_step if hasattr(ctx, "_layout_step") else 16
+    buf = np.zeros(n.value * step, np.uint8)
+    if n.value:
+        ctx.check(ctx._lib.ll_features_to_pointcloud2(ctx.h, which, buf.ctypes.data, buf.shape[0], C.byref(n)))
+    return buf.tobytes()
 
 
 class Scene_alignment:

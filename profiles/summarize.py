@@ -1,5 +1,7 @@
 """Turns the ncu captures brought back in gpurun_out/ into the text summaries committed here.
-usage: python profiles/summarize.py <report.ncu-rep> <out.txt> [title]"""
+usage: python profiles/summarize.py <report.ncu-rep> <out.txt> [title] [kernel source file under loam_livox_b200/csrc/]
+With the 4th argument the machine-readable companion (<out>.json: DRAM bytes per launch = bench.py's roofline.traffic) is stamped with the sha1 of that
+source file; bench.py quotes the traffic only while the stamp matches the source it runs, so a stale capture is never reported."""
 import csv
 import subprocess
 import sys
@@ -45,8 +47,17 @@ def main():
         def dur(name):
             v, u = float(r[hdr.index(name)].replace(",", "")), units[hdr.index(name)]
             return v * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(u, 1.0)
-        json.dump({"kernel": r[hdr.index("Kernel Name")][:100], "traffic_bytes_per_launch": val2("dram__bytes_read.sum") + val2("dram__bytes_write.sum"),
-                   "duration_us_under_ncu": dur("gpu__time_duration.sum"), "source": rep.split("/")[-1]}, open(out.rsplit(".", 1)[0] + ".json", "w"))
+        sha = None
+        if len(sys.argv) > 4:
+            import hashlib, os
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "loam_livox_b200", "csrc", sys.argv[4]), "rb") as f:
+                sha = hashlib.sha1(f.read()).hexdigest()
+        # traffic = mean over the captured launches (bench.py's roofline is the mean over all launches of the timed region, seeded iterations included)
+        tr = [float(b[hdr.index("dram__bytes_read.sum")].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[hdr.index("dram__bytes_read.sum")], 1) +
+              float(b[hdr.index("dram__bytes_write.sum")].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[hdr.index("dram__bytes_write.sum")], 1) for b in body]
+        json.dump({"kernel": r[hdr.index("Kernel Name")][:100], "traffic_bytes_per_launch": sum(tr) / len(tr), "traffic_bytes_longest_launch": val2("dram__bytes_read.sum") + val2("dram__bytes_write.sum"),
+                   "launches_captured": len(tr), "duration_us_under_ncu": dur("gpu__time_duration.sum"), "source": rep.split("/")[-1], "source_sha1": sha},
+                  open(out.rsplit(".", 1)[0] + ".json", "w"))
     print("\n".join(lines[:40]))
 
 

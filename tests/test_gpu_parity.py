@@ -706,3 +706,44 @@ def test_triple_lidar_frame_parity(ctx, oracle):
             assert st == ost and reg.result.icp_iterations == ores.icp_iterations
             assert np.linalg.norm(np.array(reg.result.t_w_curr) - np.array(ores.t_w_curr)) < 1e-6
             assert S.quat_angle(np.array(reg.result.q_w_curr), np.array(ores.q_w_curr)) < 1e-6
+
+
+@pytest.mark.gpu
+def test_frame_to_pose_equals_the_staged_triple_lidar_flow(ctx, oracle):
+    """ll_frame_to_pose (three heads, one call, features never leave the device) against the oracle's staged flow: per-head extraction with ONE extractor
+    object, summed feature clouds, the four VoxelGrids at the precision-YAML leaves, registration."""
+    from loam_livox_b200 import capi
+    from loam_livox_b200.registration import Context, Map, frame_to_pose, features_to_pointcloud2
+    c3 = Context(0, max_scan_points=300000, max_features=300000)
+    pose = S.default_pose()
+    heads = S.make_triple_scan(300000, pose)
+    stamps = [100.0 + 1e-3 * k for k in range(3)]
+    mc, ms = S.make_map(20000, 180000)
+    m = Map(c3, mc, ms)
+    guess = S.perturb_pose(pose, np.random.default_rng(3), dt=0.05, dang_deg=1.0)
+    pc = capi.PipelineCfg(pieces=2, use_piece=0, extractor_leaf_corner=0.1, extractor_leaf_surf=0.2, mapping_leaf_corner=0.1, mapping_leaf_surf=0.4, whole_frame=0)
+    st = capi.default_reg_state(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t)
+    res, nc, ns = frame_to_pose(c3, m, heads, stamps, pc, st)
+    ol = oracle.Extractor()
+    oc, os_ = [], []
+    for raw, stamp in zip(heads, stamps):
+        assert ol.extract(raw, stamp) > 5
+        a, b = ol.piece_bounds(2)
+        c, s, _ = ol.get_features(float(a[0]), float(b[0]))
+        oc.append(c); os_.append(s)
+    fc = oracle.voxel_grid(oracle.voxel_grid(np.concatenate(oc), 0.1), 0.1)
+    fs = oracle.voxel_grid(oracle.voxel_grid(np.concatenate(os_), 0.2), 0.4)
+    assert (nc, ns) == (fc.shape[0], fs.shape[0])
+    p = oracle.default_params(q_w_last=guess.q, t_w_last=guess.t, q_w_curr=guess.q, t_w_curr=guess.t)
+    ost, ores = oracle.register(mc, oracle.KdTree(mc), ms, oracle.KdTree(ms), fc, fs, p)
+    assert res.status == ost and res.icp_iterations == ores.icp_iterations
+    assert np.linalg.norm(np.array(res.t_w_curr) - np.array(ores.t_w_curr)) < 1e-6 and S.quat_angle(np.array(res.q_w_curr), np.array(ores.q_w_curr)) < 1e-6
+    # the output side of N3: the features as a PointCloud2 payload (x, y, z float32 at 0/4/8, intensity float32 at 16, point_step 32 -- PCL's layout)
+    c3.set_point_layout(32, 0, 4, 8, 16, capi.LL_I_FLOAT32)
+    for which, ref in ((0, fc), (1, fs)):
+        rec = np.frombuffer(features_to_pointcloud2(c3, which), np.uint8).reshape(-1, 32)
+        assert rec.shape[0] == ref.shape[0]
+        xyz = rec[:, :12].copy().view(np.float32).reshape(-1, 3)
+        it = rec[:, 16:20].copy().view(np.float32).reshape(-1)
+        assert np.array_equal(xyz, ref[:, :3]) and np.array_equal(it, ref[:, 3]) and not rec[:, 12:16].any() and not rec[:, 20:].any()
+    m.release(); c3.close()
