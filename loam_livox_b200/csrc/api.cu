@@ -65,6 +65,7 @@ int ll_ctx_create(const ll_config* cfg, int device, ll_ctx** out) {
   ll_ctx* ctx = new ll_ctx();
   ctx->device = device;
   if (cfg) ctx->cfg = *cfg; else ll_config_default(&ctx->cfg);
+  { const char* e = getenv("LL_KNN_TMA"); ctx->knn_tma = (e && e[0] == '1') ? 1 : 0; }
   // every call is checked: the first failure wins and the half-built context is torn down by ll_ctx_destroy (which tolerates null members)
   cudaError_t e = cudaSetDevice(device);
   auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; };

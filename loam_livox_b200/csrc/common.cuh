@@ -108,6 +108,7 @@ struct ll_ctx {
   int last_nc = 0, last_ns = 0;   // features of the last registration (ll_last_features_dev)
   float last_full_min_t = 10000.f, last_full_max_t = -10000.f;   // find_min_max_intensity over the last front end's full cloud (laser_mapping.hpp:1336)
   int num_sms = 0;
+  int knn_tma = 0;         // LL_KNN_TMA=1 in the environment at ll_ctx_create: the variant of knn_blocks_kernel that stages leaf buckets with cp.async.bulk (measurement only)
   // arenas
   DevBuf scratch;      // CUB temp storage
   DevBuf stage_in;     // raw uploads (PCL32 or XYZI16)
