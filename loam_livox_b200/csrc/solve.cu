@@ -70,7 +70,7 @@ __device__ __forceinline__ bool d_chol6(const double A[6][6], const double b[6],
       double s = A[i][j];
 #pragma unroll
       for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
-      if (i == j) { if (!(s > 0.0)) ok = false; L[i][i] = sqrt(s); inv[i] = 1.0 / L[i][i]; } else L[i][j] = s * inv[j];
+      if (i == j) { if (!(s > 0.0)) ok = false; inv[i] = rsqrt(s); L[i][i] = s * inv[i]; } else L[i][j] = s * inv[j];   // one rsqrt instead of sqrt + reciprocal: the 6 pivots are the dependent chain of the solve
     }
   }
   if (!ok) return false;
@@ -178,7 +178,9 @@ __device__ __noinline__ void compute_step(const StepIn& I, double bound, StepOut
   double A[6][6], rhs[6], Hs[6][6];
   for (int i = 0; i < 6; i++) { rhs[i] = I.g[i] * I.scaling[i]; for (int j = i; j < 6; j++) { double v = I.H[hidx(i, j)] * I.scaling[i] * I.scaling[j]; Hs[i][j] = v; Hs[j][i] = v; } }
   for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) A[i][j] = Hs[i][j];
-  for (int c = 0; c < 6; c++) { double d = sqrt(O.diagonal[c] / I.radius); A[c][c] += d * d; }
+  // Ceres forms lm_diagonal = sqrt(diagonal / radius) and the linear solver adds its square; diagonal / radius is the same number to an ulp and
+  // saves 6 square roots and 5 divisions on the serial path of every LM iteration
+  { const double inv_radius = 1.0 / I.radius; for (int c = 0; c < 6; c++) A[c][c] += O.diagonal[c] * inv_radius; }
   double step[6]; const bool solved = d_chol6(A, rhs, step);
   O.valid = 0; O.model_cost_change = 0; O.gd = 0; O.dmax = 0;
   if (solved) {
@@ -238,7 +240,7 @@ __device__ void lm_next_iteration(LmState& L, double bound, const StepOut* pre) 
   }
 }
 // Candidate point L.trial evaluated: cost + sums (normal equations at the candidate).
-__device__ void lm_accept_test(LmState& L, const double* sums, double bound) {
+__device__ void lm_accept_test(LmState& L, const double* sums, double bound, bool defer_gmax) {
   const double cand_cost = sums[27];
   double step_norm = 0; for (int k = 0; k < 7; k++) step_norm += (L.x[k] - L.trial[k]) * (L.x[k] - L.trial[k]); step_norm = sqrt(step_norm);
   if (step_norm <= LM_PTOL * (L.x_norm + LM_PTOL)) { lm_finish(L, 2); return; }
@@ -249,7 +251,8 @@ __device__ void lm_accept_test(LmState& L, const double* sums, double bound) {
     for (int k = 0; k < 7; k++) L.x[k] = L.trial[k];
     double n = 0; for (int k = 0; k < 7; k++) n += L.x[k] * L.x[k]; L.x_norm = sqrt(n);
     L.x_cost = cand_cost; for (int i = 0; i < 21; i++) L.H[i] = sums[i]; for (int i = 0; i < 6; i++) L.g[i] = sums[21 + i];
-    L.last_gmax = lm_gmax(L, bound); L.last_successful = 1;
+    if (!defer_gmax) L.last_gmax = lm_gmax(L, bound);
+    L.last_successful = 1;
     L.radius = radius_after_success(L.radius, rel);
     L.decrease_factor = 2.0; L.reuse_diagonal = 0;
     L.min_iter_cost = fmin(L.min_iter_cost, L.x_cost);
@@ -264,7 +267,8 @@ __device__ void lm_accept_test(LmState& L, const double* sums, double bound) {
 // One evaluation finished; sums = normal equations at L.trial.  Digests it up to the point where the next LM iteration would start: L.pending = 0 / 1
 // (next iteration from the accepted / the old point: the caller finishes with lm_next_iteration and the matching pre-computed step) or -1 (the solve
 // ended, or the line search goes on and L.trial is its next sample).
-__device__ __noinline__ void lm_step(LmState& L, const double* sums, double bound) {
+// defer_gmax: the caller supplies L.last_gmax of the accepted point itself (it is evaluated on another warp meanwhile), whenever pending == 0.
+__device__ __noinline__ void lm_step(LmState& L, const double* sums, double bound, bool defer_gmax) {
   L.total_evaluations++; L.pending = -1;
   if (L.phase == 0) {  // IterationZero
     for (int k = 0; k < 7; k++) { L.x[k] = L.trial[k]; L.x_best[k] = L.trial[k]; }
@@ -273,7 +277,8 @@ __device__ __noinline__ void lm_step(LmState& L, const double* sums, double boun
     L.n_valid = (int)(sums[28] + 0.5);
     L.initial_cost = L.x_cost; L.min_iter_cost = L.x_cost; L.minimum_cost = L.x_cost; L.final_cost = L.x_cost;
     for (int c = 0; c < 6; c++) L.scaling[c] = 1.0 / (1.0 + sqrt(L.H[hidx(c, c)]));
-    L.last_gmax = lm_gmax(L, bound); L.last_successful = 1; L.iteration = 0; L.radius = 1e4; L.decrease_factor = 2.0; L.reuse_diagonal = 0; L.num_invalid = 0;
+    if (!defer_gmax) L.last_gmax = lm_gmax(L, bound);
+    L.last_successful = 1; L.iteration = 0; L.radius = 1e4; L.decrease_factor = 2.0; L.reuse_diagonal = 0; L.num_invalid = 0;
     if (L.n_valid == 0) { lm_finish(L, -1); return; }
     if (!isfinite(L.x_cost)) { lm_finish(L, 4); return; }
     L.pending = 0; return;
@@ -283,7 +288,7 @@ __device__ __noinline__ void lm_step(LmState& L, const double* sums, double boun
     L.cur.x = L.ls_alpha; L.cur.value = sums[27]; L.cur.gradient = gt; L.cur.value_valid = isfinite(sums[27]) ? 1 : 0; L.cur.gradient_valid = (L.cur.value_valid && isfinite(gt)) ? 1 : 0;
     if (L.cur.value_valid && !(L.cur.value > L.x_cost + 1e-4 * L.gd * L.cur.x)) {
       for (int c = 0; c < 6; c++) L.delta[c] *= L.cur.x;   // success: trial == Plus(x, alpha*delta) is the candidate
-      lm_accept_test(L, sums, bound); return;
+      lm_accept_test(L, sums, bound, defer_gmax); return;
     }
     bool failed = false; double step_size = 0;
     if (++L.ls_iters >= 20) failed = true;
@@ -300,10 +305,10 @@ __device__ __noinline__ void lm_step(LmState& L, const double* sums, double boun
     }
     if (!failed) { L.prev = L.cur; L.ls_alpha = step_size; double sd[6]; for (int c = 0; c < 6; c++) sd[c] = step_size * L.delta[c]; d_plus(L.x, sd, bound, L.trial); return; }
     // line search failed: delta stays; the candidate is Plus(x, delta)
-    if (L.cur.x == 1.0) { lm_accept_test(L, sums, bound); return; }
+    if (L.cur.x == 1.0) { lm_accept_test(L, sums, bound, defer_gmax); return; }
     d_plus(L.x, L.delta, bound, L.trial); L.phase = 2; return;
   }
-  lm_accept_test(L, sums, bound);  // phase 2
+  lm_accept_test(L, sums, bound, defer_gmax);  // phase 2
 }
 
 // ------------------------------------------------------------------------------------------------ per-block evaluation
@@ -506,6 +511,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) lm_solve_kernel(SolveArgs a,
   __shared__ double s_red[SOLVE_THREADS / 32][NSUM + 1];
   __shared__ double s_sum[32];
   __shared__ LmState s_lm;     // EVERY CTA keeps its own copy of the solver state and advances it identically
+  __shared__ double s_gmax;
   __shared__ StepOut s_pre[2]; // the next iteration's ComputeStep under both outcomes of the accept test, evaluated by warp 1 while warp 0 decides
   __shared__ K10Smem s_k10;    // mode 4 (fused) only
   RegDevState* st = a.st;
@@ -620,15 +626,23 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) lm_solve_kernel(SolveArgs a,
         }
       }
     }
-    // ---- CTA reduce: warp shuffles, then shared memory, fixed order (warps that own no valid block contribute exact zeros)
+    // ---- CTA reduce: a transposing butterfly over the warp (lane L ends up with the warp's total of sum L: 31 shuffle-adds instead of 29 x 5),
+    // then shared memory, fixed order (warps that own no valid block contribute exact zeros)
     if (__any_sync(FULL, acc[28] != 0.0)) {
+      double w[32];
 #pragma unroll
-      for (int i = 0; i < NSUM; i++) {
-        double v = acc[i];
+      for (int i = 0; i < 32; i++) w[i] = i < NSUM ? acc[i] : 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if (lane == 0) s_red[warp][i] = v;
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; i++) {
+          const double send = upper ? w[i] : w[i + off];          // the half this lane gives away
+          const double keep = upper ? w[i + off] : w[i];
+          w[i] = keep + __shfl_xor_sync(FULL, send, off);
+        }
       }
+      if (lane < NSUM) s_red[warp][lane] = w[0];
     } else if (lane < NSUM) s_red[warp][lane] = 0.0;
     __syncthreads();
     // ---- exchange: this CTA's 29 sums into its row, tag, wait for every row, reduce all rows in fixed order (every CTA does, identically)
@@ -683,13 +697,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) lm_solve_kernel(SolveArgs a,
     if (cur_mode == 3) {
       if (tid == 0) { LmState& L = s_lm; for (int i = 0; i < 21; i++) L.H[i] = s_sum[i]; for (int i = 0; i < 6; i++) L.g[i] = s_sum[21 + i]; L.x_cost = s_sum[27]; L.n_valid = (int)(s_sum[28] + 0.5); L.done = 1; }
     } else {
-      StepIn in;
+      StepIn in; double gx[7], gg[6];
       if (warp == 1 && lane < 2) lm_hypothesis(s_lm, s_sum, lane, in);   // a private copy of the state BEFORE warp 0 touches it
+      if (tid == 64) { for (int k = 0; k < 7; k++) gx[k] = s_lm.trial[k]; for (int c = 0; c < 6; c++) gg[c] = -s_sum[21 + c]; }
       __syncthreads();
       const long long t_h0 = clock64();
       if (warp == 1 && lane < 2) { compute_step(in, bound, s_pre[lane]); if (master && lane == 0) st->prof[13] += clock64() - t_h0; }   // Cholesky + model cost + Plus: the long pole of an LM step ...
-      else if (tid == 0) { lm_step(s_lm, s_sum, bound); if (master) st->prof[14] += clock64() - t_h0; }   // ... next to the accept test, the bookkeeping and the gradient test's Plus
+      else if (tid == 0) { lm_step(s_lm, s_sum, bound, true); if (master) st->prof[14] += clock64() - t_h0; }   // ... next to the accept test and the bookkeeping ...
+      else if (tid == 64) {   // ... and the gradient test of the accepted point (max |x - Plus(x, -g)|), which only the NEXT iteration's entry check reads
+        double pg[7]; d_plus(gx, gg, bound, pg); double mx = 0; for (int k = 0; k < 7; k++) mx = fmax(mx, fabs(gx[k] - pg[k])); s_gmax = mx;
+      }
       __syncthreads();
+      if (tid == 0 && s_lm.pending == 0) s_lm.last_gmax = s_gmax;   // pending == 0 <=> the point just evaluated became x
       if (master && tid == 0) st->prof[15] += clock64() - t_h0;
       if (tid == 0 && s_lm.pending >= 0) lm_next_iteration(s_lm, bound, &s_pre[s_lm.pending]);
     }

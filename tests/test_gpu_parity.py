@@ -747,3 +747,42 @@ def test_frame_to_pose_equals_the_staged_triple_lidar_flow(ctx, oracle):
         it = rec[:, 16:20].copy().view(np.float32).reshape(-1)
         assert np.array_equal(xyz, ref[:, :3]) and np.array_equal(it, ref[:, 3]) and not rec[:, 12:16].any() and not rec[:, 20:].any()
     m.release(); c3.close()
+
+
+@pytest.mark.gpu
+def test_shard_build_on_one_gpu(ctx, oracle):
+    """csrc/shard.cu without a second GPU: every rank's shard of a 4-way split is built on this device (ll_map_build_sharded needs no peers), and
+    (1) the owner table equals the host plan, (2) the kept points are exactly the points within the halo of an owned cell (NumPy restatement), in
+    input order, (3) an exact 5-NN search of a shard returns, for queries of that rank, the neighbours of the whole map whenever the 5th distance is
+    inside the gate (squared distance < 50.0 / 2.0, point_cloud_registration.hpp:254,353)."""
+    from test_multi_gpu_host import _numpy_shard
+    from loam_livox_b200.distributed import cell_owner, plan_shards
+    from loam_livox_b200.registration import Map
+    mc, ms = S.make_map(3000, 60000)
+    world, cell = 4, 2.0
+    origin, dims, owner = plan_shards(np.concatenate([mc, ms]), world, cell)
+    full = Map(ctx, mc, ms)
+    rng = np.random.default_rng(8)
+    q = ms[rng.integers(0, ms.shape[0], 3000)].copy(); q[:, :3] += rng.normal(0, 0.05, (3000, 3)).astype(np.float32)
+    fi, fd = full.nearestKSearch(1, q)
+    own_q = cell_owner(q, origin, cell, dims, owner)
+    total_kept = 0
+    for r in range(world):
+        m = Map(ctx, mc, ms, rank=r, world=world, cell_size=cell)
+        info, table = m.shard_info()
+        assert np.array_equal(table, owner) and list(info.dims) == [int(v) for v in dims] and np.allclose(list(info.origin), origin)
+        ks = _numpy_shard(ms, origin, cell, dims, owner, r, 50.0 ** 0.5 * 1.0001 + 1e-3)
+        kc = _numpy_shard(mc, origin, cell, dims, owner, r, 2.0 ** 0.5 * 1.0001 + 1e-3)
+        assert abs(int(info.kept_surf) - int(ks.sum())) <= 2 and abs(int(info.kept_corner) - int(kc.sum())) <= 2     # fp32 vs fp64 box arithmetic at the halo's rim
+        assert info.kept_surf < info.total_surf == ms.shape[0]
+        total_kept += int(info.kept_surf)
+        sel = np.nonzero(own_q == r)[0]
+        si, sd = m.nearestKSearch(1, q[sel])
+        inside = fd[sel, 4] < 50.0
+        assert inside.any() and np.array_equal(sd[inside], fd[sel][inside])                  # same distances ...
+        kept_idx = np.nonzero(ks)[0]
+        if int(info.kept_surf) == int(ks.sum()):
+            assert np.array_equal(kept_idx[si[inside]], fi[sel][inside])                     # ... and the same points (shard indices -> map indices)
+        m.release()
+    assert total_kept > ms.shape[0]          # halos overlap: the shards together hold more than one copy
+    full.release()
