@@ -369,6 +369,10 @@ __device__ __forceinline__ void warp_knn5(const TreeView& tv, WarpWalk& ws, Warp
   }
 }
 
+#ifdef LL_KNN_R1
+#include "knn_r1.cuh"
+#endif
+
 // Parity hook (ll_knn): world-frame queries in caller order.
 __global__ void __launch_bounds__(KNN_THREADS) knn_query_kernel(TreeView tv, const float4* __restrict__ q, int nq, int* __restrict__ idx5, float* __restrict__ d5) {
   __shared__ WarpWalk walks[WARPS_PER_CTA];
@@ -376,7 +380,13 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query_kernel(TreeView tv, con
   const bool have = g < nq;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f); if (have) p = __ldg(&q[g]);
   const bool active = have && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
-  LaneTop t; warp_knn5<false>(tv, walks[threadIdx.x >> 5], nullptr, active, p.x, p.y, p.z, t, nullptr);
+  LaneTop t;
+#ifdef LL_KNN_R1
+  __shared__ r1::GroupStack stacks[WARPS_PER_CTA];
+  r1::warp_knn5_r1(tv, stacks[threadIdx.x >> 5], active, p.x, p.y, p.z, t, nullptr);
+#else
+  warp_knn5<false>(tv, walks[threadIdx.x >> 5], nullptr, active, p.x, p.y, p.z, t, nullptr);
+#endif
   if (have && lane < LL_KNN) { idx5[g * LL_KNN + lane] = (t.id == 0x7fffffff) ? -1 : t.id; d5[g * LL_KNN + lane] = t.d; }
 }
 
@@ -499,7 +509,12 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_blocks_kernel(KnnBlocksArgs a
     if (have && ncls > 2 * a.cap) skipped = ll_cap_uniform_f(a.rng_seed, a.st->icp_iter, is_corner ? 0 : 1, is_corner ? w : w - a.n_corner) * (float)ncls > (float)(2 * a.cap); }
   const bool active = have && owned && finite_in && !skipped;
   LaneTop t;
+#ifdef LL_KNN_R1
+  __shared__ r1::GroupStack stacks[WARPS_PER_CTA];
+  r1::warp_knn5_r1(tv, stacks[threadIdx.x >> 5], active, qx, qy, qz, t, (a.seed_ids && have) ? a.seed_ids + (size_t)w * LL_KNN : nullptr);
+#else
   warp_knn5<TMA>(tv, walks[threadIdx.x >> 5], TMA ? &stages[threadIdx.x >> 5] : nullptr, active, qx, qy, qz, t, (a.seed_ids && have) ? a.seed_ids + (size_t)w * LL_KNN : nullptr);
+#endif
   if (!have) return;
   if (active && lane < LL_KNN) {   // the neighbours seed the next ICP iteration's search (5 lanes, one 20-byte row)
     if (a.seed_ids) a.seed_ids[(size_t)w * LL_KNN + lane] = (t.id == 0x7fffffff) ? -1 : t.id;

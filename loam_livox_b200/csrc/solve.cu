@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) lm_solve_kernel(SolveArgs a,
   if (master && tid == 0) *((volatile unsigned*)&Y->gen) = gen;
 }
 
-#define SOLVE_MAX_SMEM (100 * 1024)   // two CTAs per SM (another context's solver, or the next launch) fit next to each other
+#define SOLVE_MAX_SMEM (200 * 1024)   // up to ~470k slots; a typical scan (<= 113 KB of slots per CTA) leaves room for a second CTA per SM (another context's solver)
 int solve_max_slots(ll_ctx* ctx) { return ctx->num_sms * ((SOLVE_MAX_SMEM / SLOT_BYTES) / SOLVE_THREADS) * SOLVE_THREADS; }
 
 int solve_prepare(ll_ctx* ctx) {
