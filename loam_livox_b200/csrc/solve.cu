@@ -913,6 +913,10 @@ int launch_solve(ll_ctx* ctx, const SolveArgs& a) {
 
 
 // ---------------------------------------------------------------------------------------------- sharded mode: K10 exchange over peer memory
+// The X buffer is single (not double-buffered): rank A may only start overwriting slot i for ICP iteration k+1 after every rank has finished reading X for
+// iteration k.  That holds because (1) the select that reads X runs on every rank BEFORE that rank's solve #2 launch (stream order), (2) solve #2's first
+// all-reduce cannot complete on any rank before every rank has entered it, and (3) A's next exchange launch follows A's solve #2 in stream order.  The host
+// clears X (NaN) at the start of an iteration; the clear of iteration k+1 is ordered after A's solve #2 of iteration k in the same way.
 struct L1ExchangeArgs { const double* l1; int M; int rank, world; char* comm_local; char* comm_peer[8]; };
 __global__ void __launch_bounds__(256) l1_exchange_kernel(L1ExchangeArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

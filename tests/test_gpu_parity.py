@@ -786,3 +786,35 @@ def test_shard_build_on_one_gpu(ctx, oracle):
         m.release()
     assert total_kept > ms.shape[0]          # halos overlap: the shards together hold more than one copy
     full.release()
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_flann_vectors_and_cap_vectors(ctx):
+    """tests/golden/golden_r2.npz: ll_knn against the answers of REAL FLANN (KDTreeSingleIndex through cv2.flann, make_golden_r2.py) on the golden map,
+    and the residual cap (cap 100, seed 3) against the committed oracle vectors: the features that pass the pre-skip, the block count of every ICP
+    iteration, the pose."""
+    import os
+    from loam_livox_b200 import capi
+    from loam_livox_b200.registration import Map, Point_cloud_registration
+    here = os.path.dirname(__file__)
+    g, s = np.load(os.path.join(here, "golden", "golden_r2.npz")), np.load(os.path.join(here, "golden", "golden_small.npz"))
+    m = Map(ctx, s["map_corner"], s["map_surf"])
+    for which, name in ((1, "surf"), (0, "corner")):
+        ki, kd = m.nearestKSearch(which, s["knn_q"])
+        assert np.array_equal(ki, g[f"flann_idx_{name}"]) and np.array_equal(kd, g[f"flann_d2_{name}"]), name
+    m2 = Map(ctx, g["cap_map_corner"], g["cap_map_surf"])
+    reg = Point_cloud_registration(ctx, maximum_allow_residual_block=int(g["cap"]), rng_seed=int(g["cap_seed"]))
+    reg.set_pose(g["cap_guess_q"], g["cap_guess_t"])
+    typ, a3, v3, ca, sa = reg.build_blocks(m2, g["cap_feat_corner"], g["cap_feat_surf"])
+    assert np.array_equal(np.nonzero(typ)[0], g["cap_slots"]) and (ca, sa) == (int(g["cap_corner_avail"]), int(g["cap_surf_avail"]))
+    st = reg.find_out_incremental_transfrom(m2, g["cap_feat_corner"], g["cap_feat_surf"])
+    r = reg.result
+    assert st == int(g["cap_status"]) and r.icp_iterations == int(g["cap_iters"]) and r.num_residual_blocks == int(g["cap_blocks"])
+    assert np.linalg.norm(np.array(r.t_w_curr) - g["cap_t"]) < 1e-7 and S.quat_angle(np.array(r.q_w_curr), g["cap_q"]) < 1e-7
+    L = capi.lib()
+    k = 0
+    for sd in (0, 3, -1):
+        for it in (0, 5):
+            for stream in (0, 1, 2):
+                assert [L.ll_cap_uniform(sd, it, stream, i) for i in (0, 1, 7, 1000, 399999)] == list(g["cap_uniform"][k])
+                k += 1

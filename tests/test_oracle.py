@@ -377,3 +377,32 @@ def test_scene_alignment_recovers_the_transform_between_two_keyframes(oracle):
     assert runs == 3 and res.registered == 1 and res.status == 1
     assert np.linalg.norm(np.array(res.t_w_curr) - t) < 0.05 and S.quat_angle(np.array(res.q_w_curr), q) < 0.01
     assert res.corner_used == 0 and 3000 < res.num_residual_blocks <= 5000 * 1.3      # ICP_LINE = 0: corners add no residual blocks (:256); the cap of 5000 binds
+
+
+# ---------------------------------------------------------------------------------------------- committed vectors of round 2
+GOLD2 = os.path.join(os.path.dirname(__file__), "golden", "golden_r2.npz")
+
+
+def test_oracle_reproduces_flann_vectors_and_cap_vectors(oracle):
+    """tests/golden/golden_r2.npz: the flann_* arrays were produced by real FLANN (cv2.flann KDTreeSingleIndex, see make_golden_r2.py), the cap_* arrays
+    by the oracle; the GPU test of the same name checks the library against the same file."""
+    g, s = np.load(GOLD2), np.load(GOLD)
+    for name, cloud in (("surf", s["map_surf"]), ("corner", s["map_corner"])):
+        oi, od, _ = oracle.KdTree(cloud).knn(s["knn_q"])
+        assert np.array_equal(oi, g[f"flann_idx_{name}"]) and np.array_equal(od, g[f"flann_d2_{name}"])
+    p = oracle.default_params(q_w_last=g["cap_guess_q"], t_w_last=g["cap_guess_t"], q_w_curr=g["cap_guess_q"], t_w_curr=g["cap_guess_t"],
+                              maximum_allow_residual_block=int(g["cap"]), rng_seed=int(g["cap_seed"]))
+    tc, ts = oracle.KdTree(g["cap_map_corner"]), oracle.KdTree(g["cap_map_surf"])
+    blocks, src, ca, sa = oracle.build_blocks(g["cap_map_corner"], tc, g["cap_map_surf"], ts, g["cap_feat_corner"], g["cap_feat_surf"], p)
+    slot = src[:, 1] + np.where(src[:, 0] == 1, g["cap_feat_corner"].shape[0], 0)
+    assert np.array_equal(slot, g["cap_slots"]) and (ca, sa) == (int(g["cap_corner_avail"]), int(g["cap_surf_avail"]))
+    st, res, tr = oracle.register(g["cap_map_corner"], tc, g["cap_map_surf"], ts, g["cap_feat_corner"], g["cap_feat_surf"], p, want_trace=True)
+    assert st == int(g["cap_status"]) and res.icp_iterations == int(g["cap_iters"]) and res.num_residual_blocks == int(g["cap_blocks"])
+    assert np.array_equal(np.array([t.blocks_before_select for t in tr]), g["cap_blocks_per_iter"])
+    assert np.allclose(res.t_w_curr, g["cap_t"], atol=1e-12) and np.allclose(res.q_w_curr, g["cap_q"], atol=1e-12)
+    k = 0
+    for sd in (0, 3, -1):
+        for it in (0, 5):
+            for stream in (0, 1, 2):
+                assert [oracle.lib().orc_cap_uniform(sd, it, stream, i) for i in (0, 1, 7, 1000, 399999)] == list(g["cap_uniform"][k])
+                k += 1
