@@ -37,3 +37,23 @@ def test_host_threads_ignores_omp_env(monkeypatch):
     import bench
     monkeypatch.setenv("OMP_NUM_THREADS", "1")
     assert bench.host_threads() == len(os.sched_getaffinity(0))
+
+
+def test_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference` as the driver launches it: rank 0 prints ONE JSON line with impl / metric / config / cpu_baseline / e2e, honours the
+    requested steps (they fit the time budget here) and uses the host's cores although torchrun-style OMP_NUM_THREADS=1 is exported; other ranks exit 0 silently."""
+    import json
+    import subprocess
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "3", "--warmup", "3"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "scans_per_sec" and d["unit"] == "scans/s" and d["higher_is_better"] is True
+    assert d["steps"] == 3 and d["n_gpus"] == 2 and d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "host threads" in d["cpu_baseline"]["sample"]
+    assert d["config"]["workload"].startswith("C2:") and d["config"]["pipeline"]["mapping_leaf_surf"] == 0.02
+    env["RANK"] = "1"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "3"], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and not r.stdout.strip()
