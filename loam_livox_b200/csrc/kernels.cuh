@@ -35,21 +35,7 @@ int launch_knn_blocks(ll_ctx* ctx, const KnnBlocksArgs& a);
 int launch_query_sort(ll_ctx* ctx, const KnnBlocksArgs& a, int* d_perm);
 
 // ---------------------------------------------------------------------------------------------- solver (solve.cu)
-struct FnSample { double x, value, gradient; int value_valid, gradient_valid; };
-
-// Levenberg-Marquardt state machine (ceres TrustRegionMinimizer restated), advanced by one thread after every
-// grid-wide evaluation.
-struct LmState {
-  int phase, iteration, max_iterations, num_invalid, done, termination, last_successful, reuse_diagonal;
-  int ls_iters, n_valid, total_iterations, total_evaluations;
-  int pending, _pad;   // after lm_step: -1 nothing to start / 0 next iteration from the accepted point / 1 from the old point
-  double x[7], x_norm, x_cost, g[6], H[21];
-  double trial[7];
-  double scaling[6], diagonal[6], radius, decrease_factor;
-  double delta[6], model_cost_change, gd, dmax, ls_alpha;
-  FnSample prev, cur;
-  double x_best[7], minimum_cost, min_iter_cost, initial_cost, final_cost, last_gmax;
-};
+#include "lm_state.h"   // FnSample, LmState (the state machine itself: lm_core.cuh, included by solve.cu)
 
 struct RegDevState {
   // pose block, contiguous: q_curr(w,x,y,z) t_curr(3) | q_last(4) t_last(3)
