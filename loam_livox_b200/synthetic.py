@@ -269,14 +269,17 @@ def make_distorted_features(pose_last, pose_curr, nc, ns, seed=0):
     return out[0], out[1]
 
 
-def trajectory(n_scans=1000, n_static=50, dt=0.1, speed=1.0, yaw_rate_deg=5.0):
+def trajectory(n_scans=1000, n_static=50, dt=0.1, speed=1.0, yaw_rate_deg=5.0, zero_mean_yaw=False):
     """C3 trajectory: n_static stationary scans, then forward motion with sinusoidal yaw."""
     poses = []
     x, y, yaw = 0.3, 0.2, 0.0
     for i in range(n_scans):
         if i >= n_static:
             k = i - n_static
-            yaw_rate = math.radians(yaw_rate_deg) * math.sin(2 * math.pi * k * dt / 20.0)
+            # zero_mean_yaw: a cosine rate, so that the yaw itself is a zero-mean sinusoid.  The default sine rate integrates to a one-sided yaw and walks the
+            # sensor through the side wall after ~700 scans (found when config C3 was first run at its full 1000 scans); short test sequences keep it.
+            ph = 2 * math.pi * k * dt / 20.0
+            yaw_rate = math.radians(yaw_rate_deg) * (math.cos(ph) if zero_mean_yaw else math.sin(ph))
             yaw += yaw_rate * dt
             x += speed * dt * math.cos(yaw) * 0.3  # keep inside the 42 m room over 950 steps
             y += speed * dt * math.sin(yaw) * 0.3
