@@ -529,7 +529,12 @@ def run_stream(args):
             l0 = ctx.launches()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res, st = gm.process_new_scan(pin[k & 1].numpy(), 100.0 + 0.1 * k)   # pinned host buffer, H2D inside the call
+        try:
+            res, st = gm.process_new_scan(pin[k & 1].numpy(), 100.0 + 0.1 * k)   # pinned host buffer, H2D inside the call
+        except Exception:
+            ls = stats_last
+            print(f"c3: scan {k} failed; pose {poses[k].t}; last stats: " + (f"features {ls.n_corner}+{ls.n_surf}, map {ls.map_corner}+{ls.map_surf}, appended {ls.appended_corner}+{ls.appended_surf}" if ls else "none"), file=sys.stderr)
+            raise
         dt = time.perf_counter() - t0
         if k >= args.warmup:
             times.append(dt)

@@ -383,7 +383,8 @@ int register_device(ll_ctx* ctx, const ll_map* map, const RegArrays& A, int nc, 
   int iter = 0; RegDevState* hs = (RegDevState*)((char*)ctx->pinned + align256(sizeof(RegDevState)));
   const bool sharded = ctx->world > 1 && map->world > 1;
   if (sharded && (map->world != ctx->world || map->rank != ctx->rank)) { ctx->set_error("map shard and context disagree on rank/world"); return LL_ERR_INVALID; }
-  if (map->world > 1 && (std::sqrt(in->maximum_dis_line_for_match) > (double)map->halo[0] || std::sqrt(in->maximum_dis_plane_for_match) > (double)map->halo[1])) {
+  // (the shard was built with halo * 1.0001 + 1 mm, shard.cu: a halo handed over as the float nearest to sqrt(gate) must pass)
+  if (map->world > 1 && (std::sqrt(in->maximum_dis_line_for_match) > (double)map->halo[0] * 1.0001 + 1e-3 || std::sqrt(in->maximum_dis_plane_for_match) > (double)map->halo[1] * 1.0001 + 1e-3)) {
     ctx->set_error("match gates wider than the halo this shard was built with: owner + halo search would no longer be exact"); return LL_ERR_INVALID;
   }
   if (map->world > 1 && ctx->world != map->world) { ctx->set_error("a sharded map needs a context connected to the same number of ranks (ll_comm_connect)"); return LL_ERR_INVALID; }

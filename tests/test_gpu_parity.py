@@ -415,6 +415,29 @@ def test_streaming_mapper_parity(ctx, oracle, mode, window):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+def test_streaming_mapper_with_the_shipped_init_gate(ctx, oracle, mode):
+    """mapping/init_accumulate_frames = 50 as in both YAMLs: 51 stationary scans are inserted unregistered (the registration sees the frame index before
+    the increment), scan 51 is the first ICP; denser leaves than the precision YAML (what bench.py --workload c3 runs).  Counts and poses against the oracle."""
+    from loam_livox_b200 import capi
+    from loam_livox_b200.registration import Laser_mapping
+    poses = S.trajectory(n_scans=58, n_static=51, speed=1.0, zero_mean_yaw=True)
+    pipe = capi.PipelineCfg(pieces=3, use_piece=0, extractor_leaf_corner=0.05, extractor_leaf_surf=0.05, mapping_leaf_corner=0.05, mapping_leaf_surf=0.1, whole_frame=1)
+    gm = Laser_mapping(ctx, reg=capi.default_reg_state(mapping_init_accumulate_frames=50), pipeline=pipe, line_resolution=0.05, plane_resolution=0.1, matching_mode=mode)
+    om = oracle.Mapper(oracle.default_params(mapping_init_accumulate_frames=50, num_threads=8), threads=8, line_resolution=0.05, plane_resolution=0.1,
+                       extractor_leaf_corner=0.05, extractor_leaf_surf=0.05, matching_mode=mode)
+    for k, pose in enumerate(poses):
+        raw = S.make_scan(30000, pose, seed=S.SEED + 300 + k)
+        res, stats = gm.process_new_scan(raw, 100.0 + 0.1 * k)
+        ost, oq, ot = om.process_scan(raw, 100.0 + 0.1 * k)
+        assert res.status == ost and res.registered == (1 if k > 50 else 0), k
+        assert (stats.n_corner, stats.n_surf) == (om.last["n_corner"], om.last["n_surf"]) and stats.n_surf > 1000, k
+        assert (stats.map_corner, stats.map_surf) == (om.last["map_corner"], om.last["map_surf"]), k
+        q, t, f = gm.pose()
+        assert np.linalg.norm(t - ot) < 1e-4 and S.quat_angle(q, oq) < 1e-4, (k, t, ot)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode,window", [(0, 20), (1, 400)])
 def test_streaming_mapper_long_sequence(ctx, oracle, mode, window):
     """60 scans with yaw motion: the history window slides (mode 0: 20 clouds, the arenas ping-pong) / the cell maps grow and get down-sampled-and-
