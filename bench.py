@@ -512,7 +512,7 @@ def run_stream(args):
     n_total = args.steps + args.warmup
     init = 50 if n_total > 200 else 3                # mapping/init_accumulate_frames (50 in both YAMLs); short smoke runs start registering earlier
     LINE, PLANE = 0.05, 0.1
-    poses = S.trajectory(n_scans=n_total, n_static=init + 1, speed=1.0, zero_mean_yaw=True)   # stays inside the room for all 1000 scans
+    poses = S.trajectory(n_scans=n_total, n_static=init + 1, speed=1.0, zero_mean_yaw=True, y0=-1.6)   # stays inside the room and between the pillar rows for all 1000 scans
     ctx = Context(0, max_scan_points=N_SCAN, max_features=N_SCAN)
     pipe = capi.PipelineCfg(pieces=3, use_piece=0, extractor_leaf_corner=LINE, extractor_leaf_surf=PLANE / 2, mapping_leaf_corner=LINE, mapping_leaf_surf=PLANE, whole_frame=1)
     gm = Laser_mapping(ctx, reg=capi.default_reg_state(mapping_init_accumulate_frames=init), pipeline=pipe, line_resolution=LINE, plane_resolution=PLANE,

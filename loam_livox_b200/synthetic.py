@@ -269,10 +269,10 @@ def make_distorted_features(pose_last, pose_curr, nc, ns, seed=0):
     return out[0], out[1]
 
 
-def trajectory(n_scans=1000, n_static=50, dt=0.1, speed=1.0, yaw_rate_deg=5.0, zero_mean_yaw=False):
+def trajectory(n_scans=1000, n_static=50, dt=0.1, speed=1.0, yaw_rate_deg=5.0, zero_mean_yaw=False, y0=0.2):
     """C3 trajectory: n_static stationary scans, then forward motion with sinusoidal yaw."""
     poses = []
-    x, y, yaw = 0.3, 0.2, 0.0
+    x, y, yaw = 0.3, y0, 0.0   # y0: the pillar rows stand at y = -3.7, 0.9, 3.9 (+-0.2); a 1000-scan path must stay in the aisle between them
     for i in range(n_scans):
         if i >= n_static:
             k = i - n_static

@@ -1,8 +1,7 @@
 #!/bin/bash
-# The command of the next gpurun call (edited between calls; the snapshot is taken when the call gets its box).
+# 8-GPU box: world 8 only (sharded check, sharded C4 bench, replicated C2 bench, C5 frames).
 O=gpurun_out
-timeout 300 python -m pytest tests -m gpu -x -q -k "init_gate or shard_build or golden or frame_to_pose or scene" 2>&1 | tail -15 > $O/r2_pytest_new.log; tail -4 $O/r2_pytest_new.log
-bash profiles/tools/run_multi.sh 2 "--cpu-scans 2" skip
-bash profiles/tools/run_multi.sh 4 "" skip
-timeout 500 python bench.py --workload c3 --steps 995 --warmup 5 --matching-mode 0 > $O/r2_bench_c3_mode0.json 2> $O/r2_bench_c3_mode0.err
-echo "== c3_mode0"; grep -E "c3:|Error" $O/r2_bench_c3_mode0.err | tail -3; head -c 400 $O/r2_bench_c3_mode0.json; echo
+bash profiles/tools/run_multi.sh 8
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+timeout 400 $TR --master-port 29777 bench.py --workload c5 --gpus 8 --steps 60 --warmup 3 --no-cpu > $O/r2_bench_c5_w8.json 2> $O/r2_bench_c5_w8.err
+head -c 300 $O/r2_bench_replicas_w8.json; echo; head -c 300 $O/r2_bench_c5_w8.json; echo; grep -E "Error" $O/r2_bench_c5_w8.err | tail -2
