@@ -377,8 +377,17 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) lm_solve_kernel(SolveArgs a,
     {
       const int val = tid & 31, grp = tid >> 5;   // (SOLVE_THREADS / 32) groups x 32 values
       double v = 0;
-      if (val < NSUM) for (int b = grp; b < (int)gridDim.x; b += SOLVE_THREADS / 32) v += __ldcg(&sync_row(Y, gen, b)[val]);
-      if (val < NSUM) s_red[grp][val] = v;
+      if (val < NSUM) {   // rows grp, grp + 8, ...: four loads in flight, four partial sums combined in a fixed order
+        constexpr int G = SOLVE_THREADS / 32;
+        double v0 = 0, v1 = 0, v2 = 0, v3 = 0; int b = grp; const int nb = (int)gridDim.x;
+        for (; b + 3 * G < nb; b += 4 * G) {
+          const double a0 = __ldcg(&sync_row(Y, gen, b)[val]), a1 = __ldcg(&sync_row(Y, gen, b + G)[val]), a2 = __ldcg(&sync_row(Y, gen, b + 2 * G)[val]), a3 = __ldcg(&sync_row(Y, gen, b + 3 * G)[val]);
+          v0 += a0; v1 += a1; v2 += a2; v3 += a3;
+        }
+        for (; b < nb; b += G) v0 += __ldcg(&sync_row(Y, gen, b)[val]);
+        v = (v0 + v1) + (v2 + v3);
+        s_red[grp][val] = v;
+      }
       __syncthreads();
       if (tid < NSUM) { double t = 0; for (int g = 0; g < SOLVE_THREADS / 32; g++) t += s_red[g][tid]; s_sum[tid] = t; }
       __syncthreads();
@@ -575,10 +584,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) lm_solve_kernel(SolveArgs a,
             }
           }
           grid_sync(Y, gen);
-          if (tid == 0) {
-            const int m = min((int)*((volatile unsigned*)&Y->list_cnt), 64); const int want = s_k10.k; double res = 0.0;
-            for (int e = 0; e < m; e++) { const double mine = __ldcg(&Y->list[e]); int rank = 0; for (int q = 0; q < m; q++) rank += (__ldcg(&Y->list[q]) < mine) ? 1 : 0; if (rank == want) res = mine; }
-            s_k10.result = res; s_k10.done = 1;
+          {   // rank the <= 64 collected values: one value per thread out of shared memory (distinct values: exactly one has the wanted rank)
+            double* cand = (double*)s_k10.hist;
+            const int m = min((int)*((volatile unsigned*)&Y->list_cnt), 64);
+            if (tid < m) cand[tid] = __ldcg(&Y->list[tid]);
+            __syncthreads();
+            if (tid < m) { const double mine = cand[tid]; int rank = 0; for (int q = 0; q < m; q++) rank += (cand[q] < mine) ? 1 : 0; if (rank == s_k10.k) s_k10.result = mine; }
+            if (tid == 0) s_k10.done = 1;
           }
           __syncthreads();
         }
