@@ -245,6 +245,8 @@ int  ll_cellmap_append(ll_ctx* ctx, ll_cellmap* map, const void* pts, size_t n, 
  * out_host (cap points) when out_host != NULL.  Cells are visited in ascending (k, j, i) index order (the PCL octree order is unspecified). */
 int  ll_cellmap_assemble(ll_ctx* ctx, ll_cellmap* map, const double q_w_curr[4], const double t_w_curr[3], float search_range, float fov_deg, float leaf,
                          int down_sample_replace, ll_point* out_host, size_t cap, size_t* n_out, int* cells_in_fov, const ll_point** out_dev);
+/* Allocate now for `store_points` stored points and appends of up to `scan_points`: no allocation afterwards while the store stays below that. */
+int  ll_cellmap_reserve(ll_ctx* ctx, ll_cellmap* map, size_t store_points, size_t scan_points);
 int  ll_cellmap_stats(ll_ctx* ctx, ll_cellmap* map, int* cells, int* stored_points, int* frame_idx);
 
 /* ---- streaming odometry: Laser_mapping::process_new_scan + update_buff_for_matching (matching_mode 0 and 1) ------------------------- */
@@ -258,6 +260,10 @@ typedef struct {
   int   matching_mode;                          /* mapping/matching_mode (:689): 0 = sliding window of the last maximum_history_size feature clouds
                                                    (:518-531,1439-1478; what both shipped YAMLs select), 1 = cells in range and in the FOV (:471-516)   */
   int   maximum_history_size;                   /* mapping/maximum_histroy_buffer (:687; YAML 400 / 200)                                   */
+  int   reserve_map_points;                     /* device memory reserved at creation, per feature kind, for the match map (history window / assembled
+                                                   cells, its VoxelGrid, snapshot and index): nothing is reallocated while the map stays below it
+                                                   (default 2 Mi points; 0 = grow on demand, by doubling)                                   */
+  int   reserve_store_points;                   /* same for each cell map's point store (default 4 Mi points; the store of mode 0 only ever grows) */
   ll_pipeline_cfg pipeline;                     /* feature-extraction glue (leaves, pieces)                                                */
   ll_reg_state reg;                             /* registration parameters; the poses in it are the initial pose                           */
 } ll_mapper_config;

@@ -171,6 +171,7 @@ class Points_cloud_map {
   }
   ~Points_cloud_map() { ll_cellmap_release(map_); }
   Points_cloud_map(const Points_cloud_map&) = delete; Points_cloud_map& operator=(const Points_cloud_map&) = delete;
+  void reserve(size_t store_points, size_t scan_points = 0) { ctx_.check(ll_cellmap_reserve(ctx_.get(), map_, store_points, scan_points)); }   // no reallocation below that
   void append_cloud(const PointCloud& pts) { ctx_.check(ll_cellmap_append(ctx_.get(), map_, pts.data(), pts.size(), LL_FMT_PCL32, LL_HOST)); }   // :619-672
   int get_cells_size() const { int c = 0, p = 0, f = 0; ctx_.check(ll_cellmap_stats(ctx_.get(), map_, &c, &p, &f)); return c; }
   // update_buff_for_matching, matching_mode 1, for this map (laser_mapping.hpp:475-516): cells within search_range of t_w_curr and in the FOV,

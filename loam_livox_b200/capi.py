@@ -24,7 +24,7 @@ EXPORTS = [
     "ll_get_features", "ll_extract_point_info", "ll_extract_split_idx", "ll_voxel_downsample", "ll_map_build", "ll_map_release", "ll_map_size",
     "ll_map_build_sharded", "ll_knn", "ll_reg_state_default", "ll_register", "ll_build_blocks", "ll_normal_equations", "ll_solve", "ll_transform",
     "ll_scan_to_pose", "ll_comm_local_handle", "ll_comm_connect", "ll_launch_count", "ll_cellmap_create", "ll_cellmap_release", "ll_cellmap_append",
-    "ll_cellmap_assemble", "ll_cellmap_stats", "ll_voxel_downsample_dev", "ll_transform_dev", "ll_last_features_dev", "ll_mapper_config_default", "ll_mapper_create", "ll_mapper_release",
+    "ll_cellmap_assemble", "ll_cellmap_reserve", "ll_cellmap_stats", "ll_voxel_downsample_dev", "ll_transform_dev", "ll_last_features_dev", "ll_mapper_config_default", "ll_mapper_create", "ll_mapper_release",
     "ll_mapper_process_scan", "ll_mapper_pose", "ll_map_rebuild", "ll_debug_solver_cycles", "ll_state_snapshot_bytes", "ll_set_point_layout", "ll_format_pose_log", "ll_reg_state_yaml", "ll_cap_uniform", "ll_map_shard_info", "ll_shard_plan", "ll_align_cfg_default", "ll_scene_align", "ll_frame_to_pose", "ll_features_to_pointcloud2",
 ]
 
@@ -66,6 +66,7 @@ class MapperConfig(C.Structure):
     _fields_ = [("line_resolution", C.c_float), ("plane_resolution", C.c_float), ("cell_resolution", C.c_float), ("threshold_cell_revisit", C.c_int),
                 ("maximum_search_range_corner", C.c_float), ("maximum_search_range_surface", C.c_float), ("maximum_in_fov_angle", C.c_float),
                 ("down_sample_replace", C.c_int), ("max_cells", C.c_int), ("matching_mode", C.c_int), ("maximum_history_size", C.c_int),
+                ("reserve_map_points", C.c_int), ("reserve_store_points", C.c_int),
                 ("pipeline", PipelineCfg), ("reg", RegState)]
 
 
@@ -143,6 +144,7 @@ def lib():
     L.ll_cellmap_release.argtypes = [vp]
     L.ll_cellmap_append.argtypes = [vp, vp, vp, sz, ci, ci]
     L.ll_cellmap_assemble.argtypes = [vp, vp, vp, vp, cf, cf, cf, ci, vp, sz, C.POINTER(sz), C.POINTER(ci), C.POINTER(vp)]
+    L.ll_cellmap_reserve.argtypes = [vp, vp, C.c_size_t, C.c_size_t]
     L.ll_cellmap_stats.argtypes = [vp, vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
     L.ll_voxel_downsample_dev.argtypes = [vp, vp, sz, cf, vp, C.POINTER(sz)]
     L.ll_transform_dev.argtypes = [vp, vp, vp, vp, sz, vp]

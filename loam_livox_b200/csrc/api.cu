@@ -273,15 +273,28 @@ int ll_last_features_dev(ll_ctx* ctx, const ll_point** corner_dev, size_t* n_cor
 
 // ---------------------------------------------------------------------------------------------- S2
 static int map_index(ll_ctx* ctx, ll_map* m, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where) {
-  size_t nmax = nc > ns ? nc : ns;
-  LL_CUDA(ctx, ctx->feat_buf.reserve(align256(nmax * 16) + 256));
-  float4* d_in = ctx->feat_buf.as<float4>();
-  int st = upload_cloud(ctx, corner, nc, fmt, where, d_in);
-  if (st == LL_OK) st = build_bucket_tree(ctx, d_in, (int)nc, &m->corner);
-  if (st == LL_OK) st = upload_cloud(ctx, surf, ns, fmt, where, d_in);
-  if (st == LL_OK) st = build_bucket_tree(ctx, d_in, (int)ns, &m->surf);
+  // device clouds already in the library's layout are indexed where they lie (the tree keeps its own source-order copy)
+  const bool in_place = where == LL_DEVICE && fmt == LL_FMT_XYZI16;
+  const float4* d_c = (const float4*)corner; const float4* d_s = (const float4*)surf;
+  int st = LL_OK;
+  if (!in_place) {
+    LL_CUDA(ctx, ctx->feat_buf.reserve(align256(nc * 16) + align256(ns * 16) + 512));
+    float4* b = ctx->feat_buf.as<float4>(); d_c = b; d_s = (const float4*)((char*)b + align256(nc * 16));
+    st = upload_cloud(ctx, corner, nc, fmt, where, (float4*)d_c);
+    if (st == LL_OK) st = upload_cloud(ctx, surf, ns, fmt, where, (float4*)d_s);
+    if (st != LL_OK) return st;
+  }
+  // the two indices side by side: corner on the side stream with its own scratch, surface on the context's stream
+  cudaStream_t s = ctx->stream;
+  LL_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
+  LL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+  st = build_bucket_tree_on(ctx, ctx->stream2, ctx->scratch2, d_c, (int)nc, &m->corner);
+  const int st2 = build_bucket_tree_on(ctx, s, ctx->scratch, d_s, (int)ns, &m->surf);
+  LL_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+  LL_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+  if (st == LL_OK) st = st2;
   // host inputs may be freed by the caller as soon as this returns; device inputs are consumed in stream order (the per-scan refresh never waits)
-  if (st == LL_OK && where == LL_HOST && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = LL_ERR_CUDA;
+  if (st == LL_OK && where == LL_HOST && cudaStreamSynchronize(s) != cudaSuccess) st = LL_ERR_CUDA;
   return st;
 }
 static int map_build_common(ll_ctx* ctx, const void* corner, size_t nc, const void* surf, size_t ns, int fmt, int where, ll_map** out) {

@@ -170,10 +170,15 @@ __global__ void cm_rebuild_kernel(const float4* __restrict__ pts, const int* __r
   else if (t < nk + nc && t < cap) { const int c = t - nk; const float4 p = cen[c]; npts[t] = make_float4(p.x, p.y, p.z, 0.f); nslot[t] = cen_slot[c]; nepoch[t] = epoch[cen_slot[c]]; }
 }
 
+static inline size_t cm_store_bytes(size_t cap) { return align256(cap * 16) + 2 * align256(cap * 4); }
 static int cm_reserve_store(ll_ctx* ctx, ll_cellmap* m, int need) {
   if (need <= m->cap_pts) return LL_OK;
   int cap = m->cap_pts > 0 ? m->cap_pts : (1 << 16); while (cap < need) cap *= 2;
-  DevBuf nb; LL_CUDA(ctx, nb.reserve(align256((size_t)cap * 16) + 2 * align256((size_t)cap * 4)));
+  if (m->n_pts == 0 && m->store_buf.cap >= cm_store_bytes((size_t)cap)) {   // nothing to carry over and the (pre-reserved) allocation is large enough
+    float4* np = m->store_buf.as<float4>(); m->pts = np; m->pt_slot = (int*)((char*)np + align256((size_t)cap * 16)); m->pt_epoch = (int*)((char*)m->pt_slot + align256((size_t)cap * 4));
+    m->cap_pts = cap; return LL_OK;
+  }
+  DevBuf nb; LL_CUDA(ctx, nb.reserve(cm_store_bytes((size_t)cap)));
   float4* np = nb.as<float4>(); int* ns = (int*)((char*)np + align256((size_t)cap * 16)); int* ne = (int*)((char*)ns + align256((size_t)cap * 4));
   if (m->n_pts > 0) {
     LL_CUDA(ctx, cudaMemcpyAsync(np, m->pts, (size_t)m->n_pts * 16, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -185,7 +190,34 @@ static int cm_reserve_store(ll_ctx* ctx, ll_cellmap* m, int need) {
   return LL_OK;
 }
 
+// CUB temporary storage of the assembly (select over the table / the store, 64-bit pair sort of the selected points)
+static size_t cm_cub_bytes(int T, int N, cudaStream_t s) {
+  const int big = T > N ? T : N;
+  size_t cub_a = 0, cub_b = 0;
+  cub::DeviceSelect::Flagged(nullptr, cub_a, cub::CountingInputIterator<int>(0), (unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, big, s);
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_b, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, big, 0, 64, s);
+  return cub_a > cub_b ? cub_a : cub_b;
+}
+
 extern "C" {
+
+// Size every buffer of the map for `store_points` stored points and appends of up to `scan_points` points, now: after this, appends and assemblies
+// allocate nothing until the store outgrows the reservation (then it doubles, as before).
+int ll_cellmap_reserve(ll_ctx* ctx, ll_cellmap* m, size_t store_points, size_t scan_points) {
+  if (!ctx || !m) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  size_t cap = 1 << 16; while (cap < store_points) cap *= 2;
+  if (cap > (size_t)1 << 30) return LL_ERR_INVALID;
+  if (m->n_pts == 0) { LL_CUDA(ctx, m->store_buf.reserve_floor(cm_store_bytes(cap))); LL_TRY(cm_reserve_store(ctx, m, (int)cap)); }
+  else LL_TRY(cm_reserve_store(ctx, m, (int)cap));
+  LL_CUDA(ctx, m->store_alt.reserve_floor(cm_store_bytes(cap)));
+  LL_CUDA(ctx, m->out_buf.reserve_floor(cap * 16 + 256));
+  if (scan_points) LL_CUDA(ctx, m->tmp_buf.reserve_floor(align256(scan_points * 16) + align256(scan_points * 4) + 256));
+  // the assembly's scratch (layout in ll_cellmap_assemble): 29 B per table slot + 39 B per stored point + alignment + CUB
+  const size_t T = (size_t)m->table_cap;
+  LL_CUDA(ctx, ctx->scratch.reserve_floor(29 * T + 39 * cap + 20 * 256 + cm_cub_bytes((int)T, (int)cap, ctx->stream) + 1024));
+  return LL_OK;
+}
 
 int ll_cellmap_create(ll_ctx* ctx, float resolution, int revisit_threshold, int max_cells, ll_cellmap** out) {
   if (!ctx || !out || !(resolution > 0.f)) return LL_ERR_INVALID;
@@ -262,11 +294,7 @@ int ll_cellmap_assemble(ll_ctx* ctx, ll_cellmap* m, const double q_wxyz[4], cons
   if (N == 0) return LL_OK;
   CmView v; for (int k = 0; k < 4; k++) v.q[k] = q_wxyz[k]; for (int k = 0; k < 3; k++) { v.t[k] = t[k]; v.sp[k] = (float)t[k]; }
   v.r2 = (double)search_range * (double)search_range; v.fov = fov_deg; v.box = m->resolution * 1.0f; v.half = m->resolution * 0.5f;
-  const int big = T > N ? T : N;
-  size_t cub_a = 0, cub_b = 0, cub_c = 0;
-  cub::DeviceSelect::Flagged(nullptr, cub_a, cub::CountingInputIterator<int>(0), (unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, big, s);
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_b, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, big, 0, 64, s);
-  cub_c = cub_a > cub_b ? cub_a : cub_b;
+  size_t cub_c = cm_cub_bytes(T, N, s);
   // scratch layout
   size_t o = 0; auto take = [&](size_t b) { size_t r = o; o += align256(b); return r; };
   const size_t o_sel = take(T), o_cslots = take((size_t)T * 4), o_ckeys = take((size_t)T * 8), o_ckeys2 = take((size_t)T * 8), o_cslots2 = take((size_t)T * 4), o_rank = take((size_t)T * 4),

@@ -97,9 +97,10 @@ __global__ void transform_kernel(const double* __restrict__ pose7, const float4*
   double wx, wy, wz; qrot_d(q, (double)p.x, (double)p.y, (double)p.z, wx, wy, wz);
   out[i] = make_float4((float)(wx + pose7[4]), (float)(wy + pose7[5]), (float)(wz + pose7[6]), p.w);
 }
-int launch_transform(ll_ctx* ctx, const double* d_pose7, const float4* d_in, int n, float4* d_out) {
+int launch_transform(ll_ctx* ctx, const double* d_pose7, const float4* d_in, int n, float4* d_out) { return launch_transform_on(ctx, ctx->stream, d_pose7, d_in, n, d_out); }
+int launch_transform_on(ll_ctx* ctx, cudaStream_t s, const double* d_pose7, const float4* d_in, int n, float4* d_out) {
   if (n == 0) return LL_OK;
-  transform_kernel<<<ll_div_up(n, 256), 256, 0, ctx->stream>>>(d_pose7, d_in, n, nullptr, d_out); ctx->launches++;
+  transform_kernel<<<ll_div_up(n, 256), 256, 0, s>>>(d_pose7, d_in, n, nullptr, d_out); ctx->launches++;
   LL_CUDA(ctx, cudaGetLastError());
   return LL_OK;
 }

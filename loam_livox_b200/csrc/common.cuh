@@ -23,6 +23,8 @@
 // ------------------------------------------------------------------------------------------------ device arrays
 struct DevBuf {  // grow-only device allocation
   void* p = nullptr; size_t cap = 0;
+  size_t floor = 0;   // smallest size ever allocated: a caller that knows how far the buffer will grow (the streaming mapper) sets it once, then nothing is
+                      // reallocated in steady state (a cudaMalloc + cudaFree pair was measured at 100-800 ms on the GPU boxes: profiles/r2/bench_c3_*)
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
     // first allocation: a little slack; regrowth: at least double, so that a buffer following a growing map is reallocated O(log n) times
@@ -30,6 +32,7 @@ struct DevBuf {  // grow-only device allocation
     size_t want = bytes + bytes / 8 + 256;
     if (want < ((size_t)8 << 20)) want = (size_t)8 << 20;   // floor: a (re)allocation costs 60-90 ms on this platform, 8 MB of a 180 GB HBM costs nothing
     if (p && want < 2 * cap) want = 2 * cap;
+    if (want < floor) want = floor;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     cudaError_t e = cudaMalloc(&p, want);
@@ -37,6 +40,7 @@ struct DevBuf {  // grow-only device allocation
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  cudaError_t reserve_floor(size_t bytes) { if (bytes > floor) floor = bytes; return reserve(floor); }   // allocate the floor now
   template <typename T> T* as() const { return (T*)p; }
 };
 

@@ -11,6 +11,7 @@ struct TreeView {
 };
 TreeView make_view(const BucketTree& t);
 int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t);
+int build_bucket_tree_on(ll_ctx* ctx, cudaStream_t s, DevBuf& scratch, const float4* d_src, int n_src, BucketTree* t);
 
 struct RegDevState;
 struct KnnBlocksArgs {
@@ -109,6 +110,7 @@ int solve_max_slots(ll_ctx* ctx);
 // ---------------------------------------------------------------------------------------------- clouds (cloud.cu)
 int upload_cloud(ll_ctx* ctx, const void* src, size_t n, int fmt, int where, float4* d_dst);   // async on ctx->stream
 int launch_transform(ll_ctx* ctx, const double* d_pose7, const float4* d_in, int n, float4* d_out);
+int launch_transform_on(ll_ctx* ctx, cudaStream_t s, const double* d_pose7, const float4* d_in, int n, float4* d_out);
 int launch_pack_strided(ll_ctx* ctx, const float4* d_src, int n, unsigned char* d_dst);   // 16-byte points -> PointCloud2 records (ctx->layout)
 // VoxelGrid on device: d_in [n] -> d_out [<= n], *d_n_out on device. n given by host, or by device count d_n_in (may be null).
 struct VoxelTemps { DevBuf* buf; };

@@ -147,10 +147,12 @@ static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Everything is enqueued on the context's stream and nothing is read back: the layout is sized from n_src (the non-finite points -- there are
 // usually none -- only leave a few all-pad buckets with neutral boxes at the end), the count of finite points and the box stay on the device.
-int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t) {
+int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t) { return build_bucket_tree_on(ctx, ctx->stream, ctx->scratch, d_src, n_src, t); }
+// Same on an explicit stream with its own scratch arena: the corner and the surface index of one map are built side by side (every kernel of a
+// 100k-point build is far too small to fill the GPU).
+int build_bucket_tree_on(ll_ctx* ctx, cudaStream_t s, DevBuf& scratch, const float4* d_src, int n_src, BucketTree* t) {
   { DevBuf keep = t->storage; *t = BucketTree(); t->storage = keep; }   // re-indexing in place (ll_map_rebuild) reuses the allocation
   t->n_src = n_src;
-  cudaStream_t s = ctx->stream;
   // key width: lidar maps are surfaces, so a grid of 2^b cells per axis has ~4^b occupied cells; b = ceil(log2(n) / 2) - 1 keeps the occupied
   // cells well below a bucket's 32 points (5M points: b = 11, 34 sorted bits = 5 radix passes instead of 8; 30k points: b = 7, 3 passes)
   int lg = 0; while ((1ll << lg) < (long long)(n_src > 0 ? n_src : 1)) lg++;
@@ -164,8 +166,8 @@ int build_bucket_tree(ll_ctx* ctx, const float4* d_src, int n_src, BucketTree* t
   else cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, n_src > 0 ? n_src : 1, 0, sort_bits, s);
   size_t off_bbox = 0, off_k0 = align256(64), off_k1 = off_k0 + align256((size_t)n_src * ksz), off_v0 = off_k1 + align256((size_t)n_src * ksz),
          off_v1 = off_v0 + align256((size_t)n_src * 4), off_tmp = off_v1 + align256((size_t)n_src * 4);
-  LL_CUDA(ctx, ctx->scratch.reserve(off_tmp + temp_bytes + 256));
-  char* base = ctx->scratch.as<char>();
+  LL_CUDA(ctx, scratch.reserve(off_tmp + temp_bytes + 256));
+  char* base = scratch.as<char>();
   int* bbox = (int*)(base + off_bbox);
   int* v0 = (int*)(base + off_v0); int* v1 = (int*)(base + off_v1);
   t->n = n_src; t->n_pad = ll_div_up(n_src > 0 ? n_src : 1, BUCKET) * BUCKET;

@@ -20,6 +20,7 @@ int ll_cellmap_create(ll_ctx*, float, int, int, ll_cellmap**);
 void ll_cellmap_release(ll_cellmap*);
 int ll_cellmap_append(ll_ctx*, ll_cellmap*, const void*, size_t, int, int);
 int ll_cellmap_assemble(ll_ctx*, ll_cellmap*, const double*, const double*, float, float, float, int, ll_point*, size_t, size_t*, int*, const ll_point**);
+int ll_cellmap_reserve(ll_ctx*, ll_cellmap*, size_t, size_t);
 }
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -51,6 +52,7 @@ struct HistoryWindow {
     segs.emplace_back(tail, n); tail += n;
     return LL_OK;
   }
+  int reserve(ll_ctx* ctx, size_t points) { for (auto& b : buf) LL_CUDA(ctx, b.reserve_floor((points + points / 2 + 1024) * 16)); return LL_OK; }
   void pop_front() { if (!segs.empty()) segs.erase(segs.begin()); }
   void release() { buf[0].release(); buf[1].release(); segs.clear(); tail = 0; }
 };
@@ -72,7 +74,29 @@ struct ll_mapper {
   bool map_dirty = false;   // m_if_mapping_updated_{corner,surface}
 };
 
+// Every buffer whose size follows the map is allocated here, once, for the configured reservation (HBM is 180 GB; a reallocation costs
+// 100-800 ms on the GPU boxes and one such spike per doubling of the map dominated the mean scan time of the 1000-scan stream in round 2's first
+// measurement).  Past the reservation everything still grows by doubling.
+static int mapper_reserve(ll_ctx* ctx, ll_mapper* m) {
+  const size_t R = (size_t)(m->cfg.reserve_map_points > 0 ? m->cfg.reserve_map_points : 0), S = (size_t)(m->cfg.reserve_store_points > 0 ? m->cfg.reserve_store_points : 0);
+  const size_t F = (size_t)ctx->cfg.max_features + 16;
+  LL_CUDA(ctx, m->work.reserve_floor(4 * align256(F * 16) + 1024));
+  if (S) { LL_TRY(ll_cellmap_reserve(ctx, m->cells_corner, S, F)); LL_TRY(ll_cellmap_reserve(ctx, m->cells_surf, S, F)); }
+  if (!R) return LL_OK;
+  LL_TRY(m->his_corner.reserve(ctx, R)); LL_TRY(m->his_surf.reserve(ctx, R));
+  LL_CUDA(ctx, m->snap.reserve_floor(2 * align256((R + 1) * 16) + 256));
+  LL_CUDA(ctx, ctx->feat_buf.reserve_floor(2 * align256(R * 16) + 512));
+  // index build (build_bucket_tree): 2 key + 2 value arrays and the radix sort's temporaries; whole-map VoxelGrid (launch_voxel_grid_on): the same order
+  LL_CUDA(ctx, ctx->scratch.reserve_floor(64 * R + ((size_t)16 << 20)));
+  LL_CUDA(ctx, ctx->scratch2.reserve_floor(64 * R + ((size_t)16 << 20)));   // the corner chains run on the side stream with this arena
+  // tree storage: padded points + source copy + boxes (1 KB per 32 buckets per level, < 1.04 B per point-byte)
+  for (BucketTree* t : {&m->match_map->corner, &m->match_map->surf}) LL_CUDA(ctx, t->storage.reserve_floor(34 * R + ((size_t)4 << 20)));
+  return LL_OK;
+}
+
 extern "C" {
+
+void ll_mapper_release(ll_mapper* m);
 
 void ll_mapper_config_default(ll_mapper_config* c) {
   memset(c, 0, sizeof(*c));
@@ -85,6 +109,7 @@ void ll_mapper_config_default(ll_mapper_config* c) {
   c->pipeline.extractor_leaf_corner = 0.1f; c->pipeline.extractor_leaf_surf = 0.2f; c->pipeline.mapping_leaf_corner = 0.1f; c->pipeline.mapping_leaf_surf = 0.4f;
   ll_reg_state_default(&c->reg);
   c->max_cells = 0;
+  c->reserve_map_points = 1 << 21; c->reserve_store_points = 1 << 22;
 }
 
 int ll_mapper_create(ll_ctx* ctx, const ll_mapper_config* cfg, ll_mapper** out) {
@@ -96,6 +121,9 @@ int ll_mapper_create(ll_ctx* ctx, const ll_mapper_config* cfg, ll_mapper** out) 
   for (int k = 0; k < 4; k++) m->q_w_curr[k] = cfg->reg.q_w_curr[k];
   for (int k = 0; k < 3; k++) m->t_w_curr[k] = cfg->reg.t_w_curr[k];
   ll_extract_reset(ctx);
+  m->match_map = new ll_map(); m->match_map->device = ctx->device;   // indexed in place by every refresh (ll_map_rebuild)
+  st = mapper_reserve(ctx, m);
+  if (st != LL_OK) { ll_mapper_release(m); return st; }
   *out = m; return LL_OK;
 }
 void ll_mapper_release(ll_mapper* m) {
@@ -147,14 +175,17 @@ int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int
     LL_CUDA(ctx, m->snap.reserve(align256((mc + 1) * 16) + align256((ms + 1) * 16) + 256));
     float4* s0 = m->snap.as<float4>(); float4* s1 = (float4*)((char*)s0 + align256((mc + 1) * 16)); int* d_sc = (int*)((char*)s1 + align256((ms + 1) * 16));
     int hc[2] = {0, 0};
-    if (mc > 0) LL_TRY(launch_voxel_grid(ctx, (const float4*)d_mc, (int)mc, nullptr, m->cfg.line_resolution, s0, d_sc)); else LL_CUDA(ctx, cudaMemsetAsync(d_sc, 0, 4, s));      // :533-534
+    // the two whole-map VoxelGrids side by side (corner on the side stream with its own scratch)
+    cudaStream_t s2 = ctx->stream2;
+    LL_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s)); LL_CUDA(ctx, cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+    if (mc > 0) LL_TRY(launch_voxel_grid_on(ctx, s2, ctx->scratch2, (const float4*)d_mc, (int)mc, nullptr, m->cfg.line_resolution, s0, d_sc)); else LL_CUDA(ctx, cudaMemsetAsync(d_sc, 0, 4, s2));      // :533-534
     if (ms > 0) LL_TRY(launch_voxel_grid(ctx, (const float4*)d_ms, (int)ms, nullptr, m->cfg.plane_resolution, s1, d_sc + 1)); else LL_CUDA(ctx, cudaMemsetAsync(d_sc + 1, 0, 4, s));   // :536-537
+    LL_CUDA(ctx, cudaEventRecord(ctx->ev_join, s2)); LL_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
     LL_CUDA(ctx, cudaMemcpyAsync(hc, d_sc, 8, cudaMemcpyDeviceToHost, s));
     LL_CUDA(ctx, cudaStreamSynchronize(s));
     m->have_map = false;
     if (hc[0] > 0 && hc[1] > 0) {
-      if (!m->match_map) LL_TRY(ll_map_build(ctx, s0, (size_t)hc[0], s1, (size_t)hc[1], LL_FMT_XYZI16, LL_DEVICE, &m->match_map));
-      else LL_TRY(ll_map_rebuild(ctx, m->match_map, s0, (size_t)hc[0], s1, (size_t)hc[1], LL_FMT_XYZI16, LL_DEVICE));   // buffers reused: no allocation per scan
+      LL_TRY(ll_map_rebuild(ctx, m->match_map, s0, (size_t)hc[0], s1, (size_t)hc[1], LL_FMT_XYZI16, LL_DEVICE));   // buffers reused: no allocation per scan
       m->have_map = true;
     }                      // :544-545
     m->snap_n[0] = hc[0]; m->snap_n[1] = hc[1]; m->fov[0] = fov_c; m->fov[1] = fov_s;
@@ -184,8 +215,13 @@ int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int
   double* h = (double*)((char*)ctx->pinned + 40960); for (int k = 0; k < 4; k++) h[k] = out->q_w_curr[k]; for (int k = 0; k < 3; k++) h[4 + k] = out->t_w_curr[k];
   double* d_pose = (double*)(d_cnt + 16);
   LL_CUDA(ctx, cudaMemcpyAsync(d_pose, h, 7 * sizeof(double), cudaMemcpyHostToDevice, s));
-  if (nc > 0) { LL_TRY(launch_transform(ctx, d_pose, A.feat, nc, w2)); LL_TRY(launch_voxel_grid(ctx, w2, nc, nullptr, m->cfg.line_resolution, w0, d_cnt)); } else LL_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 4, s));
-  if (ns > 0) { LL_TRY(launch_transform(ctx, d_pose, A.feat + nc, ns, w3)); LL_TRY(launch_voxel_grid(ctx, w3, ns, nullptr, m->cfg.plane_resolution, w1, d_cnt + 1)); } else LL_CUDA(ctx, cudaMemsetAsync(d_cnt + 1, 0, 4, s));
+  {
+    cudaStream_t s2 = ctx->stream2;
+    LL_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s)); LL_CUDA(ctx, cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+    if (nc > 0) { LL_TRY(launch_transform_on(ctx, s2, d_pose, A.feat, nc, w2)); LL_TRY(launch_voxel_grid_on(ctx, s2, ctx->scratch2, w2, nc, nullptr, m->cfg.line_resolution, w0, d_cnt)); } else LL_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 4, s2));
+    if (ns > 0) { LL_TRY(launch_transform(ctx, d_pose, A.feat + nc, ns, w3)); LL_TRY(launch_voxel_grid(ctx, w3, ns, nullptr, m->cfg.plane_resolution, w1, d_cnt + 1)); } else LL_CUDA(ctx, cudaMemsetAsync(d_cnt + 1, 0, 4, s));
+    LL_CUDA(ctx, cudaEventRecord(ctx->ev_join, s2)); LL_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+  }
   LL_CUDA(ctx, cudaMemcpyAsync(hc, d_cnt, 8, cudaMemcpyDeviceToHost, s));
   LL_CUDA(ctx, cudaStreamSynchronize(s));
   // history window (:1439-1478): r_diff / t_diff compare the pose adopted from the PREVIOUS scan (m_q_w_curr is only overwritten at :1498) with the

@@ -341,6 +341,10 @@ class Points_cloud_map:
         except Exception:
             pass
 
+    def reserve(self, store_points: int, scan_points: int = 0):
+        """Allocate now for that many stored points (and appends of up to scan_points): nothing is reallocated below that."""
+        self.ctx.check(self.ctx._lib.ll_cellmap_reserve(self.ctx.h, self.h, int(store_points), int(scan_points)))
+
     def append_cloud(self, pts):
         pts, fmt = _pts(pts)
         self.ctx.check(self.ctx._lib.ll_cellmap_append(self.ctx.h, self.h, pts.ctypes.data, pts.shape[0], fmt, capi.LL_HOST))

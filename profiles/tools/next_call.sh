@@ -1,2 +1,2 @@
 #!/bin/bash
-bash profiles/tools/final_n1.sh
+bash profiles/tools/c3_call.sh
