@@ -517,10 +517,10 @@ def run_stream(args):
     pipe = capi.PipelineCfg(pieces=3, use_piece=0, extractor_leaf_corner=LINE, extractor_leaf_surf=PLANE / 2, mapping_leaf_corner=LINE, mapping_leaf_surf=PLANE, whole_frame=1)
     gm = Laser_mapping(ctx, reg=capi.default_reg_state(mapping_init_accumulate_frames=init), pipeline=pipe, line_resolution=LINE, plane_resolution=PLANE,
                        matching_mode=args.matching_mode, maximum_history_size=400,
-                       reserve_map_points=1 << 21, reserve_store_points=1 << 23)   # sized for the whole sequence: no reallocation inside the timed calls
+                       reserve_map_points=1 << 22, reserve_store_points=1 << 23)   # sized for the whole sequence: no reallocation inside the timed calls
     pin = [torch.empty((N_SCAN, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
     sampler = ClockSampler(0); sampler.start()
-    times, stats_last, l0, phases, checkpoints = [], None, 0, [], {}
+    times, stats_last, l0, phases, checkpoints, track = [], None, 0, [], {}, []
     R0, t0w = poses[0].R(), poses[0].t
     n_cpu = 0 if args.no_cpu else min(n_total, init + 30)
     for k in range(n_total):
@@ -541,18 +541,22 @@ def run_stream(args):
             times.append(dt)
             phases.append((st.ms_front_end, st.ms_refresh, st.ms_register, st.ms_append))
         stats_last = st
+        if args.dump_poses:
+            q, t, f = gm.pose(); track.append([float(x) for x in q] + [float(x) for x in t])
         if k + 1 in (n_cpu, n_total):
             q, t, f = gm.pose()
             checkpoints[k + 1] = float(np.linalg.norm(t - R0.T @ (poses[k].t - t0w)))
             final_pose = {"scan": k + 1, "q_wxyz": [float(x) for x in q], "t": [float(x) for x in t]}
     clocks = sampler.stop()
+    if args.dump_poses:
+        np.save(args.dump_poses, np.array(track))
     line = {"metric": "scans_per_sec", "value": len(times) / float(np.sum(times)), "unit": "scans/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 kNN / f64 solve", "data": "synthetic",
             "config": {"workload": f"C3: streaming sequence of {n_total} 100k-pt scans, matching_mode {args.matching_mode} "
                                    f"({'history window of 400 feature clouds' if args.matching_mode == 0 else 'growing device cell map, radius + FOV select'}), match map re-indexed after every scan; leaves {LINE}/{PLANE} m",
                        "final_map_points": [stats_last.map_corner, stats_last.map_surf], "features_per_scan": [stats_last.n_corner, stats_last.n_surf],
                        "final_position_error_m": checkpoints.get(n_total), "position_error_m_at_scan": checkpoints,
-                       "final_pose": final_pose, "reserved_points": {"map": 1 << 21, "store": 1 << 23}, "calls_over_20ms": int(np.sum(np.array(times) > 0.02))},
+                       "final_pose": final_pose, "reserved_points": {"map": 1 << 22, "store": 1 << 23}, "calls_over_20ms": int(np.sum(np.array(times) > 0.02))},
             "clocks": clocks, "e2e": {"value": len(times) / float(np.sum(times)), "unit": "scans/s", "h2d_bytes_per_step": N_SCAN * 16, "d2h_bytes_per_step": 1400},
             "gpu_launches": int(ctx.launches() - l0), "p50_ms": 1e3 * float(np.median(times)), "p99_ms": 1e3 * float(np.quantile(times, 0.99)),
             "phase_ms_median": dict(zip(("front_end", "refresh", "register", "append"), [float(x) for x in np.median(np.array(phases), axis=0)])),
@@ -684,6 +688,7 @@ def main():
                     "sharded = config C4: ONE scan registered by all GPUs together against the 20M-point map sharded by spatial cell (strong scaling)")
     ap.add_argument("--contexts", type=int, default=1, help="scans in flight per GPU (throughput mode: K contexts on K host threads sharing one map; the reference runs maximum_parallel_thread of them)")
     ap.add_argument("--matching-mode", type=int, default=0, choices=[0, 1], help="c3 only: mapping/matching_mode (0 = history window, the shipped YAMLs' mode; 1 = cell map)")
+    ap.add_argument("--dump-poses", default=None, help="c3 only: write the pose after every scan (q_wxyz, t) to this .npy (diagnostics: first scan at which GPU and oracle part)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-scans", type=int, default=5)
     args = ap.parse_args()

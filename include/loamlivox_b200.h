@@ -262,7 +262,8 @@ typedef struct {
   int   maximum_history_size;                   /* mapping/maximum_histroy_buffer (:687; YAML 400 / 200)                                   */
   int   reserve_map_points;                     /* device memory reserved at creation, per feature kind, for the match map (history window / assembled
                                                    cells, its VoxelGrid, snapshot and index): nothing is reallocated while the map stays below it
-                                                   (default 2 Mi points; 0 = grow on demand, by doubling)                                   */
+                                                   (default 4 Mi points >= maximum_history_size x down-sampled features per scan; 0 = grow on
+                                                   demand, by doubling)                                                                     */
   int   reserve_store_points;                   /* same for each cell map's point store (default 4 Mi points; the store of mode 0 only ever grows) */
   ll_pipeline_cfg pipeline;                     /* feature-extraction glue (leaves, pieces)                                                */
   ll_reg_state reg;                             /* registration parameters; the poses in it are the initial pose                           */

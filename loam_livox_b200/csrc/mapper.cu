@@ -11,6 +11,8 @@
 // The reference refreshes the match map on a background thread after every registered scan, with the pose of that scan; here the refresh
 // runs at the start of the next scan (same pose, same map content), so the result is the reference's with maximum_parallel_thread = 1.
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 #include "kernels.cuh"
@@ -72,6 +74,7 @@ struct ll_mapper {
   int snap_n[2] = {0, 0}, fov[2] = {0, 0};
   bool have_map = false;
   bool map_dirty = false;   // m_if_mapping_updated_{corner,surface}
+  bool trace = false;       // LL_MAPPER_TRACE=1
 };
 
 // Every buffer whose size follows the map is allocated here, once, for the configured reservation (HBM is 180 GB; a reallocation costs
@@ -109,7 +112,7 @@ void ll_mapper_config_default(ll_mapper_config* c) {
   c->pipeline.extractor_leaf_corner = 0.1f; c->pipeline.extractor_leaf_surf = 0.2f; c->pipeline.mapping_leaf_corner = 0.1f; c->pipeline.mapping_leaf_surf = 0.4f;
   ll_reg_state_default(&c->reg);
   c->max_cells = 0;
-  c->reserve_map_points = 1 << 21; c->reserve_store_points = 1 << 22;
+  c->reserve_map_points = 1 << 22; c->reserve_store_points = 1 << 22;   // window of 400 clouds x up to ~10k down-sampled features; see mapper_reserve
 }
 
 int ll_mapper_create(ll_ctx* ctx, const ll_mapper_config* cfg, ll_mapper** out) {
@@ -121,6 +124,7 @@ int ll_mapper_create(ll_ctx* ctx, const ll_mapper_config* cfg, ll_mapper** out) 
   for (int k = 0; k < 4; k++) m->q_w_curr[k] = cfg->reg.q_w_curr[k];
   for (int k = 0; k < 3; k++) m->t_w_curr[k] = cfg->reg.t_w_curr[k];
   ll_extract_reset(ctx);
+  { const char* e = getenv("LL_MAPPER_TRACE"); m->trace = e && e[0] == '1'; }
   m->match_map = new ll_map(); m->match_map->device = ctx->device;   // indexed in place by every refresh (ll_map_rebuild)
   st = mapper_reserve(ctx, m);
   if (st != LL_OK) { ll_mapper_release(m); return st; }
@@ -224,6 +228,7 @@ int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int
   }
   LL_CUDA(ctx, cudaMemcpyAsync(hc, d_cnt, 8, cudaMemcpyDeviceToHost, s));
   LL_CUDA(ctx, cudaStreamSynchronize(s));
+  const double tr0 = now_ms();
   // history window (:1439-1478): r_diff / t_diff compare the pose adopted from the PREVIOUS scan (m_q_w_curr is only overwritten at :1498) with the
   // pose of the last addition; history_add_t_step = history_add_angle_step = 0 (:83-84)
   {
@@ -240,8 +245,12 @@ int ll_mapper_process_scan(ll_mapper* m, const void* raw, size_t n, int fmt, int
     if ((int)m->his_corner.segs.size() > m->cfg.maximum_history_size) m->his_corner.pop_front();
     if ((int)m->his_surf.segs.size() > m->cfg.maximum_history_size) m->his_surf.pop_front();
   }
+  const double tr1 = now_ms();
   LL_TRY(ll_cellmap_append(ctx, m->cells_corner, w0, (size_t)hc[0], LL_FMT_XYZI16, LL_DEVICE));
+  const double tr2 = now_ms();
   LL_TRY(ll_cellmap_append(ctx, m->cells_surf, w1, (size_t)hc[1], LL_FMT_XYZI16, LL_DEVICE));
+  if (m->trace && now_ms() - tp > 10.0)   // LL_MAPPER_TRACE=1: where a slow append went (transform + VoxelGrid + sync | history | corner cells | surface cells)
+    fprintf(stderr, "ll_mapper trace: frame %d append %.2f ms = features %.2f + history %.2f + cells %.2f + %.2f\n", m->frame_index, now_ms() - tp, tr0 - tp, tr1 - tr0, tr2 - tr1, now_ms() - tr2);
   m->map_dirty = true;                                                           // m_if_mapping_updated_* (:1490-1491)
   if (stats) { stats->appended_corner = hc[0]; stats->appended_surf = hc[1]; stats->ms_append = (float)(now_ms() - tp); }
   for (int k = 0; k < 4; k++) m->q_w_curr[k] = out->q_w_curr[k]; for (int k = 0; k < 3; k++) m->t_w_curr[k] = out->t_w_curr[k];   // :1496-1505

@@ -18,10 +18,12 @@ poses = S.trajectory(n_scans=n_total, n_static=init + 1, speed=1.0, zero_mean_ya
 om = oracle.Mapper(oracle.default_params(mapping_init_accumulate_frames=init, num_threads=8), threads=8, line_resolution=LINE, plane_resolution=PLANE,
                    extractor_leaf_corner=LINE, extractor_leaf_surf=PLANE / 2, matching_mode=mode, maximum_history_size=400)
 R0, t0w = poses[0].R(), poses[0].t
-out, t_start = {}, time.time()
+out, t_start, track = {}, time.time(), []
 for k in range(n_total):
     st, q, t = om.process_scan(S.make_scan(N_SCAN, poses[k], seed=S.SEED + k), 100.0 + 0.1 * k)
+    track.append([float(x) for x in q] + [float(x) for x in t])
     if k + 1 in (80, 200, 500, n_total):
         out[k + 1] = float(np.linalg.norm(t - R0.T @ (poses[k].t - t0w)))
         print(k + 1, out[k + 1], f"{time.time() - t_start:.0f} s", flush=True)
+np.save(f"/tmp/c3_oracle_track_mode{mode}.npy", np.array(track))
 print(json.dumps({"matching_mode": mode, "oracle_position_error_m_at_scan": out, "final_pose": {"scan": n_total, "q_wxyz": [float(x) for x in q], "t": [float(x) for x in t]}}))
