@@ -62,6 +62,9 @@ void ll_config_default(ll_config* cfg);
 
 int  ll_ctx_create(const ll_config* cfg, int device, ll_ctx** out);
 void ll_ctx_destroy(ll_ctx* ctx);
+/* Optional: run one toy registration now, so that the module loads and the first cooperative launch CUDA defers to first use (1 - 70 ms on a B200 box)
+ * do not land in the first registered scan.  ll_mapper_create calls it; nothing else depends on it. */
+int  ll_ctx_warmup(ll_ctx* ctx);
 const char* ll_last_error(const ll_ctx* ctx);
 /* CUDA stream of the context as a cudaStream_t cast to void* (all work of a context is enqueued on it). */
 void* ll_ctx_stream(ll_ctx* ctx);

@@ -489,6 +489,34 @@ int ll_register(ll_ctx* ctx, const ll_map* map, const void* scan_corner, size_t 
   return register_device(ctx, map, A, (int)nc, (int)ns, in, out);
 }
 
+// One tiny registration (three planes and two edges: 1240 map points, 310 features) through the whole device path, result discarded.  It pays -- once, at a
+// time of the caller's choosing -- what CUDA defers to first use: the module loads of the kNN / solver / sort kernels and the first cooperative launch
+// (1 - 70 ms on the GPU boxes, measured as the first registered scan of a stream: profiles/r2/c3_first_registration.txt).  ll_mapper_create calls it.
+int ll_ctx_warmup(ll_ctx* ctx) {
+  if (!ctx) return LL_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  std::vector<ll_point> surf, corner, fs, fc;
+  auto add = [](std::vector<ll_point>& v, float x, float y, float z) { ll_point p; p.x = x; p.y = y; p.z = z; p.intensity = 0.f; v.push_back(p); };
+  for (int i = 0; i < 20; i++) for (int j = 0; j < 20; j++) {
+    const float u = 0.1f * i + 0.013f * (j % 3), v = 0.1f * j + 0.007f * (i % 5);
+    add(surf, 1.f + u, -1.f + v, 0.f); add(surf, 1.f + u, 1.2f, 0.05f + v); add(surf, 3.2f, -1.f + u, 0.05f + v);
+    if ((i * 20 + j) % 4 == 0) { add(fs, 1.f + u + 0.004f, -1.f + v - 0.003f, 0.006f); add(fs, 1.f + u, 1.195f, 0.05f + v); add(fs, 3.194f, -1.f + u, 0.05f + v); }
+  }
+  for (int k = 0; k < 20; k++) { add(corner, 3.2f, 1.2f, 0.1f * k); add(corner, 1.f + 0.1f * k, 1.2f, 0.f); if (k % 4 == 0) { add(fc, 3.195f, 1.197f, 0.1f * k + 0.02f); add(fc, 1.02f + 0.1f * k, 1.196f, 0.004f); } }
+  if ((int)(fc.size() + fs.size()) > ctx->cfg.max_features) return LL_OK;   // a context sized for less than the toy problem: nothing to warm
+  ll_map* m = nullptr;
+  int st = ll_map_build(ctx, corner.data(), corner.size(), surf.data(), surf.size(), LL_FMT_XYZI16, LL_HOST, &m);
+  if (st == LL_OK) {
+    ll_reg_state rs; ll_reg_state_default(&rs); rs.current_frame_index = rs.mapping_init_accumulate_frames + 1;
+    ll_reg_result r;
+    st = ll_register(ctx, m, fc.data(), fc.size(), fs.data(), fs.size(), LL_FMT_XYZI16, LL_HOST, &rs, &r);
+    if (st == LL_ERR_NO_BLOCKS) st = LL_OK;   // (nothing here depends on the outcome of the toy problem)
+  }
+  if (m) ll_map_release(m);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return LL_ERR_CUDA;
+  return st;
+}
+
 int ll_build_blocks(ll_ctx* ctx, const ll_map* map, const void* scan_corner, size_t nc, const void* scan_surf, size_t ns, int fmt, int where, const ll_reg_state* in,
                     int32_t* type, double* a3, double* v3, int* corner_avail, int* surf_avail) {
   if (!ctx || !map || !in) return LL_ERR_INVALID;

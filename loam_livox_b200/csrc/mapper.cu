@@ -127,6 +127,7 @@ int ll_mapper_create(ll_ctx* ctx, const ll_mapper_config* cfg, ll_mapper** out) 
   { const char* e = getenv("LL_MAPPER_TRACE"); m->trace = e && e[0] == '1'; }
   m->match_map = new ll_map(); m->match_map->device = ctx->device;   // indexed in place by every refresh (ll_map_rebuild)
   st = mapper_reserve(ctx, m);
+  if (st == LL_OK && ll_ctx_warmup(ctx) == LL_ERR_CUDA) st = LL_ERR_CUDA;   // the first registered scan of a stream is not the one that loads the kernels
   if (st != LL_OK) { ll_mapper_release(m); return st; }
   *out = m; return LL_OK;
 }

@@ -53,6 +53,10 @@ class Context:
         self.check(self._lib.ll_set_point_layout(self.h, C.byref(L)))
         self._layout_step = point_step
 
+    def warmup(self):
+        """One toy registration now: first-use costs (module loads, first cooperative launch) are paid here instead of in the first real scan."""
+        self.check(self._lib.ll_ctx_warmup(self.h))
+
     def launches(self) -> int:
         return int(self._lib.ll_launch_count(self.h))
 

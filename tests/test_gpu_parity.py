@@ -841,3 +841,27 @@ def test_gpu_reproduces_flann_vectors_and_cap_vectors(ctx):
             for stream in (0, 1, 2):
                 assert [L.ll_cap_uniform(sd, it, stream, i) for i in (0, 1, 7, 1000, 399999)] == list(g["cap_uniform"][k])
                 k += 1
+
+
+@pytest.mark.gpu
+def test_ctx_warmup_leaves_results_untouched(oracle):
+    """ll_ctx_warmup runs a toy registration (first-use costs paid up front; ll_mapper_create calls it): it must succeed on a fresh context, launch
+    kernels, and a registration afterwards must return what it returns on a context that was never warmed."""
+    from loam_livox_b200.registration import Context, Map, Point_cloud_registration
+    mc, ms, fc, fs, pose = _mk(5000, 45000, 1000, 9000)
+    guess = S.perturb_pose(pose, np.random.default_rng(3))
+    out = []
+    for warm in (True, False):
+        c = Context(0, max_scan_points=100000, max_features=100000)
+        if warm:
+            l0 = c.launches(); c.warmup(); assert c.launches() > l0 + 5
+        m = Map(c, mc, ms)
+        reg = Point_cloud_registration(c); reg.set_pose(guess.q, guess.t)
+        assert reg.find_out_incremental_transfrom(m, fc, fs) == 1
+        r = reg.result
+        out.append((r.icp_iterations, r.num_residual_blocks, tuple(r.q_w_curr), tuple(r.t_w_curr), r.final_cost))
+        m.close() if hasattr(m, "close") else None
+        c.close()
+    assert out[0] == out[1]
+    small = Context(0, max_scan_points=1000, max_features=100)   # smaller than the toy problem: a no-op, not an error
+    small.warmup(); small.close()
