@@ -33,6 +33,7 @@ class Context {
   Context(const Context&) = delete; Context& operator=(const Context&) = delete;
   ll_ctx* get() const { return ctx_; }
   void check(int st) const { if (st != LL_OK) throw Error(st, ll_last_error(ctx_)); }
+  void warmup() { check(ll_ctx_warmup(ctx_)); }   // first-use costs (module loads, first cooperative launch) now instead of in the first registration
  private:
   ll_ctx* ctx_ = nullptr;
 };
