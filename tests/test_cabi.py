@@ -33,6 +33,14 @@ def test_pod_layouts_match_the_header():
     assert (s.icp_max_iterations, s.cere_max_iterations, s.cere_prerun_times) == (15, 50, 2)        # performance_precision.yaml:25-26, :91
     assert (s.maximum_dis_line_for_match, s.maximum_dis_plane_for_match, s.huber_a) == (2.0, 50.0, 0.1)   # point_cloud_registration.hpp:64-65,220
     assert (s.inliner_dis, s.inlier_ratio, s.para_max_speed, s.para_max_angular_rate) == (0.02, 0.8, 0.3, 20.0)
+    # ll_mapper_config: the defaults written by the library must land in the ctypes fields of the same name (a shifted layout would scramble them)
+    m = capi.MapperConfig(); capi.lib().ll_mapper_config_default(C.byref(m))
+    assert C.sizeof(capi.MapperConfig) == 13 * 4 + C.sizeof(capi.PipelineCfg) + C.sizeof(capi.RegState) and capi.MapperConfig.reg.offset == 80   # 13 scalars, pipeline, reg state
+    assert (m.matching_mode, m.maximum_history_size, m.down_sample_replace, m.threshold_cell_revisit) == (0, 400, 1, 2000)   # performance_precision.yaml:28-29, laser_mapping.hpp:277
+    assert (m.reserve_map_points, m.reserve_store_points) == (1 << 22, 1 << 22)
+    assert abs(m.line_resolution - 0.1) < 1e-7 and abs(m.plane_resolution - 0.4) < 1e-7 and m.cell_resolution == 1.0 and m.maximum_in_fov_angle == 45.0
+    assert (m.pipeline.pieces, m.pipeline.whole_frame) == (3, 1) and abs(m.pipeline.mapping_leaf_surf - 0.4) < 1e-7
+    assert (m.reg.icp_max_iterations, m.reg.cere_max_iterations, m.reg.huber_a) == (15, 50, 0.1)
     c = capi.default_config()
     assert abs(c.corner_curvature - 0.1) < 1e-7 and abs(c.surface_curvature - 0.005) < 1e-9 and c.minimum_view_angle == 5.0
 
