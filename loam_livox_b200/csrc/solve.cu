@@ -440,7 +440,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) lm_solve_kernel(SolveArgs a,
       if (master && tid == 0) st->prof[15] += clock64() - t_h0;
       if (tid == 0 && s_lm.pending >= 0) lm_next_iteration(s_lm, bound, &s_pre[s_lm.pending]);
     }
-    if (tid == 0 && !s_lm.done) setup_trial<MB>(E, s_lm.trial);
+    // (volatile: the plain test was if-converted into a load of `done` by EVERY thread, which racecheck reports against thread 0's write in lm_finish --
+    // harmless, only thread 0 ever used the value, but there is no reason to keep a flagged access)
+    if (tid == 0) { if (!*(volatile int*)&s_lm.done) setup_trial<MB>(E, s_lm.trial); }
     __syncthreads();
     if (master && tid == 0) { const long long t_e4 = clock64(); st->prof[0] += t_e1 - t_e0; st->prof[1] += t_e2 - t_e1; st->prof[2] += t_e3 - t_e2; st->prof[3] += t_e4 - t_e3; st->prof[5] += 1; }
     if (s_lm.done) break;
