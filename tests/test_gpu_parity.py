@@ -865,3 +865,27 @@ def test_ctx_warmup_leaves_results_untouched(oracle):
     assert out[0] == out[1]
     small = Context(0, max_scan_points=1000, max_features=100)   # smaller than the toy problem: a no-op, not an error
     small.warmup(); small.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,window", [(0, 400), (0, 3), (1, 400)])
+def test_streaming_mapper_reproduces_the_golden_track(ctx, mode, window):
+    """The device mapper against the COMMITTED track of tests/golden/golden_stream.npz (oracle output, make_golden_stream.py; the oracle itself is pinned
+    to it by tests/test_oracle.py): counts and ICP iterations exactly, pose < 1e-6 m / 1e-6 rad (bar 1e-4) after every one of the 14 scans."""
+    import os
+    import sys
+    from loam_livox_b200 import capi
+    from loam_livox_b200.registration import Laser_mapping
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden_stream as G
+    want = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_stream.npz"))[f"track_m{mode}_w{window}"]
+    gm = Laser_mapping(ctx, reg=capi.default_reg_state(mapping_init_accumulate_frames=G.INIT), matching_mode=mode, maximum_history_size=window)
+    for k, raw in enumerate(G.scans()):
+        res, st = gm.process_new_scan(raw, 100.0 + 0.1 * k)
+        q, t, f = gm.pose()
+        w = want[k]
+        assert (res.status, f, st.n_corner, st.n_surf, st.map_corner, st.map_surf, st.appended_corner, st.appended_surf) == tuple(int(x) for x in w[:8]), k
+        assert (res.icp_iterations if res.registered else 0) == int(w[8]), k
+        dt, da = np.linalg.norm(t - w[13:16]), S.quat_angle(q, w[9:13])
+        assert dt < 1e-4 and da < 1e-4, (k, dt, da)
+        assert dt < 1e-6 and da < 1e-6, (k, dt, da)

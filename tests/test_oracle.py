@@ -6,6 +6,7 @@ in this image (scipy cKDTree, a NumPy VoxelGrid, central differences, scipy.opti
 the committed golden file (regression pin shared with the GPU tests).
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -406,3 +407,21 @@ def test_oracle_reproduces_flann_vectors_and_cap_vectors(oracle):
             for stream in (0, 1, 2):
                 assert [oracle.lib().orc_cap_uniform(sd, it, stream, i) for i in (0, 1, 7, 1000, 399999)] == list(g["cap_uniform"][k])
                 k += 1
+
+
+GOLD_STREAM = os.path.join(os.path.dirname(__file__), "golden", "golden_stream.npz")
+
+
+@pytest.mark.parametrize("mode,window", [(0, 400), (0, 3), (1, 400)])
+def test_oracle_streaming_mapper_reproduces_the_golden_track(oracle, mode, window):
+    """tests/golden/golden_stream.npz (make_golden_stream.py): the oracle's process_new_scan loop on a 14-scan sequence -- status, frame index, feature /
+    map / append counts and ICP iterations exactly, pose to 1e-9 (OpenMP reduction order) -- in both matching modes and with a window that pops."""
+    import zlib
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden_stream as G
+    g = np.load(GOLD_STREAM)
+    raws = G.scans()
+    assert [zlib.crc32(np.ascontiguousarray(r).tobytes()) for r in raws] == [int(x) for x in g["scan_crc"]], "the synthetic generator changed: regenerate the fixture"
+    got, want = G.run(mode, window, raws, threads=2), g[f"track_m{mode}_w{window}"]
+    assert np.array_equal(got[:, :9], want[:, :9])
+    assert np.abs(got[:, 9:] - want[:, 9:]).max() < 1e-9
