@@ -1,2 +1,2 @@
 #!/bin/bash
-timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "golden_track or warmup" 2>&1 | tail -5
+timeout 200 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/r2_pytest.log; tail -3 gpurun_out/r2_pytest.log
